@@ -1,0 +1,368 @@
+/*
+ * ref_harness.c - TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * A thin plain-C access layer over the UNMODIFIED reference (compiled from
+ * /root/reference/src by oracle/Makefile into oracle/_ref/bd{8,10}/libuvg266ref.so).
+ * It exists because some reference leaf functions take reference-private structs
+ * (encoder_state_t, cu_info_t) that ctypes cannot build; the wrappers below build them
+ * the way the reference's own tests do:
+ *   - strategy collection:  tests/test_strategies.c:39-65
+ *   - cu_info_t for mts:     tests/mts_tests.c:109-114
+ *   - encoder state:         uvg266.c:90 (uvg266_open) + uvg266_internal.h:50-53
+ * It is compiled against the reference headers where they lie; no reference source
+ * is copied.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <time.h>
+
+#include "global.h"
+#include "uvg266.h"
+#include "uvg266_internal.h"
+#include "encoderstate.h"
+#include "encoder.h"
+#include "cu.h"
+#include "strategyselector.h"
+#include "strategies/strategies-picture.h"
+#include "strategies/strategies-dct.h"
+#include "strategies/strategies-quant.h"
+#include "tables.h"
+
+static strategy_list_t g_list;
+static const uvg_api *g_api;
+static uvg_config *g_cfg;
+static uvg_encoder *g_enc;
+static encoder_state_t *g_state;
+
+int refh_bitdepth(void) { return UVG_BIT_DEPTH; }
+int refh_pixel_size(void) { return (int)sizeof(uvg_pixel); }
+
+/* Look up one registered implementation, e.g. ("satd_8x8", "generic"). */
+void *refh_get(const char *type, const char *strategy)
+{
+  for (unsigned i = 0; i < g_list.count; ++i) {
+    if (!strcmp(g_list.strategies[i].type, type) &&
+        !strcmp(g_list.strategies[i].strategy_name, strategy)) {
+      return g_list.strategies[i].fptr;
+    }
+  }
+  return NULL;
+}
+
+/* Point every hot-path global (uvg_reg_sad, uvg_quant, ...) at the named strategy when it
+ * has one for that type (else keep the current). Composite functions (quantize_residual)
+ * call through these globals, so "generic" makes the whole chain the C oracle. */
+int refh_use(const char *strategy)
+{
+  int n = 0;
+  for (const strategy_to_select_t *s = strategies_to_select; s->fptr; ++s) {
+    void *f = refh_get(s->strategy_type, strategy);
+    if (f) { *(s->fptr) = f; ++n; }
+  }
+  return n;
+}
+
+/* Open an encoder (64x64 dummy frame) with "key=value,key=value" options, exactly through
+ * the public API, then collect all picture/dct/quant strategies and select `generic`. */
+int refh_open(const char *opts)
+{
+  if (g_enc) { g_api->encoder_close(g_enc); g_enc = NULL; }
+  if (g_cfg) { g_api->config_destroy(g_cfg); g_cfg = NULL; }
+  g_api = uvg_api_get(UVG_BIT_DEPTH);
+  if (!g_api) return 0;
+  g_cfg = g_api->config_alloc();
+  if (!g_cfg || !g_api->config_init(g_cfg)) return 0;
+  g_cfg->width = 64; g_cfg->height = 64;
+  g_cfg->threads = 0; g_cfg->owf = 0; g_cfg->wpp = 0;
+  g_cfg->cpuid = 1;
+  char *dup = strdup(opts ? opts : "");
+  char *save = NULL; /* strtok_r: config_parse itself uses strtok for presets */
+  for (char *tok = strtok_r(dup, ",", &save); tok; tok = strtok_r(NULL, ",", &save)) {
+    char *eq = strchr(tok, '=');
+    const char *val = "true";
+    if (eq) { *eq = 0; val = eq + 1; }
+    if (!g_api->config_parse(g_cfg, tok, val)) {
+      fprintf(stderr, "refh_open: bad option %s=%s\n", tok, val);
+      free(dup);
+      return 0;
+    }
+  }
+  free(dup);
+  g_enc = g_api->encoder_open(g_cfg);
+  if (!g_enc) return 0;
+  g_state = &g_enc->states[0];
+
+  free(g_list.strategies);
+  memset(&g_list, 0, sizeof(g_list));
+  if (!uvg_strategy_register_picture(&g_list, UVG_BIT_DEPTH)) return 0;
+  if (!uvg_strategy_register_dct(&g_list, UVG_BIT_DEPTH)) return 0;
+  if (!uvg_strategy_register_quant(&g_list, UVG_BIT_DEPTH)) return 0;
+  refh_use("generic");
+  return 1;
+}
+
+void refh_set_state(int qp, int slice_is_intra)
+{
+  g_state->qp = (int8_t)qp;
+  g_state->frame->slicetype = slice_is_intra ? UVG_SLICE_I : UVG_SLICE_P;
+}
+
+static void fill_cu(cu_info_t *cu, int cu_type, int tr_idx, int lfnst_idx, int cr_lfnst_idx, int isp_mode)
+{
+  memset(cu, 0, sizeof(*cu));
+  cu->type = cu_type;          /* CU_INTRA=1, CU_INTER=2 (cu.h) */
+  cu->tr_idx = tr_idx;
+  cu->lfnst_idx = lfnst_idx;
+  cu->cr_lfnst_idx = cr_lfnst_idx;
+  cu->intra.isp_mode = isp_mode;
+}
+
+/* mts_dct / mts_idct of the named strategy. */
+int refh_mts(const char *strategy, int inverse, int bitdepth, int color, int cu_type,
+             int tr_idx, int lfnst_idx, int cr_lfnst_idx, int isp_mode, int w, int h,
+             const int16_t *in, int16_t *out, int mts_type)
+{
+  mts_dct_func *f = refh_get(inverse ? "mts_idct" : "mts_dct", strategy);
+  if (!f) return 0;
+  cu_info_t cu;
+  fill_cu(&cu, cu_type, tr_idx, lfnst_idx, cr_lfnst_idx, isp_mode);
+  f((int8_t)bitdepth, (color_t)color, &cu, (int8_t)w, (int8_t)h, in, out, (int8_t)mts_type);
+  return 1;
+}
+
+void refh_get_tr_type(int w, int h, int color, int cu_type, int tr_idx, int lfnst_idx,
+                      int cr_lfnst_idx, int isp_mode, int mts_type, int *hor, int *ver)
+{
+  cu_info_t cu;
+  fill_cu(&cu, cu_type, tr_idx, lfnst_idx, cr_lfnst_idx, isp_mode);
+  tr_type_t th, tv;
+  uvg_get_tr_type((int8_t)w, (int8_t)h, (color_t)color, &cu, &th, &tv, (int8_t)mts_type);
+  *hor = th; *ver = tv;
+}
+
+int refh_quant(const char *strategy, const int16_t *coef, int16_t *q_coef, int w, int h,
+               int color, int scan_idx, int block_type, int transform_skip, int lfnst_idx)
+{
+  quant_func *f = refh_get("quant", strategy);
+  if (!f) return 0;
+  f(g_state, (coeff_t *)coef, q_coef, w, h, (color_t)color, (int8_t)scan_idx,
+    (int8_t)block_type, (int8_t)transform_skip, (uint8_t)lfnst_idx);
+  return 1;
+}
+
+int refh_dequant(const char *strategy, const int16_t *q_coef, int16_t *coef, int w, int h,
+                 int color, int block_type, int transform_skip)
+{
+  dequant_func *f = refh_get("dequant", strategy);
+  if (!f) return 0;
+  f(g_state, (coeff_t *)q_coef, coef, w, h, (color_t)color, (int8_t)block_type,
+    (int8_t)transform_skip);
+  return 1;
+}
+
+/* quantize_residual of the named strategy; returns has_coeffs, or -1. */
+int refh_quantize_residual(const char *strategy, int cu_type, int tr_idx, int lfnst_idx,
+                           int w, int h, int color, int use_trskip, int in_stride,
+                           int out_stride, const uvg_pixel *ref_in, const uvg_pixel *pred_in,
+                           uvg_pixel *rec_out, int16_t *coeff_out, int early_skip)
+{
+  quant_residual_func *f = refh_get("quantize_residual", strategy);
+  if (!f) return -1;
+  cu_info_t cu;
+  fill_cu(&cu, cu_type, tr_idx, lfnst_idx, 0, 0);
+  return (int)f(g_state, &cu, w, h, (color_t)color, SCAN_DIAG, use_trskip, in_stride,
+                out_stride, ref_in, pred_in, rec_out, coeff_out, early_skip != 0, 0,
+                UVG_BOTH_T);
+}
+
+/* uvg_image_calc_sad on a small picture pair (frame-edge semantics, image.c:438). */
+unsigned refh_image_calc_sad(const uvg_pixel *pic_y, const uvg_pixel *ref_y, int pic_w,
+                             int pic_h, int pic_x, int pic_y0, int ref_x, int ref_y0,
+                             int bw, int bh)
+{
+  uvg_picture *pic = uvg_image_alloc(UVG_CSP_420, pic_w, pic_h);
+  uvg_picture *ref = uvg_image_alloc(UVG_CSP_420, pic_w, pic_h);
+  for (int y = 0; y < pic_h; ++y) {
+    memcpy(&pic->y[y * pic->stride], &pic_y[y * pic_w], pic_w * sizeof(uvg_pixel));
+    memcpy(&ref->y[y * ref->stride], &ref_y[y * pic_w], pic_w * sizeof(uvg_pixel));
+  }
+  unsigned r = uvg_image_calc_sad(pic, ref, pic_x, pic_y0, ref_x, ref_y0, bw, bh, NULL);
+  uvg_image_free(pic);
+  uvg_image_free(ref);
+  return r;
+}
+
+/* encoder_control->qp_map[0] (chroma QP mapping table, encoder.c:663), or NULL. */
+const int8_t *refh_chroma_qp_map(void)
+{
+  return g_state->encoder_control->qp_map[0];
+}
+
+const uint32_t *refh_scan_table(int log2_w, int log2_h)
+{
+  return uvg_get_scan_order_table(SCAN_GROUP_4X4, SCAN_DIAG, log2_w, log2_h, 0);
+}
+
+/* ------------------------------------------------------------------------------------
+ * CPU baseline: the reference's own generic (or avx2) leaf functions timed on the host,
+ * on the per-CTU all-intra hot-path workload defined in DESIGN.md ("ctu_pass").
+ * Layout of the inputs mirrors uvg266_b200's batched API so both arms see the same bytes:
+ *   rough search : for n in {8,16}: blocks[nb][n*n] originals, preds[nb][modes][n*n]
+ *   residual     : for n in {4,8,16,32}: ref[nt][n*n], pred[nt][n*n]
+ * Each worker thread takes a contiguous slice of CTUs.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int n;              /* block size */
+  int count;          /* blocks per CTU */
+  int modes;          /* prediction candidates per block (rough search only) */
+} refh_level_t;
+
+typedef struct {
+  const char *strategy;
+  int ctu_begin, ctu_end;
+  int n_rough; const refh_level_t *rough;
+  const uvg_pixel *const *rough_orig;   /* [level] -> [ctu][count][n*n] */
+  const uvg_pixel *const *rough_pred;   /* [level] -> [ctu][count][modes][n*n] */
+  uint32_t *const *rough_cost;          /* [level] -> [ctu][count][modes] */
+  int n_tu; const refh_level_t *tu;
+  const uvg_pixel *const *tu_ref;       /* [level] -> [ctu][count][n*n] */
+  const uvg_pixel *const *tu_pred;
+  uvg_pixel *const *tu_rec;
+  int16_t *const *tu_coeff;
+  uint32_t *const *tu_ssd;              /* [level] -> [ctu][count] */
+  uint32_t *const *tu_cost;             /* [level] -> [ctu][count] (fast_coeff_cost) */
+  uint64_t weights;
+} refh_job_t;
+
+static void *ctu_pass_worker(void *arg)
+{
+  refh_job_t *j = arg;
+  cu_info_t cu;
+  fill_cu(&cu, CU_INTRA, 0, 0, 0, 0);
+  quant_residual_func *qr = refh_get("quantize_residual", j->strategy);
+  pixels_calc_ssd_func *ssd = refh_get("pixels_calc_ssd", j->strategy);
+  fast_coeff_cost_func *fcc = refh_get("fast_coeff_cost", j->strategy);
+  if (!fcc) fcc = refh_get("fast_coeff_cost", "generic");
+  if (!qr) qr = refh_get("quantize_residual", "generic");
+  if (!ssd) ssd = refh_get("pixels_calc_ssd", "generic");
+  for (int l = 0; l < j->n_rough; ++l) {
+    const int n = j->rough[l].n, cnt = j->rough[l].count, modes = j->rough[l].modes;
+    char tname[32];
+    snprintf(tname, sizeof tname, "satd_%dx%d_dual", n, n);
+    cost_pixel_nxn_multi_func *satd2 = refh_get(tname, j->strategy);
+    if (!satd2) satd2 = refh_get(tname, "generic");
+    snprintf(tname, sizeof tname, "sad_%dx%d_dual", n, n);
+    cost_pixel_nxn_multi_func *sad2 = refh_get(tname, j->strategy);
+    if (!sad2) sad2 = refh_get(tname, "generic");
+    /* pred_buffer = uvg_pixel(*)[32*32]: the two candidates of a dual call live 1024 pixels
+     * apart (strategies-picture.h:48, search_intra.c:1012); copy pairs into such a buffer
+     * like the encoder's rough search does when it predicts into preds[0..1]. */
+    ALIGNED(64) uvg_pixel pb[2][32 * 32];
+    for (int c = j->ctu_begin; c < j->ctu_end; ++c) {
+      for (int b = 0; b < cnt; ++b) {
+        const size_t bi = (size_t)c * cnt + b;
+        const uvg_pixel *orig = j->rough_orig[l] + bi * n * n;
+        for (int m = 0; m < modes; m += 2) {
+          const uvg_pixel *p0 = j->rough_pred[l] + (bi * modes + m) * n * n;
+          const int m1 = (m + 1 < modes) ? m + 1 : m;
+          const uvg_pixel *p1 = j->rough_pred[l] + (bi * modes + m1) * n * n;
+          memcpy(pb[0], p0, n * n * sizeof(uvg_pixel));
+          memcpy(pb[1], p1, n * n * sizeof(uvg_pixel));
+          unsigned satd[2], sad[2];
+          satd2((const pred_buffer)pb, orig, 2, satd);
+          sad2((const pred_buffer)pb, orig, 2, sad);
+          /* get_cost_dual, search_intra.c:133-192: cost = MIN(satd, 2*sad) */
+          uint32_t *out = j->rough_cost[l] + bi * modes;
+          out[m] = MIN(satd[0], 2 * sad[0]);
+          if (m1 != m) out[m1] = MIN(satd[1], 2 * sad[1]);
+        }
+      }
+    }
+  }
+  for (int l = 0; l < j->n_tu; ++l) {
+    const int n = j->tu[l].n, cnt = j->tu[l].count;
+    for (int c = j->ctu_begin; c < j->ctu_end; ++c) {
+      for (int b = 0; b < cnt; ++b) {
+        const size_t bi = (size_t)c * cnt + b;
+        const uvg_pixel *ref = j->tu_ref[l] + bi * n * n;
+        const uvg_pixel *pred = j->tu_pred[l] + bi * n * n;
+        uvg_pixel *rec = j->tu_rec[l] + bi * n * n;
+        int16_t *coeff = j->tu_coeff[l] + bi * n * n;
+        qr(g_state, &cu, n, n, COLOR_Y, SCAN_DIAG, 0, n, n, ref, pred, rec, coeff, false, 0,
+           UVG_BOTH_T);
+        j->tu_ssd[l][bi] = ssd(ref, rec, n, n, n, n);
+        j->tu_cost[l][bi] = fcc(coeff, n, n, j->weights);
+      }
+    }
+  }
+  return NULL;
+}
+
+/* Runs the ctu_pass over `n_ctu` CTUs with `threads` pthreads; returns seconds. */
+double refh_ctu_pass(const char *strategy, int threads, int n_ctu,
+                     int n_rough, const refh_level_t *rough,
+                     const uvg_pixel *const *rough_orig, const uvg_pixel *const *rough_pred,
+                     uint32_t *const *rough_cost,
+                     int n_tu, const refh_level_t *tu,
+                     const uvg_pixel *const *tu_ref, const uvg_pixel *const *tu_pred,
+                     uvg_pixel *const *tu_rec, int16_t *const *tu_coeff,
+                     uint32_t *const *tu_ssd, uint32_t *const *tu_cost, uint64_t weights)
+{
+  if (threads < 1) threads = 1;
+  pthread_t *th = calloc(threads, sizeof(*th));
+  refh_job_t *jobs = calloc(threads, sizeof(*jobs));
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int t = 0; t < threads; ++t) {
+    refh_job_t *j = &jobs[t];
+    j->strategy = strategy;
+    j->ctu_begin = (int)((long long)n_ctu * t / threads);
+    j->ctu_end = (int)((long long)n_ctu * (t + 1) / threads);
+    j->n_rough = n_rough; j->rough = rough;
+    j->rough_orig = rough_orig; j->rough_pred = rough_pred; j->rough_cost = rough_cost;
+    j->n_tu = n_tu; j->tu = tu;
+    j->tu_ref = tu_ref; j->tu_pred = tu_pred; j->tu_rec = tu_rec; j->tu_coeff = tu_coeff;
+    j->tu_ssd = tu_ssd; j->tu_cost = tu_cost; j->weights = weights;
+    pthread_create(&th[t], NULL, ctu_pass_worker, j);
+  }
+  for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  free(th); free(jobs);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* Pair-batch micro-baseline: n_pairs dense n*n block pairs through one nxn cost function
+ * ("sad_64x64", "satd_64x64", ...), split over threads; returns seconds. */
+typedef struct {
+  cost_pixel_nxn_func *f; const uvg_pixel *a, *b; uint32_t *out; size_t begin, end; int nn;
+} pair_job_t;
+
+static void *pair_worker(void *arg)
+{
+  pair_job_t *j = arg;
+  for (size_t i = j->begin; i < j->end; ++i)
+    j->out[i] = j->f(j->a + i * j->nn, j->b + i * j->nn);
+  return NULL;
+}
+
+double refh_pair_batch(const char *type, const char *strategy, int threads, int n,
+                       size_t n_pairs, const uvg_pixel *a, const uvg_pixel *b, uint32_t *out)
+{
+  cost_pixel_nxn_func *f = refh_get(type, strategy);
+  if (!f) return -1.0;
+  if (threads < 1) threads = 1;
+  pthread_t *th = calloc(threads, sizeof(*th));
+  pair_job_t *jobs = calloc(threads, sizeof(*jobs));
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int t = 0; t < threads; ++t) {
+    jobs[t] = (pair_job_t){ f, a, b, out, n_pairs * t / threads, n_pairs * (t + 1) / threads, n * n };
+    pthread_create(&th[t], NULL, pair_worker, &jobs[t]);
+  }
+  for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  free(th); free(jobs);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
