@@ -1,0 +1,509 @@
+#!/usr/bin/env python
+"""bench.py - CTUs/s of the uvg266 all-intra hot path (distortion + transform + quant) on
+B200, next to the reference's own CPU implementation of the same path.
+
+Workload ("ctu_pass", defined in DESIGN.md section 4): one step = one 3840x2160 8-bit frame
+= 2040 CTUs; per CTU the op mix the reference encoder itself executes for all-intra
+ultrafast (gprof call counts):
+  rough search : 64 8x8 blocks x 23 candidate modes + 16 16x16 blocks x 24 modes, each
+                 scored min(SATD, 2*SAD)              (satd_NxN_dual + sad_NxN_dual)
+  residual path: 240 4x4 + 120 8x8 + 24 16x16 + 5 32x32 TUs through the fused
+                 residual->DCT->quant->dequant->IDCT->recon (quantize_residual), each
+                 followed by pixels_calc_ssd and fast_coeff_cost
+Inputs are synthetic (seeded); predictions are the source plus seeded noise, since intra
+prediction itself is outside the path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]      -> one JSON line (rank 0)
+  python bench.py --impl reference ...                      -> reference CPU arm
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FRAME_W, FRAME_H = 3840, 2160
+CTU = 64
+CTU_COLS, CTU_ROWS = FRAME_W // CTU, (FRAME_H + CTU - 1) // CTU      # 60 x 34 = 2040
+ROUGH = [(8, 64, 23), (16, 16, 24)]            # (n, blocks per CTU, candidate modes)
+TUS = [(4, 240), (8, 120), (16, 24), (32, 5)]  # (n, TUs per CTU)
+QP = 27
+COST_WEIGHTS = (28 << 0) | (300 << 16) | (700 << 32) | (1100 << 48)   # Q8.8 weights, fast_coeff_cost
+METRIC = "CTUs/s at 3840x2160 8-bit all-intra hot path (distortion+transform+quant)"
+
+
+def bytes_per_ctu():
+    """Algorithmic bytes (8-bit): SURVEY.md 8(d). rough: orig + k preds + 4k out per block;
+    fused quantize_residual: (3s+2)*w*h + has/ssd/cost."""
+    rough = {n: cnt * ((1 + k) * n * n + 4 * k) for (n, cnt, k) in ROUGH}
+    tus = {n: cnt * (5 * n * n + 9) for (n, cnt) in TUS}
+    return rough, tus
+
+
+def rank_rows(rank, world):
+    """CTU rows of the (virtual) plane this rank owns: band (rank+f) % world of frame f, for
+    the `world` frames of one step -> every rank owns exactly one frame's worth of rows."""
+    rows = []
+    for f in range(world):
+        b = (rank + f) % world
+        lo, hi = CTU_ROWS * b // world, CTU_ROWS * (b + 1) // world
+        rows += [(f, r) for r in range(lo, hi)]
+    return rows
+
+
+def synth_plane_rows(rows, seed=1234):
+    """Luma rows of the synthetic source (sin/cos texture + Gaussian noise sigma 6, seeded per
+    frame and CTU row), padded to whole CTUs: uint8 [len(rows)*64, 3840]."""
+    out = np.empty((len(rows) * CTU, FRAME_W), np.uint8)
+    x = np.arange(FRAME_W, dtype=np.float32)[None, :]
+    for i, (f, r) in enumerate(rows):
+        y = (np.arange(CTU, dtype=np.float32) + r * CTU)[:, None]
+        base = 128 + 60 * np.sin(x * 0.013 + f) * np.cos(y * 0.011) + 40 * np.sin((x + y) * 0.047)
+        rng = np.random.default_rng([seed, f, r])
+        out[i * CTU:(i + 1) * CTU] = np.clip(base + rng.normal(0, 6, base.shape), 0, 255).astype(np.uint8)
+    return out
+
+
+def gather_blocks(plane, n, per_ctu):
+    """`per_ctu` n*n blocks (raster order inside the CTU, wrapping) of every CTU, dense."""
+    H, W = plane.shape
+    rows, cols = H // CTU, W // CTU
+    b = plane.reshape(rows, CTU // n, n, cols, CTU // n, n).transpose(0, 3, 1, 4, 2, 5)
+    b = b.reshape(rows * cols, (CTU // n) ** 2, n * n)
+    # the encoder revisits positions (RDO re-evaluations, chroma): counts may exceed the
+    # number of distinct positions, so wrap around
+    idx = np.arange(per_ctu) % b.shape[1]
+    return np.ascontiguousarray(b[:, idx]).reshape(-1)
+
+
+def noisy(a, rng, amp):
+    return np.clip(a.astype(np.int16) + rng.integers(-amp, amp + 1, a.shape, dtype=np.int16), 0, 255).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference CPU arm (oracle/_ref: the unmodified reference's generic C strategies)
+# ------------------------------------------------------------------------------------------
+class RefLevel(C.Structure):
+    _fields_ = [("n", C.c_int), ("count", C.c_int), ("modes", C.c_int)]
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuArm:
+    """Runs the ctu_pass on `n_ctu` CTUs with the reference's own leaf functions."""
+
+    def __init__(self, n_ctu, strategy=b"generic"):
+        from _libs import load_ref, ref_available
+        self.kind = "reference"
+        if not ref_available(8):
+            raise RuntimeError("oracle/_ref/bd8 is missing (build it with `make -C oracle ref` where "
+                               "/root/reference exists)")
+        self.R = load_ref(8, "preset=ultrafast,qp=%d,signhide=0,rdoq=0" % QP)
+        self.R.H.refh_set_state(QP, 1)
+        self.strategy = strategy
+        self.n_ctu = n_ctu
+        rows = [(0, r) for r in range((n_ctu + CTU_COLS - 1) // CTU_COLS)]
+        plane = synth_plane_rows(rows)
+        rng = np.random.default_rng(99)
+        self.keep = []
+        self.rough = (RefLevel * len(ROUGH))(*[RefLevel(n, c, k) for (n, c, k) in ROUGH])
+        self.tu = (RefLevel * len(TUS))(*[RefLevel(n, c, 0) for (n, c) in TUS])
+        ro, rp, rc = [], [], []
+        for (n, cnt, k) in ROUGH:
+            o = gather_blocks(plane, n, cnt)[: n_ctu * cnt * n * n]
+            p = noisy(np.repeat(o.reshape(-1, 1, n * n), k, 1), rng, 24).ravel()
+            c = np.zeros(n_ctu * cnt * k, np.uint32)
+            ro.append(o); rp.append(p); rc.append(c)
+        tr, tp, trec, tco, tss, tcs = [], [], [], [], [], []
+        for (n, cnt) in TUS:
+            r = gather_blocks(plane, n, cnt)[: n_ctu * cnt * n * n]
+            p = noisy(r, rng, 24)
+            tr.append(r); tp.append(p); trec.append(np.zeros_like(r))
+            tco.append(np.zeros(r.size, np.int16)); tss.append(np.zeros(n_ctu * cnt, np.uint32))
+            tcs.append(np.zeros(n_ctu * cnt, np.uint32))
+        self.arrays = dict(ro=ro, rp=rp, rc=rc, tr=tr, tp=tp, trec=trec, tco=tco, tss=tss, tcs=tcs)
+
+        def parr(lst):
+            a = (C.c_void_p * len(lst))(*[x.ctypes.data for x in lst])
+            self.keep.append(a)
+            return a
+        self.args = [parr(ro), parr(rp), parr(rc)], [parr(tr), parr(tp), parr(trec), parr(tco), parr(tss), parr(tcs)]
+        self.R.H.refh_ctu_pass.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+
+    def run(self, threads):
+        (ro, rp, rc), (tr, tp, trec, tco, tss, tcs) = self.args
+        return self.R.H.refh_ctu_pass(self.strategy, threads, self.n_ctu, len(ROUGH), self.rough, ro, rp, rc,
+                                      len(TUS), self.tu, tr, tp, trec, tco, tss, tcs, COST_WEIGHTS)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    n_ctu = args.ref_ctus
+    arm = CpuArm(n_ctu)
+    for _ in range(max(1, min(args.warmup, 2))):
+        arm.run(cores)
+    t = [arm.run(cores) for _ in range(args.steps)]
+    total = sum(t)
+    v = n_ctu * args.steps / total
+    line = {
+        "metric": METRIC, "value": v, "unit": "CTU/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "ctu_pass 3840x2160 8-bit all-intra (per-CTU op mix of uvg266 ultrafast)",
+                   "sample_ctus_per_step": n_ctu, "qp": QP},
+        "cpu_baseline": {"value": v, "unit": "CTU/s", "cores": cores, "kind": arm.kind,
+                         "sample": "%d CTUs per step x %d steps, generic-C strategies of the unmodified "
+                                   "reference (oracle/_ref), %d pthreads" % (n_ctu, args.steps, cores)},
+        "e2e": {"value": v, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import uvg266_b200 as U
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the uvg266_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    U.init(local_rank)
+    L = U.lib()
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- inputs: this rank's bands of the `world` frames of a step ----
+    rows = rank_rows(rank, world)
+    plane_h = synth_plane_rows(rows)
+    n_ctu = len(rows) * CTU_COLS
+    rng = np.random.default_rng(99 + rank)
+    plane = torch.from_numpy(plane_h).to(dev)
+    cfg = U.QuantCfg.make(QP, 8, 1, 0, 0)
+
+    rough = []
+    for (n, cnt, k) in ROUGH:
+        assert cnt == (CTU // n) ** 2
+        nb = n_ctu * cnt
+        o_h = gather_blocks(plane_h, n, cnt)
+        o = torch.from_numpy(o_h).to(dev)
+        p = torch.from_numpy(o_h).to(dev).view(nb, 1, n * n).expand(nb, k, n * n).to(torch.int16)
+        p = (p + torch.randint(-24, 25, p.shape, device=dev, dtype=torch.int16)).clamp_(0, 255).to(torch.uint8).contiguous()
+        out = torch.zeros(nb * k, dtype=torch.int32, device=dev)
+        rough.append(dict(n=n, k=k, nb=nb, o=o, p=p, out=out, A=U.Blocks.dense(o.data_ptr(), n, n),
+                          B=U.Blocks.dense(p.data_ptr(), n, n),
+                          bytes=nb * ((1 + k) * n * n + 4 * k)))
+    tus = []
+    for (n, cnt) in TUS:
+        nt = n_ctu * cnt
+        r_h = gather_blocks(plane_h, n, cnt)
+        r = torch.from_numpy(r_h).to(dev)
+        p = (r.to(torch.int16) + torch.randint(-24, 25, r.shape, device=dev, dtype=torch.int16)).clamp_(0, 255).to(torch.uint8)
+        rec = torch.zeros_like(r)
+        coeff = torch.zeros(nt * n * n, dtype=torch.int16, device=dev)
+        has = torch.zeros(nt, dtype=torch.uint8, device=dev)
+        ssd = torch.zeros(nt, dtype=torch.int32, device=dev); cost = torch.zeros(nt, dtype=torch.int32, device=dev)
+        tus.append(dict(n=n, nt=nt, r=r, p=p, rec=rec, coeff=coeff, has=has, ssd=ssd, cost=cost,
+                        R=U.Blocks.dense(r.data_ptr(), n, n), P=U.Blocks.dense(p.data_ptr(), n, n),
+                        O=U.Blocks.dense(rec.data_ptr(), n, n), bytes=nt * (5 * n * n + 9)))
+    step_bytes = sum(x["bytes"] for x in rough) + sum(x["bytes"] for x in tus)
+
+    def step(ev=None):
+        for i, x in enumerate(rough):
+            if ev is not None and i == 0:
+                ev[0].record()
+            U.check(L.uvg_b200_rough_cost_dev(8, x["n"], C.byref(x["A"]), C.byref(x["B"]), x["out"].data_ptr(),
+                                              x["nb"], x["k"], stream))
+            if ev is not None and i == 0:
+                ev[1].record()
+        for x in tus:
+            U.check(L.uvg_b200_quantize_residual_dev(C.byref(cfg), 1, 0, x["n"], x["n"], 0, 0, 0, C.byref(x["R"]),
+                                                     C.byref(x["P"]), C.byref(x["O"]), x["coeff"].data_ptr(),
+                                                     x["has"].data_ptr(), x["ssd"].data_ptr(), x["cost"].data_ptr(),
+                                                     COST_WEIGHTS, x["nt"], stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    # timed region: exactly K steps; the dominant kernel (rough cost 8x8) is bracketed by its own
+    # events inside the same region
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.uvg_b200_launch_count()
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        step(kev[s])
+    e1.record()
+    barrier()
+    launches = L.uvg_b200_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_ctus = n_ctu * world * args.steps
+    value = total_ctus / (ms_max * 1e-3)
+
+    # ---- per-kernel breakdown + the 64x64 SAD/SATD pair kernels (north_star's GB/s metric) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = rough[0]
+    achieved = dom["bytes"] / (kms * 1e-3) / 1e9
+    roofline = {"kernel": "rough_cost_kernel<u8> n=8 k=23", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": dom["bytes"], "ms_per_launch": kms}
+    extra = {}
+    if rank == 0:
+        extra["kernels"] = kernel_breakdown(torch, U, L, rough, tus, cfg, stream, hbm_peak)
+        extra["pairs_64x64"] = pair_bench(torch, U, L, dev, stream, hbm_peak)
+
+    # ---- e2e: the same step through the host-buffer C-ABI entry points (pinned host memory) ----
+    e2e = e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, dev)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            arm = CpuArm(args.cpu_ctus)
+            cores = host_cores()
+            arm.run(cores)
+            secs = min(arm.run(cores) for _ in range(3))
+            cpu_baseline = {"value": arm.n_ctu / secs, "unit": "CTU/s", "cores": cores, "kind": arm.kind,
+                            "sample": "%d CTUs of the same workload, best of 3, generic-C strategies of the "
+                                      "unmodified reference (oracle/_ref), %d pthreads" % (arm.n_ctu, cores)}
+            s1 = arm.run(1)
+            cpu_baseline["value_1thread"] = arm.n_ctu / s1
+        except Exception as exc:  # reported, never silently replaced
+            cpu_baseline = {"value": None, "unit": "CTU/s", "cores": host_cores(), "kind": "reference",
+                            "sample": "unavailable: %s" % exc}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "CTU/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "ctu_pass 3840x2160 8-bit all-intra (per-CTU op mix of uvg266 ultrafast): "
+                                   "rough 64x(8x8,23 modes)+16x(16x16,24 modes); TUs 240x4x4+120x8x8+24x16x16+5x32x32",
+                       "ctus_per_step_per_gpu": n_ctu, "qp": QP, "sharding": "CTU-row bands, no collective",
+                       "l2": "inputs %.0f MB per step >> 126 MB L2, no flush" % (step_bytes / 1e6),
+                       "algorithmic_bytes_per_step": step_bytes},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "step_gbps": step_bytes * args.steps / (ms_max * 1e-3) / 1e9,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _time(torch, fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def kernel_breakdown(torch, U, L, rough, tus, cfg, stream, hbm_peak):
+    out = []
+    for x in rough:
+        ms = _time(torch, lambda: U.check(L.uvg_b200_rough_cost_dev(8, x["n"], C.byref(x["A"]), C.byref(x["B"]),
+                                                                    x["out"].data_ptr(), x["nb"], x["k"], stream)))
+        out.append({"kernel": "rough_cost n=%d k=%d" % (x["n"], x["k"]), "ms": ms, "bytes": x["bytes"],
+                    "gbps": x["bytes"] / ms / 1e6, "frac": x["bytes"] / ms / 1e6 / hbm_peak})
+    for x in tus:
+        ms = _time(torch, lambda: U.check(L.uvg_b200_quantize_residual_dev(
+            C.byref(cfg), 1, 0, x["n"], x["n"], 0, 0, 0, C.byref(x["R"]), C.byref(x["P"]), C.byref(x["O"]),
+            x["coeff"].data_ptr(), x["has"].data_ptr(), x["ssd"].data_ptr(), x["cost"].data_ptr(), COST_WEIGHTS,
+            x["nt"], stream)))
+        macs = x["nt"] * 4 * x["n"] ** 3
+        out.append({"kernel": "quantize_residual %dx%d" % (x["n"], x["n"]), "ms": ms, "bytes": x["bytes"],
+                    "gbps": x["bytes"] / ms / 1e6, "frac": x["bytes"] / ms / 1e6 / hbm_peak,
+                    "gmacs": macs / ms / 1e6})
+    return out
+
+
+def pair_bench(torch, U, L, dev, stream, hbm_peak):
+    """N = 2^17 independent 64x64 uint8 block pairs (1 GiB read, >> L2): the north_star's
+    'SAD/SATD GB/s vs HBM roofline at 64x64' figure. Algorithmic bytes = 2*64*64 + 4 per pair."""
+    n, N = 64, 1 << 17
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    a = torch.randint(0, 256, (N * n * n,), dtype=torch.uint8, device=dev, generator=g)
+    b = torch.randint(0, 256, (N * n * n,), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.zeros(N, dtype=torch.int32, device=dev)
+    A, B = U.Blocks.dense(a.data_ptr(), n, n), U.Blocks.dense(b.data_ptr(), n, n)
+    res = {}
+    for name, metric in (("sad", U.SAD_NXN), ("satd", U.SATD), ("ssd", U.SSD)):
+        ms = _time(torch, lambda: U.check(L.uvg_b200_distortion_dev(metric, 8, n, n, C.byref(A), C.byref(B),
+                                                                    out.data_ptr(), N, 1, stream)), iters=10)
+        nbytes = N * (2 * n * n + 4)
+        res[name] = {"ms": ms, "gbps": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / hbm_peak, "pairs": N}
+    return res
+
+
+def e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, dev):
+    """Same step through uvg_b200_*_host (host pointers): every step copies the inputs
+    host->device from pinned memory and the results device->host, inside the timed region."""
+    def pinned(t):
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h
+    hr = []
+    for x in rough:
+        o, p = pinned(x["o"]), pinned(x["p"])
+        out = torch.empty(x["nb"] * x["k"], dtype=torch.int32, pin_memory=True)
+        hr.append(dict(n=x["n"], k=x["k"], nb=x["nb"], o=o, p=p, out=out, A=U.Blocks.dense(o.data_ptr(), x["n"], x["n"]),
+                       B=U.Blocks.dense(p.data_ptr(), x["n"], x["n"])))
+    ht = []
+    for x in tus:
+        r, p = pinned(x["r"]), pinned(x["p"])
+        rec = torch.empty_like(r).pin_memory()
+        coeff = torch.empty(x["nt"] * x["n"] ** 2, dtype=torch.int16, pin_memory=True)
+        has = torch.empty(x["nt"], dtype=torch.uint8, pin_memory=True)
+        ssd = torch.empty(x["nt"], dtype=torch.int32, pin_memory=True); cost = torch.empty(x["nt"], dtype=torch.int32, pin_memory=True)
+        ht.append(dict(n=x["n"], nt=x["nt"], r=r, p=p, rec=rec, coeff=coeff, has=has, ssd=ssd, cost=cost,
+                       R=U.Blocks.dense(r.data_ptr(), x["n"], x["n"]), P=U.Blocks.dense(p.data_ptr(), x["n"], x["n"]),
+                       O=U.Blocks.dense(rec.data_ptr(), x["n"], x["n"])))
+    h2d = sum(x["o"].numel() + x["p"].numel() for x in hr) + sum(x["r"].numel() + x["p"].numel() for x in ht)
+    d2h = sum(x["out"].numel() * 4 for x in hr) + sum(x["rec"].numel() + x["coeff"].numel() * 2 + x["nt"] * 9 for x in ht)
+
+    def step():
+        for x in hr:
+            U.check(L.uvg_b200_rough_cost_host(8, x["n"], C.byref(x["A"]), x["o"].numel(), C.byref(x["B"]),
+                                               x["p"].numel(), x["out"].data_ptr(), x["nb"], x["k"]))
+        for x in ht:
+            U.check(L.uvg_b200_quantize_residual_host(C.byref(cfg), 1, 0, x["n"], x["n"], 0, 0, 0, C.byref(x["R"]),
+                                                      x["r"].numel(), C.byref(x["P"]), x["p"].numel(), C.byref(x["O"]),
+                                                      x["rec"].numel(), x["coeff"].data_ptr(), x["has"].data_ptr(),
+                                                      x["ssd"].data_ptr(), x["cost"].data_ptr(), COST_WEIGHTS, x["nt"]))
+    k = max(3, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    barrier()
+    secs = time.perf_counter() - t0
+    t = torch.tensor([secs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    return {"value": n_ctu * world * k / secs, "unit": "CTU/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": k, "ms_per_step": 1e3 * secs / k,
+            "api": "uvg_b200_rough_cost_host + uvg_b200_quantize_residual_host (pinned host buffers)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-ctus", type=int, default=480, help="CTUs per step of the reference arm")
+    ap.add_argument("--cpu-ctus", type=int, default=960, help="CTUs of the cpu_baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,317 @@
+/*
+ * uvg266_b200.h - C ABI of libuvg266_b200.so: B200 (sm_100a) implementation of uvg266's
+ * block-distortion + transform + quant hot path.
+ *
+ * Three layers, all plain C (pointers + sizes, no CUDA/torch types in any signature):
+ *
+ *  (1) DROP-IN leaf functions with exactly the reference's strategy signatures
+ *      (host pointers, synchronous, re-entrant from any number of encoder threads). These
+ *      are what uvg266's strategyselector table binds; see INTEGRATION.md for the
+ *      registration glue (uvg266_b200/glue/strategies_cuda.c).
+ *        strategies-picture.h:115-157   reg_sad, sad/satd NxN (+dual), satd_any_size(+quad,
+ *                                       +vtm), pixels_calc_ssd, ver_sad, hor_sad,
+ *                                       generate_residual, get_optimized_sad
+ *        strategies-dct.h:44,63-83      dct/idct NxN, fast dst 4x4, mts_dct, mts_idct
+ *        strategies-quant.h:48-91       quant, dequant, quantize_residual, coeff_abs_sum,
+ *                                       fast_coeff_cost
+ *      Reference-private structs (encoder_state_t, cu_info_t) do not cross this ABI: the
+ *      glue flattens them into uvg_b200_quant_cfg / plain ints.
+ *
+ *  (2) BATCHED DEVICE entry points (`*_dev`): device pointers, asynchronous on a caller
+ *      stream. One launch evaluates thousands of blocks / TUs; this is the path the
+ *      roofline numbers are measured on.
+ *
+ *  (3) BATCHED HOST entry points (`*_host`): same work from host buffers; H2D, kernels and
+ *      D2H are issued inside the call (the end-to-end number of bench.py).
+ *
+ * Pixel type follows the reference's compile-time UVG_BIT_DEPTH (uvg266.h:89-97): every
+ * function taking pixels has a `bitdepth` argument (8 -> uint8_t pixels, 9..16 ->
+ * uint16_t pixels); the drop-in layer is instantiated per bit depth by the glue.
+ *
+ * All results are bit-exact with the reference's generic-C strategies.
+ * Errors: functions returning int return 0 on success, non-zero on failure
+ * (uvg_b200_last_error() has the text). Leaf drop-ins have no error channel
+ * (strategies-*.h): a device failure after init aborts the process with a message -
+ * there is NO CPU fallback anywhere in this library.
+ */
+#ifndef UVG266_B200_H_
+#define UVG266_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UVG_B200_API __attribute__((visibility("default")))
+
+/* ---------------------------------------------------------------------------------- */
+/* Library / device                                                                    */
+/* ---------------------------------------------------------------------------------- */
+UVG_B200_API int uvg_b200_init(int device);           /* idempotent; selects the device  */
+UVG_B200_API int uvg_b200_device_count(void);         /* 0 when no CUDA device/driver     */
+UVG_B200_API const char *uvg_b200_last_error(void);
+UVG_B200_API const char *uvg_b200_version(void);
+UVG_B200_API int uvg_b200_sm_count(void);
+/* Kernel launches issued by this library since load (all threads). bench.py reads it to
+ * report gpu_launches. */
+UVG_B200_API uint64_t uvg_b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------- */
+/* Block addressing for the batched entry points                                       */
+/* ---------------------------------------------------------------------------------- */
+/* Block i of an operand starts at pixel offset
+ *     (i / blocks_per_row) * row_pitch + (i % blocks_per_row) * col_pitch
+ * from `base`, and its rows are `stride` pixels apart. Two common instances:
+ *   dense array of w*h blocks : stride = w, blocks_per_row = 1, row_pitch = w*h
+ *   tiling of a picture plane : stride = plane stride, blocks_per_row = plane_w / w,
+ *                               col_pitch = w, row_pitch = h * plane stride
+ * `base` is a device pointer for *_dev functions and a host pointer for *_host ones. */
+typedef struct uvg_b200_blocks {
+  const void *base;
+  uint32_t stride;
+  uint32_t blocks_per_row;
+  uint64_t col_pitch;
+  uint64_t row_pitch;
+} uvg_b200_blocks;
+
+/* Distortion metric selector for the batched picture kernels. */
+enum uvg_b200_metric {
+  UVG_B200_SAD = 0,       /* reg_sad: sum|a-b|, no shift                    (picture-generic.c:99)   */
+  UVG_B200_SAD_NXN = 1,   /* sad_NxN: sum|a-b| >> (bitdepth-8)              (:1054)                  */
+  UVG_B200_SATD = 2,      /* satd_any_size / satd_NxN (N>=8): 8x8 + 4x4 Hadamards, >> (bitdepth-8)   */
+  UVG_B200_SATD_4X4 = 3,  /* satd_4x4: one 4x4 Hadamard, no shift           (:205)                   */
+  UVG_B200_SATD_VTM = 4,  /* satd_any_size_vtm (xGetHADs)                   (:949)                   */
+  UVG_B200_SSD = 5,       /* pixels_calc_ssd: sum (a-b)^2 >> 2*(bitdepth-8) (:1115)                  */
+  UVG_B200_SATD_QUAD = 6  /* per-candidate satd_any_size_quad semantics     (:412)                   */
+};
+
+/* ---------------------------------------------------------------------------------- */
+/* (2) Batched device entry points                                                     */
+/* ---------------------------------------------------------------------------------- */
+/* out[i*k + c] = metric(block i of `a`, block (i*k + c) of `b`), i < n_blocks, c < k.
+ * k = 1: independent pairs. k = 2 / 4: the reference's *_dual / *_quad shape. k = number
+ * of intra modes: one original scored against all candidate predictions in one launch. */
+UVG_B200_API int uvg_b200_distortion_dev(int metric, int bitdepth, int w, int h,
+                                         const uvg_b200_blocks *a, const uvg_b200_blocks *b,
+                                         uint32_t *out, size_t n_blocks, int k, void *stream);
+
+/* Intra rough-search cost, search_intra.c:133-192 (get_cost_dual):
+ * out[i*k + c] = min(satd, 2*sad) of square n*n blocks (satd_NxN_dual + sad_NxN_dual). */
+UVG_B200_API int uvg_b200_rough_cost_dev(int bitdepth, int n, const uvg_b200_blocks *orig,
+                                         const uvg_b200_blocks *preds, uint32_t *out,
+                                         size_t n_blocks, int k, void *stream);
+
+/* Motion-search SAD (search_inter.c:204-247 check_mv_cost -> image.c:438
+ * uvg_image_calc_sad): for block j of the current picture (top-left cur_x[j], cur_y[j],
+ * size w*h) and every integer displacement (dx,dy) in [-range,range]^2 around
+ * (mv_x[j], mv_y[j]), out[j*(2r+1)^2 + (dy+r)*(2r+1) + (dx+r)] = SAD >> (bitdepth-8)
+ * against the reference picture with frame-edge replication (ver/hor/cor_sad). */
+UVG_B200_API int uvg_b200_sad_search_dev(int bitdepth, int w, int h,
+                                         const void *cur, const void *ref, int pic_w, int pic_h,
+                                         int stride, const int32_t *cur_x, const int32_t *cur_y,
+                                         const int32_t *mv_x, const int32_t *mv_y, int range,
+                                         uint32_t *out, size_t n_blocks, void *stream);
+
+/* residual[i][y*w+x] = a - b (int16, dense), generate_residual (picture-generic.c:1360). */
+UVG_B200_API int uvg_b200_residual_dev(int bitdepth, int w, int h, const uvg_b200_blocks *ref,
+                                       const uvg_b200_blocks *pred, int16_t *residual,
+                                       size_t n_blocks, void *stream);
+
+/* Transform types, tr_type_t (uvg266.h:234). */
+enum { UVG_B200_DCT2 = 0, UVG_B200_DCT8 = 1, UVG_B200_DST7 = 2 };
+
+/* 2-D separable transform of n_tus dense w*h int16 blocks (mts_dct_generic /
+ * mts_idct_generic, dct-generic.c:2560-2678, and dct_NxN/idct_NxN :720-740 which are the
+ * DCT2/DCT2 instance). skip_w/skip_h: zero-out widths as derived by the reference
+ * (:2582-2600). inverse = 0 forward, 1 inverse. */
+UVG_B200_API int uvg_b200_transform_dev(int inverse, int bitdepth, int w, int h, int type_hor,
+                                        int type_ver, int skip_w, int skip_h, const int16_t *in,
+                                        int16_t *out, size_t n_tus, void *stream);
+
+/* Quantiser configuration: the fields uvg_quant_generic / uvg_dequant_generic /
+ * uvg_quantize_residual_generic read through encoder_state_t (last row). */
+typedef struct uvg_b200_quant_cfg {
+  int32_t qp;            /* state->qp                                                  */
+  int32_t bitdepth;      /* encoder_control->bitdepth                                  */
+  int32_t slice_intra;   /* state->frame->slicetype == UVG_SLICE_I                     */
+  int32_t signhide;      /* cfg.signhide_enable                                        */
+  int32_t mts;           /* cfg.mts (enum uvg_mts): selects mts_dct in uvg_transform2d */
+  int32_t reserved;
+  int8_t chroma_qp_map[128]; /* encoder_control->qp_map[0][qp] for qp 0..127 (entry =   */
+  int32_t has_chroma_qp_map; /*   mapped qp), valid when has_chroma_qp_map != 0        */
+} uvg_b200_quant_cfg;
+
+/* q_coef = quant(coef) for n_tus dense w*h blocks (uvg_quant_generic, flat lists). */
+UVG_B200_API int uvg_b200_quant_dev(const uvg_b200_quant_cfg *cfg, const int16_t *coef,
+                                    int16_t *q_coef, int w, int h, int color,
+                                    int transform_skip, int lfnst_idx, size_t n_tus,
+                                    void *stream);
+UVG_B200_API int uvg_b200_dequant_dev(const uvg_b200_quant_cfg *cfg, const int16_t *q_coef,
+                                      int16_t *coef, int w, int h, int color,
+                                      int transform_skip, size_t n_tus, void *stream);
+
+/* The fused op of the path (uvg_quantize_residual_generic, quant-generic.c:460-612), one
+ * launch for n_tus TUs of one shape:
+ *   residual = ref - pred -> forward transform -> quant -> has_coeffs
+ *   -> dequant -> inverse transform -> rec = clip(residual' + pred)   (rec = pred if none)
+ * plus what the caller computes on the result right after (search.c:438, rdo.c:440):
+ *   ssd[i]  = pixels_calc_ssd(ref, rec)            (may be NULL)
+ *   cost[i] = fast_coeff_cost(coeff, weights)      (may be NULL)
+ * coeff_out: dense int16 [n_tus][w*h]; has_coeffs: uint8 [n_tus]. rec may alias pred. */
+UVG_B200_API int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, int cu_type,
+                                                int tr_idx, int w, int h, int color,
+                                                int use_trskip, int early_skip,
+                                                const uvg_b200_blocks *ref,
+                                                const uvg_b200_blocks *pred,
+                                                const uvg_b200_blocks *rec,
+                                                int16_t *coeff_out, uint8_t *has_coeffs,
+                                                uint32_t *ssd, uint32_t *cost,
+                                                uint64_t cost_weights, size_t n_tus,
+                                                void *stream);
+
+/* coeff_abs_sum / fast_coeff_cost over n_tus dense blocks of `len` coefficients. */
+UVG_B200_API int uvg_b200_coeff_abs_sum_dev(const int16_t *coeffs, size_t len, uint32_t *out,
+                                            size_t n_tus, void *stream);
+UVG_B200_API int uvg_b200_fast_coeff_cost_dev(const int16_t *coeffs, int w, int h,
+                                              uint64_t weights, uint32_t *out, size_t n_tus,
+                                              void *stream);
+
+/* ---------------------------------------------------------------------------------- */
+/* (3) Batched host entry points (H2D + kernels + D2H inside the call, synchronous)    */
+/* ---------------------------------------------------------------------------------- */
+UVG_B200_API int uvg_b200_distortion_host(int metric, int bitdepth, int w, int h,
+                                          const uvg_b200_blocks *a, size_t a_bytes,
+                                          const uvg_b200_blocks *b, size_t b_bytes,
+                                          uint32_t *out, size_t n_blocks, int k);
+UVG_B200_API int uvg_b200_rough_cost_host(int bitdepth, int n, const uvg_b200_blocks *orig,
+                                          size_t orig_bytes, const uvg_b200_blocks *preds,
+                                          size_t preds_bytes, uint32_t *out, size_t n_blocks,
+                                          int k);
+UVG_B200_API int uvg_b200_transform_host(int inverse, int bitdepth, int w, int h, int type_hor,
+                                         int type_ver, int skip_w, int skip_h,
+                                         const int16_t *in, int16_t *out, size_t n_tus);
+UVG_B200_API int uvg_b200_quantize_residual_host(const uvg_b200_quant_cfg *cfg, int cu_type,
+                                                 int tr_idx, int w, int h, int color,
+                                                 int use_trskip, int early_skip,
+                                                 const uvg_b200_blocks *ref, size_t ref_bytes,
+                                                 const uvg_b200_blocks *pred, size_t pred_bytes,
+                                                 const uvg_b200_blocks *rec, size_t rec_bytes,
+                                                 int16_t *coeff_out, uint8_t *has_coeffs,
+                                                 uint32_t *ssd, uint32_t *cost,
+                                                 uint64_t cost_weights, size_t n_tus);
+
+/* Pinned host memory for callers that want the fast H2D path (optional). */
+UVG_B200_API void *uvg_b200_host_alloc(size_t bytes);
+UVG_B200_API void uvg_b200_host_free(void *p);
+
+/* ---------------------------------------------------------------------------------- */
+/* (1) Drop-in leaf functions (host pointers). `_8` = uint8_t pixels (UVG_BIT_DEPTH 8), */
+/*     `_16` = uint16_t pixels (UVG_BIT_DEPTH 10); bitdepth for the _16 set is fixed by */
+/*     uvg_b200_set_dropin_bitdepth (default 10).                                       */
+/* ---------------------------------------------------------------------------------- */
+UVG_B200_API void uvg_b200_set_dropin_bitdepth(int bitdepth);
+
+#define UVG_B200_DECL_PICTURE(SUF, PIX)                                                        \
+  UVG_B200_API unsigned uvg_b200_reg_sad_##SUF(const PIX *d1, const PIX *d2, int w, int h,      \
+                                               unsigned stride1, unsigned stride2);            \
+  UVG_B200_API unsigned uvg_b200_sad_4x4_##SUF(const PIX *a, const PIX *b);                     \
+  UVG_B200_API unsigned uvg_b200_sad_8x8_##SUF(const PIX *a, const PIX *b);                     \
+  UVG_B200_API unsigned uvg_b200_sad_16x16_##SUF(const PIX *a, const PIX *b);                   \
+  UVG_B200_API unsigned uvg_b200_sad_32x32_##SUF(const PIX *a, const PIX *b);                   \
+  UVG_B200_API unsigned uvg_b200_sad_64x64_##SUF(const PIX *a, const PIX *b);                   \
+  UVG_B200_API unsigned uvg_b200_satd_4x4_##SUF(const PIX *a, const PIX *b);                    \
+  UVG_B200_API unsigned uvg_b200_satd_8x8_##SUF(const PIX *a, const PIX *b);                    \
+  UVG_B200_API unsigned uvg_b200_satd_16x16_##SUF(const PIX *a, const PIX *b);                  \
+  UVG_B200_API unsigned uvg_b200_satd_32x32_##SUF(const PIX *a, const PIX *b);                  \
+  UVG_B200_API unsigned uvg_b200_satd_64x64_##SUF(const PIX *a, const PIX *b);                  \
+  /* preds = pred_buffer: candidate k at preds + k*1024 pixels (strategies-picture.h:48) */    \
+  UVG_B200_API void uvg_b200_sad_4x4_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);   \
+  UVG_B200_API void uvg_b200_sad_8x8_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);   \
+  UVG_B200_API void uvg_b200_sad_16x16_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out); \
+  UVG_B200_API void uvg_b200_sad_32x32_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out); \
+  UVG_B200_API void uvg_b200_satd_4x4_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);  \
+  UVG_B200_API void uvg_b200_satd_8x8_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);  \
+  UVG_B200_API void uvg_b200_satd_16x16_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);\
+  UVG_B200_API void uvg_b200_satd_32x32_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);\
+  UVG_B200_API unsigned uvg_b200_satd_any_size_##SUF(int w, int h, const PIX *b1, int s1,       \
+                                                     const PIX *b2, int s2);                   \
+  UVG_B200_API unsigned uvg_b200_satd_any_size_vtm_##SUF(int w, int h, const PIX *b1, int s1,   \
+                                                         const PIX *b2, int s2);               \
+  UVG_B200_API void uvg_b200_satd_any_size_quad_##SUF(int w, int h, const PIX **preds,          \
+                                                      int stride, const PIX *orig,             \
+                                                      int orig_stride, unsigned num_modes,     \
+                                                      unsigned *costs_out, int8_t *valid);     \
+  UVG_B200_API unsigned uvg_b200_pixels_calc_ssd_##SUF(const PIX *ref, const PIX *rec,          \
+                                                       int ref_stride, int rec_stride, int w,  \
+                                                       int h);                                 \
+  UVG_B200_API uint32_t uvg_b200_ver_sad_##SUF(const PIX *pic, const PIX *ref_row, int32_t w,   \
+                                               int32_t h, uint32_t pic_stride);                \
+  UVG_B200_API uint32_t uvg_b200_hor_sad_##SUF(const PIX *pic, const PIX *ref, int32_t w,       \
+                                               int32_t h, uint32_t pic_stride,                 \
+                                               uint32_t ref_stride, uint32_t left,             \
+                                               uint32_t right);                                \
+  UVG_B200_API void uvg_b200_generate_residual_##SUF(const PIX *ref, const PIX *pred,           \
+                                                     int16_t *residual, int w, int h,          \
+                                                     int ref_stride, int pred_stride);         \
+  /* optimized_sad_func_ptr_t (optimized_sad_func_ptr_t.h:13): width-specialised SADs */       \
+  typedef uint32_t (*uvg_b200_optimized_sad_##SUF)(const PIX *, const PIX *, int32_t height,    \
+                                                   uint32_t stride1, uint32_t stride2);        \
+  UVG_B200_API uvg_b200_optimized_sad_##SUF uvg_b200_get_optimized_sad_##SUF(int32_t width);
+
+UVG_B200_DECL_PICTURE(8, uint8_t)
+UVG_B200_DECL_PICTURE(16, uint16_t)
+
+/* strategies-dct.h:44 dct_func (the typedef's unsigned return is never used; void here) */
+UVG_B200_API void uvg_b200_dct_4x4(int8_t bitdepth, const int16_t *in, int16_t *out);
+UVG_B200_API void uvg_b200_dct_8x8(int8_t bitdepth, const int16_t *in, int16_t *out);
+UVG_B200_API void uvg_b200_dct_16x16(int8_t bitdepth, const int16_t *in, int16_t *out);
+UVG_B200_API void uvg_b200_dct_32x32(int8_t bitdepth, const int16_t *in, int16_t *out);
+UVG_B200_API void uvg_b200_idct_4x4(int8_t bitdepth, const int16_t *in, int16_t *out);
+UVG_B200_API void uvg_b200_idct_8x8(int8_t bitdepth, const int16_t *in, int16_t *out);
+UVG_B200_API void uvg_b200_idct_16x16(int8_t bitdepth, const int16_t *in, int16_t *out);
+UVG_B200_API void uvg_b200_idct_32x32(int8_t bitdepth, const int16_t *in, int16_t *out);
+UVG_B200_API void uvg_b200_fast_forward_dst_4x4(int8_t bitdepth, const int16_t *in, int16_t *out);
+UVG_B200_API void uvg_b200_fast_inverse_dst_4x4(int8_t bitdepth, const int16_t *in, int16_t *out);
+/* mts_dct_func (strategies-dct.h:63-71) with cu_info_t flattened to the five fields the
+ * reference reads (dct-generic.c:2501-2557): tu->type, tr_idx, lfnst_idx, cr_lfnst_idx,
+ * intra.isp_mode. */
+UVG_B200_API void uvg_b200_mts_dct(int8_t bitdepth, int color, int cu_type, int tr_idx,
+                                   int lfnst_idx, int cr_lfnst_idx, int isp_mode, int8_t w,
+                                   int8_t h, const int16_t *in, int16_t *out, int8_t mts_type);
+UVG_B200_API void uvg_b200_mts_idct(int8_t bitdepth, int color, int cu_type, int tr_idx,
+                                    int lfnst_idx, int cr_lfnst_idx, int isp_mode, int8_t w,
+                                    int8_t h, const int16_t *in, int16_t *out, int8_t mts_type);
+UVG_B200_API void uvg_b200_get_tr_type(int w, int h, int color, int cu_type, int tr_idx,
+                                       int lfnst_idx, int cr_lfnst_idx, int isp_mode,
+                                       int mts_type, int *hor, int *ver);
+
+/* strategies-quant.h:48-91 with encoder_state_t flattened into uvg_b200_quant_cfg. */
+UVG_B200_API void uvg_b200_quant(const uvg_b200_quant_cfg *cfg, const int16_t *coef,
+                                 int16_t *q_coef, int32_t w, int32_t h, int color,
+                                 int8_t scan_idx, int8_t block_type, int8_t transform_skip,
+                                 uint8_t lfnst_idx);
+UVG_B200_API void uvg_b200_dequant(const uvg_b200_quant_cfg *cfg, const int16_t *q_coef,
+                                   int16_t *coef, int32_t w, int32_t h, int color,
+                                   int8_t block_type, int8_t transform_skip);
+UVG_B200_API int uvg_b200_quantize_residual_8(const uvg_b200_quant_cfg *cfg, int cu_type,
+                                              int tr_idx, int w, int h, int color,
+                                              int use_trskip, int in_stride, int out_stride,
+                                              const uint8_t *ref_in, const uint8_t *pred_in,
+                                              uint8_t *rec_out, int16_t *coeff_out,
+                                              int early_skip);
+UVG_B200_API int uvg_b200_quantize_residual_16(const uvg_b200_quant_cfg *cfg, int cu_type,
+                                               int tr_idx, int w, int h, int color,
+                                               int use_trskip, int in_stride, int out_stride,
+                                               const uint16_t *ref_in, const uint16_t *pred_in,
+                                               uint16_t *rec_out, int16_t *coeff_out,
+                                               int early_skip);
+UVG_B200_API uint32_t uvg_b200_coeff_abs_sum(const int16_t *coeffs, size_t length);
+UVG_B200_API uint32_t uvg_b200_fast_coeff_cost(const int16_t *coeff, int32_t w, int32_t h,
+                                               uint64_t weights);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UVG266_B200_H_ */

@@ -1,0 +1,66 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/uvg266_b200.h declares, and refuses to work without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+import uvg266_b200 as U
+
+
+def test_library_loads_and_exports_all_declared_symbols():
+    L = U.lib()
+    names = U.exported_symbols()
+    assert len(names) > 90
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_every_reference_strategy_type_has_a_dropin():
+    """Type strings of STRATEGIES_PICTURE/DCT/QUANT_EXPORTS on the hot path
+    (strategies-picture.h:210-243, strategies-dct.h:93-106, strategies-quant.h:104-110)."""
+    L = U.lib()
+    picture = (["reg_sad", "satd_any_size", "satd_any_size_vtm", "satd_any_size_quad", "pixels_calc_ssd",
+                "get_optimized_sad", "ver_sad", "hor_sad", "generate_residual"] +
+               ["%s_%dx%d" % (m, n, n) for m in ("sad", "satd") for n in (4, 8, 16, 32, 64)] +
+               ["%s_%dx%d_dual" % (m, n, n) for m in ("sad", "satd") for n in (4, 8, 16, 32)])
+    for suf in ("8", "16"):
+        for t in picture:
+            assert hasattr(L, "uvg_b200_%s_%s" % (t, suf)), t
+    dct = (["dct_%dx%d" % (n, n) for n in (4, 8, 16, 32)] + ["idct_%dx%d" % (n, n) for n in (4, 8, 16, 32)] +
+           ["fast_forward_dst_4x4", "fast_inverse_dst_4x4", "mts_dct", "mts_idct"])
+    quant = ["quant", "dequant", "coeff_abs_sum", "fast_coeff_cost"]
+    for t in dct + quant:
+        assert hasattr(L, "uvg_b200_" + t), t
+    assert hasattr(L, "uvg_b200_quantize_residual_8") and hasattr(L, "uvg_b200_quantize_residual_16")
+
+
+def test_only_uvg_prefixed_symbols_are_exported():
+    """tests/test_external_symbols.sh of the reference: exported symbols must be uvg_-prefixed."""
+    out = subprocess.check_output(["nm", "-D", "--defined-only", U.LIB_PATH]).decode()
+    bad = []
+    for line in out.splitlines():
+        parts = line.split()
+        if len(parts) == 3 and parts[1] in "TDBR":
+            if not parts[2].startswith("uvg_"):
+                bad.append(parts[2])
+    assert not bad, bad[:10]
+
+
+def test_no_silent_cpu_fallback():
+    """Without a CUDA device every entry point must fail loudly."""
+    L = U.lib()
+    if L.uvg_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    assert L.uvg_b200_init(0) != 0
+    assert b"no CPU fallback" in L.uvg_b200_last_error()
+    a = U.Blocks.dense(None, 8, 8)
+    assert L.uvg_b200_distortion_dev(U.SAD, 8, 8, 8, C.byref(a), C.byref(a), None, 1, 1, None) != 0
+
+
+def test_product_does_not_link_the_oracle():
+    out = subprocess.check_output(["ldd", U.LIB_PATH]).decode()
+    assert "oracle" not in out and "uvg266ref" not in out
+    syms = subprocess.check_output(["nm", "-D", U.LIB_PATH]).decode()
+    assert "orc_" not in syms and "refh_" not in syms

@@ -1,0 +1,577 @@
+// quant.cu - scalar quantisation / dequantisation and the fused
+// residual -> transform -> quant -> dequant -> inverse transform -> reconstruction kernel
+// for sm_100a. Restates quant-generic.c: uvg_quant_generic :51-234 (incl. sign-bit hiding),
+// uvg_dequant_generic :618-669 (flat lists), uvg_quantize_residual_generic :460-612,
+// coeff_abs_sum_generic :671, fast_coeff_cost_generic :688.
+#include "transform.cuh"
+#include <mutex>
+
+namespace uvgb {
+
+int launch_transform(bool inverse, const TrPlan &p, const int16_t *in, int16_t *out, size_t n_tus,
+                     cudaStream_t st);
+
+// -------------------------------------------------------------------------------------
+// scan tables (uvg_get_scan_order_table(SCAN_GROUP_4X4, SCAN_DIAG, ...), tables.c:2646):
+// coefficient groups (uvg_g_log2_sbb_size, tables.c:13-24) in up-right diagonal order,
+// diagonal order inside each group.
+// -------------------------------------------------------------------------------------
+static uint16_t h_scan[63 * 63];
+static int h_scan_off[6][6];
+static uint16_t *d_scan = nullptr;
+static std::once_flag scan_once;
+static cudaError_t scan_err = cudaSuccess;
+
+static void cg_log2(int l2w, int l2h, int *cw, int *ch)
+{
+  if (l2w >= 2 && l2h >= 2) { *cw = 2; *ch = 2; return; }
+  if (l2w == 0) { *cw = 0; *ch = l2h < 4 ? l2h : 4; return; }
+  if (l2h == 0) { *ch = 0; *cw = l2w < 4 ? l2w : 4; return; }
+  if (l2w == 1) { *cw = 1; *ch = (l2h <= 2) ? 1 : 3; return; }
+  *ch = 1; *cw = (l2w <= 2) ? 1 : 3;
+}
+
+static int diag_fill(int w, int h, int *xs, int *ys)
+{
+  int n = 0;
+  for (int s = 0; s < w + h - 1; ++s)
+    for (int x = 0; x < w; ++x) {
+      const int y = s - x;
+      if (y >= 0 && y < h) { xs[n] = x; ys[n] = y; ++n; }
+    }
+  return n;
+}
+
+static void build_scan()
+{
+  int off = 0;
+  static int gx[1024], gy[1024], ix[1024], iy[1024];
+  for (int l2w = 0; l2w <= 5; ++l2w)
+    for (int l2h = 0; l2h <= 5; ++l2h) {
+      h_scan_off[l2w][l2h] = off;
+      int cw, ch;
+      cg_log2(l2w, l2h, &cw, &ch);
+      const int w = 1 << l2w, gw = 1 << cw, gh = 1 << ch;
+      const int ng = diag_fill(w >> cw, (1 << l2h) >> ch, gx, gy);
+      const int ni = diag_fill(gw, gh, ix, iy);
+      for (int g = 0; g < ng; ++g)
+        for (int i = 0; i < ni; ++i)
+          h_scan[off++] = (uint16_t)((gy[g] * gh + iy[i]) * w + gx[g] * gw + ix[i]);
+    }
+  scan_err = cudaMalloc(&d_scan, sizeof(h_scan));
+  if (scan_err == cudaSuccess) scan_err = cudaMemcpy(d_scan, h_scan, sizeof(h_scan), cudaMemcpyHostToDevice);
+}
+
+int init_quant_tables()
+{
+  std::call_once(scan_once, build_scan);
+  if (scan_err != cudaSuccess) { set_error("scan tables: %s", cudaGetErrorString(scan_err)); return 1; }
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------
+// quantiser parameters (host)
+// -------------------------------------------------------------------------------------
+static const int16_t k_quant_scales[2][6] = { { 26214, 23302, 20560, 18396, 16384, 14564 },
+                                              { 18396, 16384, 14564, 13107, 11651, 10280 } };  // scalinglist.c:91
+static const int16_t k_inv_quant_scales[2][6] = { { 40, 45, 51, 57, 64, 72 },
+                                                  { 57, 64, 72, 80, 90, 102 } };               // scalinglist.c:95
+
+struct QParams {
+  int w, h, area;
+  // quant
+  int q_bits, add, q_bits8, coeff_default, coeff_list, signhide, lfnst_idx, max_lfnst;
+  const uint16_t *scan;
+  // dequant
+  int dq_shift, dq_scale, dq_add;
+  // reconstruction
+  int pixel_max, ssd_shift;
+};
+
+// uvg_get_scaled_qp, transform.c:150-165
+static int scaled_qp(const uvg_b200_quant_cfg *c, int color)
+{
+  const int off = (c->bitdepth - 8) * 6;
+  if (color == 0) return c->qp + off;
+  int q = c->qp < -off ? -off : (c->qp > 57 ? 57 : c->qp);
+  if (c->has_chroma_qp_map) return c->chroma_qp_map[c->qp & 127] + off;
+  return q + off;
+}
+
+static int make_qparams(QParams &q, const uvg_b200_quant_cfg *c, int w, int h, int color,
+                        int transform_skip, int lfnst_idx)
+{
+  if (!c) { set_error("quant cfg is NULL"); return 1; }
+  if (c->bitdepth < 8 || c->bitdepth > 12) { set_error("quant: bitdepth %d unsupported", c->bitdepth); return 1; }
+  auto pow2 = [](int v) { return v >= 1 && v <= 32 && (v & (v - 1)) == 0; };
+  if (!pow2(w) || !pow2(h)) { set_error("quant: block %dx%d unsupported", w, h); return 1; }
+  const int l2w = ilog2_host(w), l2h = ilog2_host(h);
+  int qp_scaled = scaled_qp(c, color);
+  if (transform_skip && qp_scaled < 4 + 6 * 2) qp_scaled = 4 + 6 * 2;   // MIN_QP_PRIME_TS
+  if (qp_scaled < 0) { set_error("negative scaled qp"); return 1; }
+  const int needs_scale = !transform_skip && ((l2w + l2h) % 2 == 1);
+  const int transform_shift = 15 - c->bitdepth - ((l2w + l2h) >> 1) - needs_scale;       // :76
+  q.w = w; q.h = h; q.area = w * h;
+  q.q_bits = 14 + qp_scaled / 6 + (transform_skip ? 0 : transform_shift);                // :77
+  if (q.q_bits < 9 || q.q_bits > 30) { set_error("q_bits %d out of range", q.q_bits); return 1; }
+  q.add = (c->slice_intra ? 171 : 85) << (q.q_bits - 9);                                 // :78
+  q.q_bits8 = q.q_bits - 8;
+  q.coeff_default = k_quant_scales[needs_scale][qp_scaled % 6];                          // :81
+  q.coeff_list = k_quant_scales[0][qp_scaled % 6];   // flat quant_coeff[] (scalinglist.c:416)
+  q.signhide = c->signhide;
+  q.lfnst_idx = lfnst_idx;
+  q.max_lfnst = ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 8 : 16;                    // :103
+  if (lfnst_idx && (w < 4 || h < 4)) { set_error("lfnst needs a >=4x4 block"); return 1; }
+  if (c->signhide && q.area < 16) { set_error("sign hiding needs >= 16 coefficients"); return 1; }
+  q.scan = d_scan + h_scan_off[l2w][l2h];
+  // dequant :629-637, :660-661
+  const int ts_deq = 15 - c->bitdepth - ((l2w + l2h) >> 1);
+  q.dq_shift = 20 - 14 - (transform_skip ? 0 : ts_deq - needs_scale);
+  if (q.dq_shift < 1) { set_error("dequant shift %d unsupported for %dx%d", q.dq_shift, w, h); return 1; }
+  q.dq_scale = k_inv_quant_scales[needs_scale][qp_scaled % 6] << (qp_scaled / 6);
+  q.dq_add = 1 << (q.dq_shift - 1);
+  q.pixel_max = (1 << c->bitdepth) - 1;
+  q.ssd_shift = 2 * (c->bitdepth - 8);
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------
+// device building blocks (operate on one TU held in shared memory; `tid`/`nt` index the
+// threads cooperating on that TU)
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ int quant_level(int c, int coeff, const QParams &q)
+{
+  const unsigned a = (unsigned)abs(c);
+  // |c| <= 32768 and coeff <= 26214: the product + add stays below 2^31
+  int level = (int)((a * (unsigned)coeff + (unsigned)q.add) >> q.q_bits);
+  return level;
+}
+
+// level loop of uvg_quant_generic (:86-121); returns this thread's partial ac_sum
+__device__ __forceinline__ unsigned quant_elems(const int16_t *coef, int16_t *qc, const QParams &q,
+                                                int tid, int nt)
+{
+  unsigned ac = 0;
+  if (q.lfnst_idx == 0) {
+    for (int n = tid; n < q.area; n += nt) {
+      const int c = coef[n];
+      int level = quant_level(c, q.coeff_default, q);
+      ac += (unsigned)level;
+      level = c < 0 ? -level : level;
+      qc[n] = (int16_t)clip3(-32768, 32767, level);
+    }
+  } else {
+    // memset(q_coef, 0) :104; the kept coefficients are written by quant_lfnst_elems after
+    // a barrier
+    for (int n = tid; n < q.area; n += nt) qc[n] = 0;
+  }
+  return ac;
+}
+
+__device__ __forceinline__ unsigned quant_lfnst_elems(const int16_t *coef, int16_t *qc,
+                                                      const QParams &q, int tid, int nt)
+{
+  unsigned ac = 0;
+  for (int n = tid; n < q.max_lfnst; n += nt) {
+    const int idx = q.scan[n];
+    const int c = coef[idx];
+    int level = quant_level(c, q.coeff_list, q);   // always the list table, :114
+    ac += (unsigned)level;
+    level = c < 0 ? -level : level;
+    qc[idx] = (int16_t)clip3(-32768, 32767, level);
+  }
+  return ac;
+}
+
+__device__ __forceinline__ int delta_u_of(int c, const QParams &q)
+{
+  const unsigned a = (unsigned)abs(c);
+  const unsigned prod = a * (unsigned)q.coeff_list;        // list table even when lists are off (:132,:144)
+  const int level = (int)((prod + (unsigned)q.add) >> q.q_bits);
+  return ((int)prod - (level << q.q_bits)) >> q.q_bits8;
+}
+
+// Sign-bit hiding for coefficient group `cg` (:151-233). `is_last_cg`: this is the first
+// group, scanning from the end, that holds a non-zero level.
+__device__ void signhide_cg(const int16_t *coef, int16_t *qc, const QParams &q, int cg, bool is_last_cg)
+{
+  const uint16_t *scan = q.scan + (cg << 4);
+  int first_nz = 16, last_nz = -1;
+  for (int n = 15; n >= 0; --n) if (qc[scan[n]]) { last_nz = n; break; }
+  if (last_nz < 0) return;
+  for (int n = 0; n < 16; ++n) if (qc[scan[n]]) { first_nz = n; break; }
+  if (last_nz - first_nz < 4) return;
+  int abssum = 0;
+  for (int n = first_nz; n <= last_nz; ++n) abssum += qc[scan[n]];
+  const int signbit = qc[scan[first_nz]] > 0 ? 0 : 1;
+  if (signbit == (abssum & 1)) return;
+  int min_cost = 0x7fffffff, cur_cost = 0x7fffffff, min_pos = -1;
+  int final_change = 0, cur_change = 0;
+  for (int n = is_last_cg ? last_nz : 15; n >= 0; --n) {
+    const int pos = scan[n];
+    const int qv = qc[pos];
+    if (qv != 0) {
+      const int du = delta_u_of(coef[pos], q);
+      if (du > 0) { cur_cost = -du; cur_change = 1; }
+      else if (n == first_nz && abs(qv) == 1) { cur_cost = 0x7fffffff; }
+      else { cur_cost = du; cur_change = -1; }
+    } else if (n < first_nz && ((coef[pos] >= 0) ? 0 : 1) != signbit) {
+      cur_cost = 0x7fffffff;
+    } else {
+      cur_cost = -delta_u_of(coef[pos], q); cur_change = 1;
+    }
+    if (cur_cost < min_cost) { min_cost = cur_cost; final_change = cur_change; min_pos = pos; }
+  }
+  if (qc[min_pos] == 32767 || qc[min_pos] == -32768) final_change = -1;
+  if (coef[min_pos] >= 0) qc[min_pos] = (int16_t)(qc[min_pos] + final_change);
+  else qc[min_pos] = (int16_t)(qc[min_pos] - final_change);
+}
+
+// dequant, flat branch (:660-668)
+__device__ __forceinline__ void dequant_elems(const int16_t *qc, int16_t *coef, const QParams &q,
+                                              int tid, int nt)
+{
+  for (int n = tid; n < q.area; n += nt) {
+    const int v = ((int)qc[n] * q.dq_scale + q.dq_add) >> q.dq_shift;
+    coef[n] = (int16_t)clip3(-32768, 32767, v);
+  }
+}
+
+// Whole quant step for the TUs of a CTA, shared by the standalone and the fused kernel.
+// s_coef / s_q: per-slot buffers; s_acc[slot] / s_cgnz[slot*64..]: per-slot scratch.
+// All threads of the CTA must call it (contains __syncthreads).
+__device__ __forceinline__ void quant_step(const int16_t *s_coef, int16_t *s_q, const QParams &q,
+                                           unsigned *s_acc, unsigned char *s_cgnz, int slot, int tid,
+                                           int nt, bool active)
+{
+  if (tid == 0) s_acc[slot] = 0;
+  __syncthreads();
+  if (active) {
+    unsigned ac = quant_elems(s_coef, s_q, q, tid, nt);
+    if (q.lfnst_idx == 0 && ac) atomicAdd(&s_acc[slot], ac);
+  }
+  if (q.lfnst_idx) {
+    __syncthreads();
+    if (active) {
+      unsigned ac = quant_lfnst_elems(s_coef, s_q, q, tid, nt);
+      if (ac) atomicAdd(&s_acc[slot], ac);
+    }
+  }
+  __syncthreads();
+  if (q.signhide) {
+    const int ncg = q.area >> 4;
+    unsigned char *nz = s_cgnz + slot * 64;
+    if (active && s_acc[slot] >= 2) {
+      for (int cg = tid; cg < ncg; cg += nt) {
+        bool any = false;
+        for (int n = 0; n < 16; ++n) any |= s_q[q.scan[(cg << 4) + n]] != 0;
+        nz[cg] = any;
+      }
+    }
+    __syncthreads();
+    if (active && s_acc[slot] >= 2) {
+      for (int cg = tid; cg < ncg; cg += nt) {
+        if (!nz[cg]) continue;
+        bool higher = false;
+        for (int c2 = cg + 1; c2 < ncg; ++c2) higher |= nz[c2] != 0;
+        signhide_cg(s_coef, s_q, q, cg, !higher);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// standalone quant / dequant kernels
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+quant_kernel(const int16_t *__restrict__ coef, int16_t *__restrict__ qcoef, size_t n_tus, QParams q,
+             int slots)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int16_t *sbuf = reinterpret_cast<int16_t *>(smem_raw);
+  unsigned *s_acc = reinterpret_cast<unsigned *>(sbuf + (size_t)slots * 2 * q.area);
+  unsigned char *s_cgnz = reinterpret_cast<unsigned char *>(s_acc + slots);
+  const int tps = blockDim.x / slots;
+  const int slot = threadIdx.x / tps, tid = threadIdx.x - slot * tps;
+  int16_t *s_coef = sbuf + (size_t)slot * 2 * q.area, *s_q = s_coef + q.area;
+  for (size_t base = (size_t)blockIdx.x * slots; base < n_tus; base += (size_t)gridDim.x * slots) {
+    const size_t tu = base + slot;
+    const bool active = tu < n_tus;
+    __syncthreads();
+    if (active) for (int t = tid; t < q.area; t += tps) s_coef[t] = coef[tu * q.area + t];
+    __syncthreads();
+    quant_step(s_coef, s_q, q, s_acc, s_cgnz, slot, tid, tps, active);
+    if (active) for (int t = tid; t < q.area; t += tps) qcoef[tu * q.area + t] = s_q[t];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dequant_kernel(const int16_t *__restrict__ qcoef, int16_t *__restrict__ coef, size_t total, QParams q)
+{
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const int v = ((int)qcoef[t] * q.dq_scale + q.dq_add) >> q.dq_shift;
+    coef[t] = (int16_t)clip3(-32768, 32767, v);
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// fused quantize_residual
+// -------------------------------------------------------------------------------------
+struct FusedArgs {
+  Blocks ref, pred, rec;
+  int16_t *coeff_out;
+  uint8_t *has_coeffs;
+  uint32_t *ssd;
+  uint32_t *cost;
+  unsigned w0, w1, w2, w3;   // fast_coeff_cost weights (Q8.8), rdo.c:440
+  int use_trskip, early_skip, rec_is_pred;
+};
+
+template <typename Pix>
+__global__ void __launch_bounds__(256)
+quantize_residual_kernel(FusedArgs a, size_t n_tus, QParams q, TrPlan fp, TrPlan ip, int slots)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // matrices: forward pair transposed, inverse pair row-major
+  int8_t *sF1 = reinterpret_cast<int8_t *>(smem_raw);
+  int8_t *sF2 = sF1 + fp.n1 * fp.n1;
+  int8_t *sI1 = sF2 + fp.n2 * fp.n2;
+  int8_t *sI2 = sI1 + ip.n1 * ip.n1;
+  const int mat_bytes = (fp.n1 * fp.n1 + fp.n2 * fp.n2 + ip.n1 * ip.n1 + ip.n2 * ip.n2 + 15) & ~15;
+  int16_t *sbuf = reinterpret_cast<int16_t *>(smem_raw + mat_bytes);
+  unsigned *s_acc = reinterpret_cast<unsigned *>(sbuf + (size_t)slots * 3 * q.area);
+  unsigned *s_red = s_acc + slots;                       // [slots][3]: nonzero, ssd, cost
+  unsigned char *s_cgnz = reinterpret_cast<unsigned char *>(s_red + slots * 3);
+  if (!a.use_trskip) {
+    for (int t = threadIdx.x; t < fp.n1 * fp.n1; t += blockDim.x) { const int k = t / fp.n1, i = t - k * fp.n1; sF1[i * fp.n1 + k] = fp.t1[t]; }
+    for (int t = threadIdx.x; t < fp.n2 * fp.n2; t += blockDim.x) { const int k = t / fp.n2, i = t - k * fp.n2; sF2[i * fp.n2 + k] = fp.t2[t]; }
+    for (int t = threadIdx.x; t < ip.n1 * ip.n1; t += blockDim.x) sI1[t] = ip.t1[t];
+    for (int t = threadIdx.x; t < ip.n2 * ip.n2; t += blockDim.x) sI2[t] = ip.t2[t];
+  }
+  const int tps = blockDim.x / slots;
+  const int slot = threadIdx.x / tps, tid = threadIdx.x - slot * tps;
+  int16_t *bufA = sbuf + (size_t)slot * 3 * q.area, *bufB = bufA + q.area, *bufQ = bufB + q.area;
+  const int w = q.w, area = q.area;
+  for (size_t base = (size_t)blockIdx.x * slots; base < n_tus; base += (size_t)gridDim.x * slots) {
+    const size_t tu = base + slot;
+    const bool active = tu < n_tus;
+    const Pix *pref = nullptr, *ppred = nullptr; Pix *prec = nullptr;
+    if (active) {
+      pref = static_cast<const Pix *>(a.ref.base) + a.ref.offset(tu);
+      ppred = static_cast<const Pix *>(a.pred.base) + a.pred.offset(tu);
+      prec = const_cast<Pix *>(static_cast<const Pix *>(a.rec.base)) + a.rec.offset(tu);
+    }
+    __syncthreads();
+    if (tid < 3) s_red[slot * 3 + tid] = 0;
+    // 1. residual (generate_residual :480)
+    if (active)
+      for (int t = tid; t < area; t += tps) {
+        const int y = t / w, x = t - y * w;
+        bufA[t] = (int16_t)((int)pref[(size_t)y * a.ref.stride + x] - (int)ppred[(size_t)y * a.pred.stride + x]);
+      }
+    __syncthreads();
+    // 2. forward transform (:495-501) -> coefficients in bufA
+    if (!a.use_trskip) {
+      if (active) fwd_pass(bufA, bufB, sF1, fp.n1, fp.line1, fp.reduced1, fp.cutoff1, fp.shift1, tid, tps);
+      __syncthreads();
+      if (fp.n2) {
+        if (active) fwd_pass(bufB, bufA, sF2, fp.n2, fp.line2, fp.reduced2, fp.cutoff2, fp.shift2, tid, tps);
+      } else {
+        if (active) for (int t = tid; t < area; t += tps) bufA[t] = bufB[t];
+      }
+      __syncthreads();
+    }
+    // 3. quant (+ sign hiding) :536-539
+    quant_step(bufA, bufQ, q, s_acc, s_cgnz, slot, tid, tps, active);
+    // 4. coefficients out, has_coeffs (:542-550), fast coefficient cost
+    if (active) {
+      unsigned nzf = 0, cst = 0;
+      for (int t = tid; t < area; t += tps) {
+        const int16_t v = bufQ[t];
+        a.coeff_out[tu * area + t] = v;
+        nzf |= (v != 0);
+        const unsigned av = min((unsigned)abs((int)v), 3u);
+        cst += av == 0 ? a.w0 : av == 1 ? a.w1 : av == 2 ? a.w2 : a.w3;
+      }
+      if (nzf) atomicOr(&s_red[slot * 3 + 0], 1u);
+      if (a.cost && cst) atomicAdd(&s_red[slot * 3 + 2], cst);
+    }
+    __syncthreads();
+    const bool has = active && s_red[slot * 3 + 0] != 0;
+    const bool recon = has && !a.early_skip;
+    // 5. dequant + inverse transform (:553-570) -> residual' in bufA
+    if (recon) dequant_elems(bufQ, a.use_trskip ? bufA : bufB, q, tid, tps);
+    __syncthreads();
+    if (!a.use_trskip) {
+      // bufB holds dequantised coefficients
+      if (recon) inv_pass(bufB, ip.n2 ? bufQ : bufA, sI1, ip.n1, ip.line1, ip.reduced1, ip.cutoff1, ip.shift1, tid, tps);
+      __syncthreads();
+      if (ip.n2) {
+        if (recon) inv_pass(bufQ, bufA, sI2, ip.n2, ip.line2, ip.reduced2, ip.cutoff2, ip.shift2, tid, tps);
+        __syncthreads();
+      }
+    }
+    // 6. reconstruction (:591-611) + SSD against the source
+    if (active) {
+      unsigned ssd = 0;
+      for (int t = tid; t < area; t += tps) {
+        const int y = t / w, x = t - y * w;
+        const int pv = (int)ppred[(size_t)y * a.pred.stride + x];
+        int rv = pv;
+        if (recon) rv = clip3(0, q.pixel_max, (int)(short)(bufA[t] + pv));
+        if (recon || !a.rec_is_pred) prec[(size_t)y * a.rec.stride + x] = (Pix)rv;
+        const int d = (int)pref[(size_t)y * a.ref.stride + x] - rv;
+        ssd += (unsigned)(d * d);
+      }
+      if (a.ssd && ssd) atomicAdd(&s_red[slot * 3 + 1], ssd);
+    }
+    __syncthreads();
+    if (active && tid == 0) {
+      a.has_coeffs[tu] = has ? 1 : 0;
+      if (a.ssd) a.ssd[tu] = (uint32_t)((int32_t)s_red[slot * 3 + 1] >> q.ssd_shift);
+      if (a.cost) a.cost[tu] = (s_red[slot * 3 + 2] + 128u) >> 8;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// coefficient sums
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+coeff_sum_kernel(const int16_t *__restrict__ coeffs, size_t len, uint32_t *__restrict__ out, size_t n_tus,
+                 int mode, unsigned w0, unsigned w1, unsigned w2, unsigned w3)
+{
+  // one warp per block of `len` coefficients
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_tus) return;
+  const int16_t *p = coeffs + warp * len;
+  unsigned s = 0;
+  for (size_t i = lane; i < len; i += 32) {
+    const unsigned av = (unsigned)abs((int)p[i]);
+    if (mode == 0) s += av;
+    else { const unsigned c = min(av, 3u); s += c == 0 ? w0 : c == 1 ? w1 : c == 2 ? w2 : w3; }
+  }
+  s = (unsigned)warp_sum((int)s);
+  if (lane == 0) out[warp] = mode == 0 ? s : (s + 128u) >> 8;
+}
+
+static int slots_for(int area)
+{
+  int slots = 256 / (area < 16 ? 16 : area);
+  if (slots < 1) slots = 1;
+  if (slots > 16) slots = 16;
+  return slots;
+}
+
+}  // namespace uvgb
+
+using namespace uvgb;
+
+extern "C" int uvg_b200_quant_dev(const uvg_b200_quant_cfg *cfg, const int16_t *coef, int16_t *q_coef,
+                                  int w, int h, int color, int transform_skip, int lfnst_idx,
+                                  size_t n_tus, void *stream)
+{
+  if (ensure_init()) return 1;
+  if (n_tus == 0) return 0;
+  QParams q;
+  if (make_qparams(q, cfg, w, h, color, transform_skip, lfnst_idx)) return 1;
+  const int slots = slots_for(q.area);
+  const size_t smem = (size_t)slots * 2 * q.area * sizeof(int16_t) + slots * sizeof(unsigned) + slots * 64;
+  size_t grid = (n_tus + slots - 1) / slots;
+  const size_t cap = (size_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  quant_kernel<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(coef, q_coef, n_tus, q, slots);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int uvg_b200_dequant_dev(const uvg_b200_quant_cfg *cfg, const int16_t *q_coef, int16_t *coef,
+                                    int w, int h, int color, int transform_skip, size_t n_tus,
+                                    void *stream)
+{
+  if (ensure_init()) return 1;
+  if (n_tus == 0) return 0;
+  QParams q;
+  uvg_b200_quant_cfg c = *cfg; c.signhide = 0;
+  if (make_qparams(q, &c, w, h, color, transform_skip, 0)) return 1;
+  const size_t total = n_tus * (size_t)q.area;
+  size_t grid = (total + 255) / 256;
+  const size_t cap = (size_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  dequant_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q_coef, coef, total, q);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx,
+                                              int w, int h, int color, int use_trskip, int early_skip,
+                                              const uvg_b200_blocks *ref, const uvg_b200_blocks *pred,
+                                              const uvg_b200_blocks *rec, int16_t *coeff_out,
+                                              uint8_t *has_coeffs, uint32_t *ssd, uint32_t *cost,
+                                              uint64_t cost_weights, size_t n_tus, void *stream)
+{
+  if (ensure_init()) return 1;
+  if (n_tus == 0) return 0;
+  if (!cfg || !ref || !pred || !rec || !coeff_out || !has_coeffs) { set_error("quantize_residual: NULL argument"); return 1; }
+  QParams q;
+  // quant is called with transform_skip = (tr_idx == MTS_SKIP && luma), quant-generic.c:538
+  const int ts_flag = (tr_idx == 1 && color == 0) ? 1 : 0;
+  if (make_qparams(q, cfg, w, h, color, ts_flag, 0)) return 1;
+  TrPlan fp{}, ip{};
+  if (!use_trskip) {
+    int th, tv, sw, sh;
+    // uvg_transform2d (transform.c:256): mts_dct when cfg.mts or non-square, else dct_NxN -
+    // both are this matrix product; with mts off the types are DCT2/DCT2.
+    derive_tr(w, h, color, cu_type, tr_idx, 0, 0, 0, cfg->mts, &th, &tv, &sw, &sh);
+    if (make_fwd_plan(fp, cfg->bitdepth, w, h, th, tv, sw, sh)) return 1;
+    if (make_inv_plan(ip, cfg->bitdepth, w, h, th, tv, sw, sh)) return 1;
+  }
+  FusedArgs a;
+  a.ref = to_blocks(ref); a.pred = to_blocks(pred); a.rec = to_blocks(rec);
+  a.coeff_out = coeff_out; a.has_coeffs = has_coeffs; a.ssd = ssd; a.cost = cost;
+  a.w0 = (unsigned)(cost_weights & 0xffff); a.w1 = (unsigned)((cost_weights >> 16) & 0xffff);
+  a.w2 = (unsigned)((cost_weights >> 32) & 0xffff); a.w3 = (unsigned)((cost_weights >> 48) & 0xffff);
+  a.use_trskip = use_trskip; a.early_skip = early_skip;
+  a.rec_is_pred = (rec->base == pred->base && rec->stride == pred->stride &&
+                   rec->col_pitch == pred->col_pitch && rec->row_pitch == pred->row_pitch &&
+                   rec->blocks_per_row == pred->blocks_per_row);
+  const int slots = slots_for(q.area);
+  const int mat_bytes = (fp.n1 * fp.n1 + fp.n2 * fp.n2 + ip.n1 * ip.n1 + ip.n2 * ip.n2 + 15) & ~15;
+  const size_t smem = mat_bytes + (size_t)slots * 3 * q.area * sizeof(int16_t) + slots * 4 * sizeof(unsigned) + slots * 64;
+  size_t grid = (n_tus + slots - 1) / slots;
+  const size_t cap = (size_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cfg->bitdepth == 8) quantize_residual_kernel<uint8_t><<<(unsigned)grid, 256, smem, st>>>(a, n_tus, q, fp, ip, slots);
+  else quantize_residual_kernel<uint16_t><<<(unsigned)grid, 256, smem, st>>>(a, n_tus, q, fp, ip, slots);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int uvg_b200_coeff_abs_sum_dev(const int16_t *coeffs, size_t len, uint32_t *out, size_t n_tus,
+                                          void *stream)
+{
+  if (ensure_init()) return 1;
+  if (n_tus == 0) return 0;
+  const size_t threads = n_tus * 32;
+  coeff_sum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      coeffs, len, out, n_tus, 0, 0, 0, 0, 0);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int uvg_b200_fast_coeff_cost_dev(const int16_t *coeffs, int w, int h, uint64_t weights,
+                                            uint32_t *out, size_t n_tus, void *stream)
+{
+  if (ensure_init()) return 1;
+  if (n_tus == 0) return 0;
+  const size_t threads = n_tus * 32;
+  coeff_sum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      coeffs, (size_t)w * h, out, n_tus, 1, (unsigned)(weights & 0xffff), (unsigned)((weights >> 16) & 0xffff),
+      (unsigned)((weights >> 32) & 0xffff), (unsigned)((weights >> 48) & 0xffff));
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
