@@ -260,8 +260,9 @@ def test_dropin_quantize_residual(bd, mts_val):
                 for tr_idx in ((0, 2, 3, 5) if mts_val == 3 else (0,)):
                     for early in (0, 1):
                         for alias in (0, 1):
-                            p = OrcQuantParams(qp, bd, 1, 1, mts_val, qptr)
-                            cfg = U.QuantCfg.make(qp, bd, 1, 1, mts_val, qlist)
+                            sh = (n_cases >> 1) & 1
+                            p = OrcQuantParams(qp, bd, 1, sh, mts_val, qptr)
+                            cfg = U.QuantCfg.make(qp, bd, 1, sh, mts_val, qlist)
                             stride = 64 if color == 0 else 32
                             hi = 1 << bd
                             ref = rng.integers(0, hi, stride * h).astype(pix_dtype(bd))
@@ -384,10 +385,13 @@ def test_batched_rough_cost(bd):
 
 
 @pytest.mark.parametrize("bd", BDS)
-def test_batched_quantize_residual_and_transform(bd):
+@pytest.mark.parametrize("signhide", [0, 1])
+def test_batched_quantize_residual_and_transform(bd, signhide):
+    """signhide=0 takes the shape-specialised kernels (registers-only 4x4/8x8, tensor-core
+    16x16/32x32), signhide=1 the general shared-memory kernel."""
     O = load_oracle(bd)
     L = U.lib()
-    rng = np.random.default_rng(1800 + bd)
+    rng = np.random.default_rng(1800 + bd + signhide)
     hi = 1 << bd
     dt = pix_dtype(bd)
     weights = (28 << 0) | (300 << 16) | (700 << 32) | (1100 << 48)
@@ -399,12 +403,12 @@ def test_batched_quantize_residual_and_transform(bd):
             rec = np.zeros(nt * n * n, dt)
             coeff = np.zeros(nt * n * n, np.int16); has = np.zeros(nt, np.uint8)
             ssd = np.zeros(nt, np.uint32); cost = np.zeros(nt, np.uint32)
-            cfg = U.QuantCfg.make(qp, bd, 1, 1, 0)
+            cfg = U.QuantCfg.make(qp, bd, 1, signhide, 0)
             R, P, Rc = (U.Blocks.dense(a.ctypes.data, n, n) for a in (ref, pred, rec))
             U.check(L.uvg_b200_quantize_residual_host(C.byref(cfg), 1, 0, n, n, 0, 0, 0, C.byref(R), ref.nbytes,
                                                       C.byref(P), pred.nbytes, C.byref(Rc), rec.nbytes, ptr(coeff),
                                                       ptr(has), ptr(ssd), ptr(cost), weights, nt))
-            p = OrcQuantParams(qp, bd, 1, 1, 0, None)
+            p = OrcQuantParams(qp, bd, 1, signhide, 0, None)
             for t in range(nt):
                 sl = slice(t * n * n, (t + 1) * n * n)
                 r2 = np.zeros(n * n, dt); c2 = np.zeros(n * n, np.int16)

@@ -107,6 +107,28 @@ sad_ssd_kernel(Blocks A, Blocks B, uint32_t *__restrict__ out, size_t n_items, i
   }
 }
 
+// Arbitrary widths (w % 4 != 0): the frame-edge splitter image_interpolated_sad (image.c:310-427)
+// calls reg_sad / hor_sad / ver_sad on slivers such as 32x1 or 3x8. Pixel-at-a-time path.
+template <typename Pix, int OP>
+__global__ void __launch_bounds__(128)
+sad_ssd_px_kernel(Blocks A, Blocks B, uint32_t *__restrict__ out, size_t n_items, int k, int w, int h,
+                  int shift)
+{
+  const size_t item = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per item
+  const int lane = threadIdx.x & 31;
+  if (item >= n_items) return;
+  const Pix *pa = static_cast<const Pix *>(A.base) + A.offset(item / k);
+  const Pix *pb = static_cast<const Pix *>(B.base) + B.offset(item);
+  uint32_t acc = 0;
+  for (int e = lane; e < w * h; e += 32) {
+    const int y = e / w, x = e - y * w;
+    const int d = (int)__ldg(pa + (size_t)y * A.stride + x) - (int)__ldg(pb + (size_t)y * B.stride + x);
+    acc += (OP == OP_SAD) ? (uint32_t)abs(d) : (uint32_t)(d * d);
+  }
+  acc = group_sum<32>(acc);
+  if (lane == 0) out[item] = (OP == OP_SSD) ? (uint32_t)((int32_t)acc >> shift) : (acc >> shift);
+}
+
 // -------------------------------------------------------------------------------------
 // Hadamard building blocks (32-bit path: any bit depth)
 // -------------------------------------------------------------------------------------
@@ -508,6 +530,11 @@ static int launch_sad_ssd(const Blocks &A, const Blocks &B, uint32_t *out, size_
                           int w, int h, int shift, cudaStream_t st)
 {
   constexpr int PW = PixTraits<Pix>::kPerWord;
+  if (w % PW) {
+    sad_ssd_px_kernel<Pix, OP><<<grid_for(n_items * 32, 128), 128, 0, st>>>(A, B, out, n_items, k, w, h, shift);
+    UVGB_LAUNCH_CHECK();
+    return 0;
+  }
   const bool wide = (w % (4 * PW)) == 0;
   const int chunks = wide ? (w / (4 * PW)) * h : (w / PW) * h;
   // aim for >= 4 chunks per lane so several loads are in flight per thread
@@ -621,7 +648,8 @@ extern "C" int uvg_b200_distortion_dev(int metric, int bitdepth, int w, int h,
   if (ensure_init()) return 1;
   if (check_dims(bitdepth, w, h, k)) return 1;
   if (n_blocks == 0) return 0;
-  if (metric != UVG_B200_SATD_VTM && ((w % 4) || (h % 4))) {
+  const bool is_satd = metric == UVG_B200_SATD || metric == UVG_B200_SATD_4X4 || metric == UVG_B200_SATD_QUAD;
+  if (is_satd && ((w % 4) || (h % 4))) {
     set_error("metric %d needs w,h multiples of 4 (got %dx%d)", metric, w, h);
     return 1;
   }

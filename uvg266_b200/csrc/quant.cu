@@ -4,6 +4,7 @@
 // uvg_dequant_generic :618-669 (flat lists), uvg_quantize_residual_generic :460-612,
 // coeff_abs_sum_generic :671, fast_coeff_cost_generic :688.
 #include "transform.cuh"
+#include "quant.cuh"
 #include <mutex>
 
 namespace uvgb {
@@ -76,17 +77,6 @@ static const int16_t k_quant_scales[2][6] = { { 26214, 23302, 20560, 18396, 1638
                                               { 18396, 16384, 14564, 13107, 11651, 10280 } };  // scalinglist.c:91
 static const int16_t k_inv_quant_scales[2][6] = { { 40, 45, 51, 57, 64, 72 },
                                                   { 57, 64, 72, 80, 90, 102 } };               // scalinglist.c:95
-
-struct QParams {
-  int w, h, area;
-  // quant
-  int q_bits, add, q_bits8, coeff_default, coeff_list, signhide, lfnst_idx, max_lfnst;
-  const uint16_t *scan;
-  // dequant
-  int dq_shift, dq_scale, dq_add;
-  // reconstruction
-  int pixel_max, ssd_shift;
-};
 
 // uvg_get_scaled_qp, transform.c:150-165
 static int scaled_qp(const uvg_b200_quant_cfg *c, int color)
@@ -319,16 +309,6 @@ dequant_kernel(const int16_t *__restrict__ qcoef, int16_t *__restrict__ coef, si
 // -------------------------------------------------------------------------------------
 // fused quantize_residual
 // -------------------------------------------------------------------------------------
-struct FusedArgs {
-  Blocks ref, pred, rec;
-  int16_t *coeff_out;
-  uint8_t *has_coeffs;
-  uint32_t *ssd;
-  uint32_t *cost;
-  unsigned w0, w1, w2, w3;   // fast_coeff_cost weights (Q8.8), rdo.c:440
-  int use_trskip, early_skip, rec_is_pred;
-};
-
 template <typename Pix>
 __global__ void __launch_bounds__(256)
 quantize_residual_kernel(FusedArgs a, size_t n_tus, QParams q, TrPlan fp, TrPlan ip, int slots)
@@ -521,8 +501,8 @@ extern "C" int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, int
   const int ts_flag = (tr_idx == 1 && color == 0) ? 1 : 0;
   if (make_qparams(q, cfg, w, h, color, ts_flag, 0)) return 1;
   TrPlan fp{}, ip{};
+  int th = UVG_B200_DCT2, tv = UVG_B200_DCT2, sw = 0, sh = 0;
   if (!use_trskip) {
-    int th, tv, sw, sh;
     // uvg_transform2d (transform.c:256): mts_dct when cfg.mts or non-square, else dct_NxN -
     // both are this matrix product; with mts off the types are DCT2/DCT2.
     derive_tr(w, h, color, cu_type, tr_idx, 0, 0, 0, cfg->mts, &th, &tv, &sw, &sh);
@@ -538,13 +518,20 @@ extern "C" int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, int
   a.rec_is_pred = (rec->base == pred->base && rec->stride == pred->stride &&
                    rec->col_pitch == pred->col_pitch && rec->row_pitch == pred->row_pitch &&
                    rec->blocks_per_row == pred->blocks_per_row);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // shape-specialised kernels first: registers-only for 4x4/8x8, tensor cores for 16x16/32x32
+  {
+    int rc = launch_fused_small(a, n_tus, q, cfg->bitdepth, th, tv, st);
+    if (rc >= 0) return rc;
+    rc = launch_fused_mma(a, n_tus, q, cfg->bitdepth, th, tv, sw, sh, st);
+    if (rc >= 0) return rc;
+  }
   const int slots = slots_for(q.area);
   const int mat_bytes = (fp.n1 * fp.n1 + fp.n2 * fp.n2 + ip.n1 * ip.n1 + ip.n2 * ip.n2 + 15) & ~15;
   const size_t smem = mat_bytes + (size_t)slots * 3 * q.area * sizeof(int16_t) + slots * 4 * sizeof(unsigned) + slots * 64;
   size_t grid = (n_tus + slots - 1) / slots;
   const size_t cap = (size_t)sm_count() * 8;
   if (grid > cap) grid = cap;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (cfg->bitdepth == 8) quantize_residual_kernel<uint8_t><<<(unsigned)grid, 256, smem, st>>>(a, n_tus, q, fp, ip, slots);
   else quantize_residual_kernel<uint16_t><<<(unsigned)grid, 256, smem, st>>>(a, n_tus, q, fp, ip, slots);
   UVGB_LAUNCH_CHECK();

@@ -1,0 +1,39 @@
+// quant.cuh - parameter blocks shared by the quant / fused kernels (quant.cu,
+// fused_small.cu, fused_mma.cu).
+#pragma once
+#include "transform.cuh"
+
+namespace uvgb {
+
+struct QParams {
+  int w, h, area;
+  // quant
+  int q_bits, add, q_bits8, coeff_default, coeff_list, signhide, lfnst_idx, max_lfnst;
+  const uint16_t *scan;
+  // dequant
+  int dq_shift, dq_scale, dq_add;
+  // reconstruction
+  int pixel_max, ssd_shift;
+};
+
+
+struct FusedArgs {
+  Blocks ref, pred, rec;
+  int16_t *coeff_out;
+  uint8_t *has_coeffs;
+  uint32_t *ssd;
+  uint32_t *cost;
+  unsigned w0, w1, w2, w3;   // fast_coeff_cost weights (Q8.8), rdo.c:440
+  int use_trskip, early_skip, rec_is_pred;
+};
+
+
+// Thread-per-TU register kernel for square 4x4 / 8x8 TUs (fused_small.cu). Returns -1 when
+// the shape/config is not covered (caller falls through to the general kernel).
+int launch_fused_small(const FusedArgs &a, size_t n_tus, const QParams &q, int bitdepth, int type_hor,
+                       int type_ver, cudaStream_t st);
+// Tensor-core (mma.sync) kernel for square 16x16 / 32x32 TUs (fused_mma.cu); -1 = not covered.
+int launch_fused_mma(const FusedArgs &a, size_t n_tus, const QParams &q, int bitdepth, int type_hor,
+                     int type_ver, int skip_w, int skip_h, cudaStream_t st);
+
+}  // namespace uvgb
