@@ -279,19 +279,30 @@ def gpu_arm(args):
                         O=U.Blocks.dense(rec.data_ptr(), n, n), bytes=nt * (5 * n * n + 9)))
     step_bytes = sum(x["bytes"] for x in rough) + sum(x["bytes"] for x in tus)
 
+    names = ["rough_cost 8x8 k=23 (rough_staged_kernel<8>)", "rough_cost 16x16 k=24 (rough_staged_kernel<16>)",
+             "quantize_residual 4x4 (fused_small_kernel<4>)", "quantize_residual 8x8 (fused_small_kernel<8>)",
+             "quantize_residual 16x16 (fused_mma_kernel<16>)", "quantize_residual 32x32 (fused_mma_kernel<32>)"]
+    kbytes = [x["bytes"] for x in rough] + [x["bytes"] for x in tus]
+
     def step(ev=None):
-        for i, x in enumerate(rough):
-            if ev is not None and i == 0:
-                ev[0].record()
+        """One frame: 6 launches. ev: 7 events bracketing each launch (timed region only)."""
+        i = 0
+        for x in rough:
+            if ev is not None:
+                ev[i].record()
             U.check(L.uvg_b200_rough_cost_dev(8, x["n"], C.byref(x["A"]), C.byref(x["B"]), x["out"].data_ptr(),
                                               x["nb"], x["k"], stream))
-            if ev is not None and i == 0:
-                ev[1].record()
+            i += 1
         for x in tus:
+            if ev is not None:
+                ev[i].record()
             U.check(L.uvg_b200_quantize_residual_dev(C.byref(cfg), 1, 0, x["n"], x["n"], 0, 0, 0, C.byref(x["R"]),
                                                      C.byref(x["P"]), C.byref(x["O"]), x["coeff"].data_ptr(),
                                                      x["has"].data_ptr(), x["ssd"].data_ptr(), x["cost"].data_ptr(),
                                                      COST_WEIGHTS, x["nt"], stream))
+            i += 1
+        if ev is not None:
+            ev[i].record()
 
     def barrier():
         if world > 1:
@@ -305,9 +316,9 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    # timed region: exactly K steps; the dominant kernel (rough cost 8x8) is bracketed by its own
-    # events inside the same region
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # timed region: exactly K steps; every launch is bracketed by events inside the same region so
+    # the dominant kernel's duration is measured live
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.uvg_b200_launch_count()
     barrier()
@@ -319,7 +330,7 @@ def gpu_arm(args):
     launches = L.uvg_b200_launch_count() - launches0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    per_kernel_ms = [float(np.mean([ev[i].elapsed_time(ev[i + 1]) for ev in kev])) for i in range(6)]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -335,11 +346,16 @@ def gpu_arm(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    dom = rough[0]
-    achieved = dom["bytes"] / (kms * 1e-3) / 1e9
-    roofline = {"kernel": "rough_cost_kernel<u8> n=8 k=23", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+    di = int(np.argmax(per_kernel_ms))
+    achieved = kbytes[di] / (per_kernel_ms[di] * 1e-3) / 1e9
+    roofline = {"kernel": names[di], "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "bytes_per_launch": dom["bytes"], "ms_per_launch": kms}
+                "bytes_per_launch": kbytes[di], "ms_per_launch": per_kernel_ms[di],
+                "share_of_step": per_kernel_ms[di] / (ms / args.steps),
+                "all_kernels_in_timed_region": [
+                    {"kernel": names[i], "ms": per_kernel_ms[i], "bytes": kbytes[i],
+                     "gbps": kbytes[i] / per_kernel_ms[i] / 1e6, "frac": kbytes[i] / per_kernel_ms[i] / 1e6 / hbm_peak}
+                    for i in range(6)]}
     extra = {}
     if rank == 0:
         extra["kernels"] = kernel_breakdown(torch, U, L, rough, tus, cfg, stream, hbm_peak)
@@ -460,15 +476,40 @@ def e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, d
     h2d = sum(x["o"].numel() + x["p"].numel() for x in hr) + sum(x["r"].numel() + x["p"].numel() for x in ht)
     d2h = sum(x["out"].numel() * 4 for x in hr) + sum(x["rec"].numel() + x["coeff"].numel() * 2 + x["nt"] * 9 for x in ht)
 
+    # The boundary is re-entrant (one stream + staging area per calling thread, like the encoder's
+    # worker threads): T host threads each push a contiguous slice of every batch through the
+    # *_host calls, so one slice's H2D overlaps another's kernels and D2H (PCIe is full duplex).
+    T = max(1, args.e2e_threads)
+
+    def rough_slice(x, w):
+        lo, hi = x["nb"] * w // T, x["nb"] * (w + 1) // T
+        n, k = x["n"], x["k"]
+        A = U.Blocks.dense(x["o"].data_ptr() + lo * n * n, n, n)
+        B = U.Blocks.dense(x["p"].data_ptr() + lo * k * n * n, n, n)
+        return (A, (hi - lo) * n * n, B, (hi - lo) * k * n * n, x["out"].data_ptr() + lo * k * 4, hi - lo)
+
+    def tu_slice(x, w):
+        lo, hi = x["nt"] * w // T, x["nt"] * (w + 1) // T
+        n = x["n"]; nn = n * n
+        R = U.Blocks.dense(x["r"].data_ptr() + lo * nn, n, n); P = U.Blocks.dense(x["p"].data_ptr() + lo * nn, n, n)
+        O = U.Blocks.dense(x["rec"].data_ptr() + lo * nn, n, n)
+        return (R, P, O, (hi - lo) * nn, x["coeff"].data_ptr() + lo * nn * 2, x["has"].data_ptr() + lo,
+                x["ssd"].data_ptr() + lo * 4, x["cost"].data_ptr() + lo * 4, hi - lo)
+    plans = [([rough_slice(x, w) for x in hr], [tu_slice(x, w) for x in ht]) for w in range(T)]
+
+    def work(w):
+        rs, ts = plans[w]
+        for x, (A, ab, B, bb, out, nb) in zip(hr, rs):
+            U.check(L.uvg_b200_rough_cost_host(8, x["n"], C.byref(A), ab, C.byref(B), bb, out, nb, x["k"]))
+        for x, (R, P, O, nbytes, coeff, has, ssd, cost, nt) in zip(ht, ts):
+            U.check(L.uvg_b200_quantize_residual_host(C.byref(cfg), 1, 0, x["n"], x["n"], 0, 0, 0, C.byref(R), nbytes,
+                                                      C.byref(P), nbytes, C.byref(O), nbytes, coeff, has, ssd, cost,
+                                                      COST_WEIGHTS, nt))
+    import concurrent.futures
+    pool = concurrent.futures.ThreadPoolExecutor(T)
+
     def step():
-        for x in hr:
-            U.check(L.uvg_b200_rough_cost_host(8, x["n"], C.byref(x["A"]), x["o"].numel(), C.byref(x["B"]),
-                                               x["p"].numel(), x["out"].data_ptr(), x["nb"], x["k"]))
-        for x in ht:
-            U.check(L.uvg_b200_quantize_residual_host(C.byref(cfg), 1, 0, x["n"], x["n"], 0, 0, 0, C.byref(x["R"]),
-                                                      x["r"].numel(), C.byref(x["P"]), x["p"].numel(), C.byref(x["O"]),
-                                                      x["rec"].numel(), x["coeff"].data_ptr(), x["has"].data_ptr(),
-                                                      x["ssd"].data_ptr(), x["cost"].data_ptr(), COST_WEIGHTS, x["nt"]))
+        list(pool.map(work, range(T)))
     k = max(3, min(args.steps, args.e2e_steps))
     for _ in range(2):
         step()
@@ -484,6 +525,7 @@ def e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, d
     secs = float(t.item())
     return {"value": n_ctu * world * k / secs, "unit": "CTU/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": k, "ms_per_step": 1e3 * secs / k,
+            "host_threads": T,
             "api": "uvg_b200_rough_cost_host + uvg_b200_quantize_residual_host (pinned host buffers)"}
 
 
@@ -496,6 +538,7 @@ def main():
     ap.add_argument("--ref-ctus", type=int, default=480, help="CTUs per step of the reference arm")
     ap.add_argument("--cpu-ctus", type=int, default=960, help="CTUs of the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the *_host calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -6,8 +6,12 @@
 // coalesced 8/16-byte loads, enough independent loads in flight per thread, packed 16-bit
 // butterflies for the 8-bit Hadamard, and grids sized in multiples of the SM count.
 #include "common.cuh"
+#include "hadamard.cuh"
 
 namespace uvgb {
+
+int launch_rough_staged(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_items, int k, int n,
+                        cudaStream_t st);
 
 // -------------------------------------------------------------------------------------
 // pixel loads
@@ -201,59 +205,17 @@ __device__ __forceinline__ unsigned satd4_sub(const Pix *o, int so, const Pix *c
 }
 
 // ---- 8x8 sub-block ------------------------------------------------------------------
-// 8-bit fast path: differences are 9-bit, the 8x8 Hadamard grows them by 6 bits -> every
-// intermediate fits int16, so two values travel in one 32-bit register in "packed-linear"
-// form word = hi*65536 + lo (lo signed, its borrow absorbed by hi). That form is closed
-// under 32-bit add/sub, i.e. every butterfly is ONE integer instruction for two values.
-// Packing (e_j, e_j+2) of a row in one word leaves exactly one butterfly stage (distance 2)
-// inside words; it is folded into the final sum through |a+b| + |a-b| = 2*max(|a|,|b|).
+// 8-bit fast path: packed 16-bit butterflies, see hadamard.cuh.
 __device__ __forceinline__ unsigned satd8_sub_u8(const uint8_t *o, int so, const uint8_t *c, int sc)
 {
-  // r[y][0..3] = packed words (e0,e2) (e1,e3) (e4,e6) (e5,e7) of row y of (o - c)
-  int r[8][4];
+  uint32_t wo[8][2], wc[8][2];
 #pragma unroll
   for (int y = 0; y < 8; ++y) {
-    uint32_t wo[2], wc[2];
-    load_words<uint8_t, 2>(o + (size_t)y * so, wo);
-    load_words<uint8_t, 2>(c + (size_t)y * sc, wc);
-#pragma unroll
-    for (int hw = 0; hw < 2; ++hw) {
-      // bytes b0 b1 b2 b3 -> (b0 | b2<<16) and (b1 | b3<<16)
-      const int oe = (int)__byte_perm(wo[hw], 0, 0x4240), oo = (int)__byte_perm(wo[hw], 0, 0x4341);
-      const int ce = (int)__byte_perm(wc[hw], 0, 0x4240), co = (int)__byte_perm(wc[hw], 0, 0x4341);
-      r[y][hw * 2 + 0] = oe - ce;   // packed-linear: (d_e0, d_e2)
-      r[y][hw * 2 + 1] = oo - co;   // (d_e1, d_e3)
-    }
-    // horizontal butterflies at distance 4 and 1 (word level)
-    int a0 = r[y][0] + r[y][2], a1 = r[y][1] + r[y][3], a2 = r[y][0] - r[y][2], a3 = r[y][1] - r[y][3];
-    r[y][0] = a0 + a1; r[y][1] = a0 - a1; r[y][2] = a2 + a3; r[y][3] = a2 - a3;
+    load_words<uint8_t, 2>(o + (size_t)y * so, wo[y]);
+    load_words<uint8_t, 2>(c + (size_t)y * sc, wc[y]);
   }
-  // vertical butterflies (distance 4, 2, 1 in y), word level
-#pragma unroll
-  for (int len = 4; len >= 1; len >>= 1)
-#pragma unroll
-    for (int i = 0; i < 8; i += len << 1)
-#pragma unroll
-      for (int j = i; j < i + len; ++j)
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const int a = r[j][x], b = r[j + len][x];
-          r[j][x] = a + b; r[j + len][x] = a - b;
-        }
-  // remaining stage (distance 2, inside words) + abs-sum: |lo+hi| + |lo-hi| = 2*max(|lo|,|hi|)
-  int s = 0, dc = 0;
-#pragma unroll
-  for (int y = 0; y < 8; ++y)
-#pragma unroll
-    for (int x = 0; x < 4; ++x) {
-      const int wv = r[y][x];
-      const int lo = (int)(short)(wv & 0xffff);
-      const int hi = (wv - lo) >> 16;
-      if (y == 0 && x == 0) dc = lo + hi;         // all-plus coefficient
-      s += max(abs(lo), abs(hi));
-    }
-  s = 2 * s - abs(dc) + (abs(dc) >> 2);
-  return (unsigned)((s + 2) >> 2);                 // :343-345
+  unsigned sad;
+  return satd8_words_u8<false>(wo, wc, sad);
 }
 
 template <typename Pix>
@@ -671,6 +633,11 @@ extern "C" int uvg_b200_rough_cost_dev(int bitdepth, int n, const uvg_b200_block
   const Blocks A = to_blocks(orig), B = to_blocks(preds);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n_items = n_blocks * (size_t)k;
+  if (bitdepth == 8) {
+    // dense, 16-byte aligned candidates: shared-memory staged kernel (rough.cu)
+    const int rc = launch_rough_staged(A, B, out, n_items, k, n, st);
+    if (rc >= 0) return rc;
+  }
   const int nsub = n == 4 ? 1 : (n / 8) * (n / 8);
   const int G = pick_group(nsub);
   const int block = 128;
