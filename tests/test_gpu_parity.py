@@ -395,7 +395,7 @@ def test_batched_quantize_residual_and_transform(bd, signhide):
     hi = 1 << bd
     dt = pix_dtype(bd)
     weights = (28 << 0) | (300 << 16) | (700 << 32) | (1100 << 48)
-    for (n, nt) in ((4, 300), (8, 130), (16, 40), (32, 9)):
+    for (n, nt) in ((4, 300), (8, 131), (16, 40), (32, 9)):
         for qp in (22, 37):
             ref = rng.integers(0, hi, nt * n * n).astype(dt)
             pred = np.clip(ref.astype(int) + rng.integers(-30, 31, nt * n * n), 0, hi - 1).astype(dt)

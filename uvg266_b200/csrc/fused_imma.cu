@@ -1,0 +1,456 @@
+// fused_imma.cu - quantize_residual for square 8x8 / 16x16 / 32x32 TUs (8-bit video) on the
+// INT8 tensor cores: the whole chain residual -> forward transform -> quant -> dequant ->
+// inverse transform -> reconstruction in ONE warp, entirely in registers, in exact integer
+// arithmetic (int8 x int8 -> int32 mma.sync.m16n8k16).
+//
+// Products (same chaining as fused_mma.cu: the C fragment of each product is the A or B
+// fragment of the next, so nothing leaves registers between the pixel loads and the stores):
+//   F1  D'  = Th * Xref^T + (-Th) * Xpred^T     pixel BYTES are the B operand - no residual ALU
+//   F2  Y^T = D' * Tv^T                          A = D' split into bytes (lo u8, hi s8)
+//       quant / dequant element-wise on fragments
+//   I1  U   = Tv^T * C                           B = dequantised coefficients, byte split
+//   I2  R   = U * Th                             A = U, byte split
+// A 16-bit value v = hi*256 + lo is multiplied as two byte planes with separate int32
+// accumulators recombined as accH*256 + accL: exact by construction (int32 accumulate, all
+// |sums| < 2^27). Rounding shifts, int16 wraps and clips of dct-generic.c run on the int32
+// accumulators between products.
+//
+// A thread's C fragment holds columns (2t, 2t+1) of each 8-wide tile, its A/B byte fragment
+// needs four consecutive contraction indices: the contraction index is therefore permuted
+// (slot 4t+e <-> column 8*(e>>1) + 2t + (e&1) of a 16-wide group) and the constant matrix
+// fragments are built with the same permutation. The output-column permutation of I2 makes
+// every thread reconstruct 4 CONTIGUOUS pixels of the rows it loaded for F1.
+//
+// 8x8 TUs: two TUs per warp, stacked in the M dimension with block-diagonal constant operands
+// (rows g <-> TU A, rows g+8 <-> TU B), so fragments are fully used.
+#include "quant.cuh"
+
+namespace uvgb {
+
+struct ImmaParams {
+  const int8_t *th, *tv;          // device matrices T[k*N+i]
+  int shift_f1, shift_f2, shift_i1, shift_i2;
+  int cut1, cut2;                 // forward zero-out: frequencies >= cut are zero (hor, ver)
+};
+
+// D(16x8,s32) += A(16x16 bytes) * B(16x8 bytes); AU/BU: operand is unsigned
+template <bool AU, bool BU>
+__device__ __forceinline__ void imma(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0)
+{
+  if (AU && !BU)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+  else if (!AU && BU)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+
+// bytes (lo plane, hi plane) of four 16-bit values held in int registers
+__device__ __forceinline__ void split4(int v0, int v1, int v2, int v3, uint32_t &lo, uint32_t &hi)
+{
+  const uint32_t p01 = __byte_perm((uint32_t)v0, (uint32_t)v1, 0x5410);   // v0.lo16 | v1.lo16 << 16
+  const uint32_t p23 = __byte_perm((uint32_t)v2, (uint32_t)v3, 0x5410);
+  lo = __byte_perm(p01, p23, 0x6420);
+  hi = __byte_perm(p01, p23, 0x7531);
+}
+
+__device__ __forceinline__ uint32_t pack4(int b0, int b1, int b2, int b3)
+{
+  return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
+}
+
+// contraction slot -> column inside a 16-wide group (C-fragment pairs of two adjacent 8-wide tiles)
+__device__ __forceinline__ int pi_col(int t, int e) { return 8 * (e >> 1) + 2 * t + (e & 1); }
+
+template <int N> struct ImmaShape {
+  static constexpr int MT = N >= 16 ? N / 16 : 1;
+  static constexpr int NT = N / 8;
+  static constexpr int KT = N >= 16 ? N / 16 : 1;
+  static constexpr int TUS = N >= 16 ? 1 : 2;        // TUs per warp
+};
+
+template <int N>
+__global__ void __launch_bounds__(128)
+fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
+{
+  using S = ImmaShape<N>;
+  constexpr int MT = S::MT, NT = S::NT, KT = S::KT;
+  // constant operand fragments, [tile][reg][lane]
+  __shared__ uint32_t sAH[MT * KT * 2 * 32];     // F1  A =  Th        (natural contraction order: pixel columns)
+  __shared__ uint32_t sANH[MT * KT * 2 * 32];    // F1  A = -Th
+  __shared__ uint32_t sBV[KT * NT * 32];         // F2  B = Tv^T       (contraction permuted by pi)
+  __shared__ uint32_t sAVT[MT * KT * 2 * 32];    // I1  A = Tv^T       (contraction permuted by pi)
+  __shared__ uint32_t sBH[KT * NT * 32];         // I2  B = Th         (contraction pi, output columns sigma)
+
+  for (int e0 = threadIdx.x; e0 < MT * KT * 2 * 32; e0 += blockDim.x) {
+    const int ln = e0 & 31, r = (e0 >> 5) & 1, tile = e0 >> 6, kt = tile % KT, mt = tile / KT;
+    const int g = ln >> 2, t = ln & 3;
+    int bh[4], bv[4];
+    if (N >= 16) {
+      const int row = mt * 16 + g + 8 * r;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        bh[e] = p.th[row * N + kt * 16 + 4 * t + e];                       // Th[k=row][i]
+        bv[e] = p.tv[(kt * 16 + pi_col(t, e)) * N + row];                  // Tv[kv][iv=row]
+      }
+    } else {
+      // block diagonal: row g -> TU A (r = 0), row g+8 -> TU B (r = 1)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ks = 4 * t + e;                                          // F1 slot: K 0-7 TU A pixels, 8-15 TU B pixels
+        bh[e] = ((ks >> 3) == r) ? p.th[g * N + (ks & 7)] : 0;
+        // I1 slot e<2 -> (TU A, kv = 2t+e), e>=2 -> (TU B, kv = 2t+e-2)
+        bv[e] = ((e >> 1) == r) ? p.tv[(2 * t + (e & 1)) * N + g] : 0;
+      }
+    }
+    sAH[e0] = pack4(bh[0], bh[1], bh[2], bh[3]);
+    sANH[e0] = pack4(-bh[0], -bh[1], -bh[2], -bh[3]);
+    sAVT[e0] = pack4(bv[0], bv[1], bv[2], bv[3]);
+  }
+  for (int e0 = threadIdx.x; e0 < KT * NT * 32; e0 += blockDim.x) {
+    const int ln = e0 & 31, tile = e0 >> 5, nt = tile % NT, kt = tile / NT;
+    const int g = ln >> 2, t = ln & 3;
+    int bv[4], bh[4];
+    if (N >= 16) {
+      const int kv = nt * 8 + g;
+      const int ih = 16 * (nt >> 1) + 4 * (g >> 1) + 2 * (nt & 1) + (g & 1);   // sigma: output column slot -> pixel column
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kk = kt * 16 + pi_col(t, e);
+        bv[e] = p.tv[kv * N + kk];                                         // B[j][kv] = Tv[kv][j]
+        bh[e] = p.th[kk * N + ih];                                         // B[kh][ih] = Th[kh][ih]
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        bv[e] = e < 2 ? p.tv[g * N + 2 * t + e] : 0;                       // F2: A slots e>=2 are zero padding
+        bh[e] = e < 2 ? p.th[(2 * t + e) * N + g] : 0;                     // I2
+      }
+    }
+    sBV[e0] = pack4(bv[0], bv[1], bv[2], bv[3]);
+    sBH[e0] = pack4(bh[0], bh[1], bh[2], bh[3]);
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
+  const int add_f1 = p.shift_f1 > 0 ? 1 << (p.shift_f1 - 1) : 0;
+  const int add_f2 = 1 << (p.shift_f2 - 1), add_i1 = 1 << (p.shift_i1 - 1), add_i2 = 1 << (p.shift_i2 - 1);
+  const size_t n_units = (n_tus + S::TUS - 1) / S::TUS;
+
+  for (size_t unit = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < n_units; unit += warps_total) {
+    // ---- pixel loads -------------------------------------------------------------------
+    // N >= 16: row tile nt (rows nt*8+g), column group kt: pixels kt*16+4t..+3 of TU `unit`
+    // N == 8 : TU 2*unit + (t>>1), row g, pixels 4*(t&1)..+3
+    uint32_t refw[NT][KT], predw[NT][KT];
+    const uint8_t *pref, *ppred; uint8_t *prec;
+    size_t tu0 = unit * S::TUS;
+    bool tu_valid = true;
+    if (N >= 16) {
+      pref = static_cast<const uint8_t *>(a.ref.base) + a.ref.offset(tu0);
+      ppred = static_cast<const uint8_t *>(a.pred.base) + a.pred.offset(tu0);
+      prec = const_cast<uint8_t *>(static_cast<const uint8_t *>(a.rec.base)) + a.rec.offset(tu0);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          refw[nt][kt] = __ldg(reinterpret_cast<const uint32_t *>(pref + (size_t)(nt * 8 + g) * a.ref.stride + kt * 16 + 4 * t));
+          predw[nt][kt] = __ldg(reinterpret_cast<const uint32_t *>(ppred + (size_t)(nt * 8 + g) * a.pred.stride + kt * 16 + 4 * t));
+        }
+    } else {
+      const size_t mytu = tu0 + (t >> 1);
+      tu_valid = mytu < n_tus;
+      const size_t ltu = tu_valid ? mytu : tu0;
+      pref = static_cast<const uint8_t *>(a.ref.base) + a.ref.offset(ltu);
+      ppred = static_cast<const uint8_t *>(a.pred.base) + a.pred.offset(ltu);
+      prec = const_cast<uint8_t *>(static_cast<const uint8_t *>(a.rec.base)) + a.rec.offset(ltu);
+      refw[0][0] = __ldg(reinterpret_cast<const uint32_t *>(pref + (size_t)g * a.ref.stride + 4 * (t & 1)));
+      predw[0][0] = __ldg(reinterpret_cast<const uint32_t *>(ppred + (size_t)g * a.pred.stride + 4 * (t & 1)));
+      if (!tu_valid) predw[0][0] = refw[0][0];        // odd tail: the phantom TU has zero residual
+    }
+
+    // ---- F1 ----------------------------------------------------------------------------
+    int v[MT][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        int acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          const int fi = ((mt * KT + kt) * 2) * 32 + lane;
+          imma<false, true>(acc, sAH[fi], sAH[fi + 32], refw[nt][kt]);
+          imma<false, true>(acc, sANH[fi], sANH[fi + 32], predw[nt][kt]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = N >= 16 ? mt * 16 + g + 8 * (c >> 1) : g;
+          const int s = (int)(short)((acc[c] + add_f1) >> p.shift_f1);
+          v[mt][nt][c] = k < p.cut1 ? s : 0;
+        }
+      }
+
+    // ---- F2 ----------------------------------------------------------------------------
+    {
+      int y[MT][NT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        int accL[NT][4], accH[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { accL[nt][c] = 0; accH[nt][c] = 0; }
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          uint32_t lo0, hi0, lo1, hi1;
+          if (N >= 16) {
+            split4(v[mt][2 * kt][0], v[mt][2 * kt][1], v[mt][2 * kt + 1][0], v[mt][2 * kt + 1][1], lo0, hi0);   // row g
+            split4(v[mt][2 * kt][2], v[mt][2 * kt][3], v[mt][2 * kt + 1][2], v[mt][2 * kt + 1][3], lo1, hi1);   // row g+8
+          } else {
+            split4(v[0][0][0], v[0][0][1], 0, 0, lo0, hi0);
+            split4(v[0][0][2], v[0][0][3], 0, 0, lo1, hi1);
+          }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const uint32_t b0 = sBV[(kt * NT + nt) * 32 + lane];
+            imma<true, false>(accL[nt], lo0, lo1, b0);
+            imma<false, false>(accH[nt], hi0, hi1, b0);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int kv = nt * 8 + 2 * t + (c & 1);
+            const int s = (int)(short)((accH[nt][c] * 256 + accL[nt][c] + add_f2) >> p.shift_f2);
+            y[mt][nt][c] = kv < p.cut2 ? s : 0;
+          }
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[mt][nt][c] = y[mt][nt][c];
+    }
+
+    // ---- quant, coefficients out, cost, dequant ------------------------------------------
+    // N >= 16: one TU; N == 8: c0,c1 belong to TU A (rows g), c2,c3 to TU B (rows g+8)
+    unsigned nzA = 0, nzB = 0, costA = 0, costB = 0;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int cf = v[mt][nt][c];
+          const unsigned av = (unsigned)abs(cf);
+          int level = (int)((av * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits);
+          level = cf < 0 ? -level : level;
+          level = clip3(-32768, 32767, level);
+          const int kv = nt * 8 + 2 * t + (c & 1);
+          const unsigned al = min((unsigned)abs(level), 3u);
+          const unsigned wgt = al == 0 ? a.w0 : al == 1 ? a.w1 : al == 2 ? a.w2 : a.w3;
+          if (N >= 16) {
+            const int kh = mt * 16 + g + 8 * (c >> 1);
+            a.coeff_out[tu0 * (size_t)(N * N) + kv * N + kh] = (int16_t)level;
+            nzA |= (unsigned)(level != 0); costA += wgt;
+          } else {
+            const size_t tuc = tu0 + (c >> 1);
+            if (tuc < n_tus) a.coeff_out[tuc * (size_t)(N * N) + kv * N + g] = (int16_t)level;
+            if (c >> 1) { nzB |= (unsigned)(level != 0); costB += wgt; } else { nzA |= (unsigned)(level != 0); costA += wgt; }
+          }
+          v[mt][nt][c] = clip3(-32768, 32767, (level * q.dq_scale + q.dq_add) >> q.dq_shift);   // dequant
+        }
+    const bool hasA = __any_sync(0xffffffffu, nzA != 0);
+    const bool hasB = N >= 16 ? false : __any_sync(0xffffffffu, nzB != 0);
+    if (a.cost) {
+      costA = (unsigned)warp_sum((int)costA);
+      if (N < 16) costB = (unsigned)warp_sum((int)costB);
+      if (lane == 0) {
+        a.cost[tu0] = (costA + 128u) >> 8;
+        if (N < 16 && tu0 + 1 < n_tus) a.cost[tu0 + 1] = (costB + 128u) >> 8;
+      }
+    }
+    if (lane == 0) {
+      a.has_coeffs[tu0] = hasA ? 1 : 0;
+      if (N < 16 && tu0 + 1 < n_tus) a.has_coeffs[tu0 + 1] = hasB ? 1 : 0;
+    }
+    const bool any_recon = (hasA || hasB) && !a.early_skip;
+
+    // ---- I1 + I2 (skipped when no TU of the warp has coefficients) --------------------------
+    int rr[MT][NT][4];
+    if (any_recon) {
+      int u[MT][NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        int accL[MT][4], accH[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { accL[mt][c] = 0; accH[mt][c] = 0; }
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          uint32_t lo, hi;
+          if (N >= 16) {
+            const int h2 = 2 * (nt & 1);
+            split4(v[nt >> 1][2 * kt][h2], v[nt >> 1][2 * kt][h2 + 1], v[nt >> 1][2 * kt + 1][h2], v[nt >> 1][2 * kt + 1][h2 + 1], lo, hi);
+          } else {
+            split4(v[0][0][0], v[0][0][1], v[0][0][2], v[0][0][3], lo, hi);
+          }
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int fi = ((mt * KT + kt) * 2) * 32 + lane;
+            imma<false, true>(accL[mt], sAVT[fi], sAVT[fi + 32], lo);
+            imma<false, false>(accH[mt], sAVT[fi], sAVT[fi + 32], hi);
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            u[mt][nt][c] = clip3(-32768, 32767, (accH[mt][c] * 256 + accL[mt][c] + add_i1) >> p.shift_i1);
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        int accL[NT][4], accH[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { accL[nt][c] = 0; accH[nt][c] = 0; }
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          uint32_t lo0, hi0, lo1, hi1;
+          if (N >= 16) {
+            split4(u[mt][2 * kt][0], u[mt][2 * kt][1], u[mt][2 * kt + 1][0], u[mt][2 * kt + 1][1], lo0, hi0);
+            split4(u[mt][2 * kt][2], u[mt][2 * kt][3], u[mt][2 * kt + 1][2], u[mt][2 * kt + 1][3], lo1, hi1);
+          } else {
+            split4(u[0][0][0], u[0][0][1], 0, 0, lo0, hi0);
+            split4(u[0][0][2], u[0][0][3], 0, 0, lo1, hi1);
+          }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const uint32_t b0 = sBH[(kt * NT + nt) * 32 + lane];
+            imma<true, false>(accL[nt], lo0, lo1, b0);
+            imma<false, false>(accH[nt], hi0, hi1, b0);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            rr[mt][nt][c] = clip3(-32768, 32767, (accH[nt][c] * 256 + accL[nt][c] + add_i2) >> p.shift_i2);
+      }
+    }
+
+    // ---- reconstruction + SSD ------------------------------------------------------------
+    if (N >= 16) {
+      const bool recon = any_recon;
+      unsigned ssd = 0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)          // row tile of the pixel words
+#pragma unroll
+        for (int qs = 0; qs < KT; ++qs) {
+          const int mt = nt >> 1, hh = nt & 1;
+          uint32_t outw = predw[nt][qs];
+          if (recon) {
+            int px[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int r = rr[mt][2 * qs + (e >> 1)][2 * hh + (e & 1)];
+              px[e] = clip3(0, q.pixel_max, (int)(short)(r + (int)((predw[nt][qs] >> (8 * e)) & 0xffu)));
+            }
+            outw = pack4(px[0], px[1], px[2], px[3]);
+          }
+          if (recon || !a.rec_is_pred)
+            *reinterpret_cast<uint32_t *>(prec + (size_t)(nt * 8 + g) * a.rec.stride + qs * 16 + 4 * t) = outw;
+          const uint32_t d4 = __vabsdiffu4(refw[nt][qs], outw);
+          ssd = __dp4a(d4, d4, ssd);
+        }
+      if (a.ssd) {
+        ssd = (unsigned)warp_sum((int)ssd);
+        if (lane == 0) a.ssd[tu0] = (uint32_t)((int32_t)ssd >> q.ssd_shift);
+      }
+    } else {
+      // thread holds (TU A, row g, px 2t,2t+1) in rr[..][0],[1] and (TU B, row g, px 2t,2t+1) in [2],[3];
+      // pred/ref words live in lane (g, TU*2 + (t>>1)): px 4*(t>>1).. -> fetch and pick the half
+      const uint32_t pA = __shfl_sync(0xffffffffu, predw[0][0], (g << 2) | (t >> 1));
+      const uint32_t pB = __shfl_sync(0xffffffffu, predw[0][0], (g << 2) | 2 | (t >> 1));
+      const uint32_t rA = __shfl_sync(0xffffffffu, refw[0][0], (g << 2) | (t >> 1));
+      const uint32_t rB = __shfl_sync(0xffffffffu, refw[0][0], (g << 2) | 2 | (t >> 1));
+      const int sh = 16 * (t & 1);
+      unsigned ssdA = 0, ssdB = 0;
+#pragma unroll
+      for (int tb = 0; tb < 2; ++tb) {
+        const bool recon = (tb ? hasB : hasA) && !a.early_skip;
+        const uint32_t pw = ((tb ? pB : pA) >> sh) & 0xffffu, rw = ((tb ? rB : rA) >> sh) & 0xffffu;
+        uint32_t ow = pw;
+        if (recon) {
+          const int x0 = clip3(0, q.pixel_max, (int)(short)(rr[0][0][2 * tb] + (int)(pw & 0xffu)));
+          const int x1 = clip3(0, q.pixel_max, (int)(short)(rr[0][0][2 * tb + 1] + (int)(pw >> 8)));
+          ow = (uint32_t)x0 | ((uint32_t)x1 << 8);
+        }
+        const size_t tuc = tu0 + tb;
+        if (tuc < n_tus && (recon || !a.rec_is_pred)) {
+          uint8_t *dst = const_cast<uint8_t *>(static_cast<const uint8_t *>(a.rec.base)) + a.rec.offset(tuc) +
+                         (size_t)g * a.rec.stride + 2 * t;
+          *reinterpret_cast<uint16_t *>(dst) = (uint16_t)ow;
+        }
+        const uint32_t d4 = __vabsdiffu4(rw, ow);
+        if (tb) ssdB = __dp4a(d4, d4, ssdB); else ssdA = __dp4a(d4, d4, ssdA);
+      }
+      if (a.ssd) {
+        ssdA = (unsigned)warp_sum((int)ssdA); ssdB = (unsigned)warp_sum((int)ssdB);
+        if (lane == 0) {
+          a.ssd[tu0] = (uint32_t)((int32_t)ssdA >> q.ssd_shift);
+          if (tu0 + 1 < n_tus) a.ssd[tu0 + 1] = (uint32_t)((int32_t)ssdB >> q.ssd_shift);
+        }
+      }
+    }
+  }
+}
+
+template <int N>
+static int launch_imma(const FusedArgs &a, size_t n_tus, const QParams &q, const ImmaParams &p, cudaStream_t st)
+{
+  const int warps_per_block = 4;
+  const size_t n_units = (n_tus + ImmaShape<N>::TUS - 1) / ImmaShape<N>::TUS;
+  size_t grid = (n_units + warps_per_block - 1) / warps_per_block;
+  const size_t cap = (size_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  fused_imma_kernel<N><<<(unsigned)grid, warps_per_block * 32, 0, st>>>(a, n_tus, q, p);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+static bool word_aligned(const Blocks &b, int n)
+{
+  // every row start must be 4-byte aligned (8x8 rec stores need 2-byte alignment only, covered)
+  return (reinterpret_cast<uintptr_t>(b.base) & 3) == 0 && (b.stride & 3) == 0 && (b.col_pitch & 3) == 0 &&
+         (b.row_pitch & 3) == 0 && n % 4 == 0;
+}
+
+// 8-bit video, square 8/16/32, no sign hiding / transform skip, word-aligned rows. -1 = not covered.
+int launch_fused_imma(const FusedArgs &a, size_t n_tus, const QParams &q, int bitdepth, int th, int tv, int skip_w,
+                      int skip_h, cudaStream_t st)
+{
+  if (bitdepth != 8 || q.w != q.h || (q.w != 8 && q.w != 16 && q.w != 32)) return -1;
+  if (q.signhide || q.lfnst_idx || a.use_trskip) return -1;
+  if (!word_aligned(a.ref, q.w) || !word_aligned(a.pred, q.w) || !word_aligned(a.rec, q.w)) return -1;
+  const int N = q.w, l2 = ilog2_host(N);
+  ImmaParams p;
+  p.th = tr_matrix_dev(th, N); p.tv = tr_matrix_dev(tv, N);
+  p.shift_f1 = l2 - 1 + bitdepth - 8; p.shift_f2 = l2 + 6; p.shift_i1 = 7; p.shift_i2 = 20 - bitdepth;
+  p.cut1 = (th == UVG_B200_DCT2 || N < 8) ? N : N - skip_w;
+  p.cut2 = (tv == UVG_B200_DCT2 || N < 8) ? N : N - skip_h;
+  switch (N) {
+    case 8: return launch_imma<8>(a, n_tus, q, p, st);
+    case 16: return launch_imma<16>(a, n_tus, q, p, st);
+    default: return launch_imma<32>(a, n_tus, q, p, st);
+  }
+}
+
+}  // namespace uvgb

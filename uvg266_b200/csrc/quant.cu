@@ -6,6 +6,8 @@
 #include "transform.cuh"
 #include "quant.cuh"
 #include <mutex>
+#include <string.h>
+#include <stdlib.h>
 
 namespace uvgb {
 
@@ -521,9 +523,14 @@ extern "C" int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // shape-specialised kernels first: registers-only for 4x4/8x8, tensor cores for 16x16/32x32
   {
-    int rc = launch_fused_small(a, n_tus, q, cfg->bitdepth, th, tv, st);
+    // UVG266_B200_FUSED = imma | small | hmma | generic restricts the choice (A/B measurements)
+    static const char *force = getenv("UVG266_B200_FUSED");
+    int rc = -1;
+    if (!force || !strcmp(force, "imma")) rc = launch_fused_imma(a, n_tus, q, cfg->bitdepth, th, tv, sw, sh, st);
     if (rc >= 0) return rc;
-    rc = launch_fused_mma(a, n_tus, q, cfg->bitdepth, th, tv, sw, sh, st);
+    if (!force || !strcmp(force, "small") || (!strcmp(force, "imma") && q.w == 4)) rc = launch_fused_small(a, n_tus, q, cfg->bitdepth, th, tv, st);
+    if (rc >= 0) return rc;
+    if (!force || !strcmp(force, "hmma")) rc = launch_fused_mma(a, n_tus, q, cfg->bitdepth, th, tv, sw, sh, st);
     if (rc >= 0) return rc;
   }
   const int slots = slots_for(q.area);

@@ -36,4 +36,8 @@ int launch_fused_small(const FusedArgs &a, size_t n_tus, const QParams &q, int b
 int launch_fused_mma(const FusedArgs &a, size_t n_tus, const QParams &q, int bitdepth, int type_hor,
                      int type_ver, int skip_w, int skip_h, cudaStream_t st);
 
+// INT8 tensor-core kernel for 8-bit square 8x8 / 16x16 / 32x32 TUs (fused_imma.cu); -1 = not covered.
+int launch_fused_imma(const FusedArgs &a, size_t n_tus, const QParams &q, int bitdepth, int type_hor,
+                      int type_ver, int skip_w, int skip_h, cudaStream_t st);
+
 }  // namespace uvgb
