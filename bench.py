@@ -370,10 +370,13 @@ def gpu_arm(args):
             arm = CpuArm(args.cpu_ctus)
             cores = host_cores()
             arm.run(cores)
-            secs = min(arm.run(cores) for _ in range(3))
+            runs = [arm.run(cores) for _ in range(5)]
+            secs = sum(runs) / len(runs)
             cpu_baseline = {"value": arm.n_ctu / secs, "unit": "CTU/s", "cores": cores, "kind": arm.kind,
-                            "sample": "%d CTUs of the same workload, best of 3, generic-C strategies of the "
-                                      "unmodified reference (oracle/_ref), %d pthreads" % (arm.n_ctu, cores)}
+                            "best": arm.n_ctu / min(runs),
+                            "sample": "%d CTUs of the same workload, mean of 5 passes after 1 warm-up, generic-C "
+                                      "strategies of the unmodified reference (oracle/_ref), %d pthreads, dynamic "
+                                      "4-CTU work units" % (arm.n_ctu, cores)}
             s1 = arm.run(1)
             cpu_baseline["value_1thread"] = arm.n_ctu / s1
         except Exception as exc:  # reported, never silently replaced
@@ -535,8 +538,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-ctus", type=int, default=480, help="CTUs per step of the reference arm")
-    ap.add_argument("--cpu-ctus", type=int, default=960, help="CTUs of the cpu_baseline sample")
+    ap.add_argument("--ref-ctus", type=int, default=2040, help="CTUs per step of the reference arm")
+    ap.add_argument("--cpu-ctus", type=int, default=2040, help="CTUs of the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the *_host calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -234,20 +234,19 @@ typedef struct {
   uint32_t *const *tu_ssd;              /* [level] -> [ctu][count] */
   uint32_t *const *tu_cost;             /* [level] -> [ctu][count] (fast_coeff_cost) */
   uint64_t weights;
+  int *next_unit;                       /* shared work counter */
 } refh_job_t;
 
-static void *ctu_pass_worker(void *arg)
+/* Work is handed out dynamically: unit u = (level, chunk of CTU_CHUNK CTUs), popped from one
+ * atomic counter, so a thread that is scheduled late (or shares a core) does not stall the
+ * step - the same load balancing the encoder's own threadqueue gives its per-CTU jobs. */
+#define CTU_CHUNK 4
+static void ctu_pass_range(refh_job_t *j, int level, int c0, int c1)
 {
-  refh_job_t *j = arg;
   cu_info_t cu;
   fill_cu(&cu, CU_INTRA, 0, 0, 0, 0);
-  quant_residual_func *qr = refh_get("quantize_residual", j->strategy);
-  pixels_calc_ssd_func *ssd = refh_get("pixels_calc_ssd", j->strategy);
-  fast_coeff_cost_func *fcc = refh_get("fast_coeff_cost", j->strategy);
-  if (!fcc) fcc = refh_get("fast_coeff_cost", "generic");
-  if (!qr) qr = refh_get("quantize_residual", "generic");
-  if (!ssd) ssd = refh_get("pixels_calc_ssd", "generic");
-  for (int l = 0; l < j->n_rough; ++l) {
+  if (level < j->n_rough) {
+    const int l = level;
     const int n = j->rough[l].n, cnt = j->rough[l].count, modes = j->rough[l].modes;
     char tname[32];
     snprintf(tname, sizeof tname, "satd_%dx%d_dual", n, n);
@@ -260,7 +259,7 @@ static void *ctu_pass_worker(void *arg)
      * apart (strategies-picture.h:48, search_intra.c:1012); copy pairs into such a buffer
      * like the encoder's rough search does when it predicts into preds[0..1]. */
     ALIGNED(64) uvg_pixel pb[2][32 * 32];
-    for (int c = j->ctu_begin; c < j->ctu_end; ++c) {
+    for (int c = c0; c < c1; ++c) {
       for (int b = 0; b < cnt; ++b) {
         const size_t bi = (size_t)c * cnt + b;
         const uvg_pixel *orig = j->rough_orig[l] + bi * n * n;
@@ -280,22 +279,43 @@ static void *ctu_pass_worker(void *arg)
         }
       }
     }
+    return;
   }
-  for (int l = 0; l < j->n_tu; ++l) {
-    const int n = j->tu[l].n, cnt = j->tu[l].count;
-    for (int c = j->ctu_begin; c < j->ctu_end; ++c) {
-      for (int b = 0; b < cnt; ++b) {
-        const size_t bi = (size_t)c * cnt + b;
-        const uvg_pixel *ref = j->tu_ref[l] + bi * n * n;
-        const uvg_pixel *pred = j->tu_pred[l] + bi * n * n;
-        uvg_pixel *rec = j->tu_rec[l] + bi * n * n;
-        int16_t *coeff = j->tu_coeff[l] + bi * n * n;
-        qr(g_state, &cu, n, n, COLOR_Y, SCAN_DIAG, 0, n, n, ref, pred, rec, coeff, false, 0,
-           UVG_BOTH_T);
-        j->tu_ssd[l][bi] = ssd(ref, rec, n, n, n, n);
-        j->tu_cost[l][bi] = fcc(coeff, n, n, j->weights);
-      }
+  const int l = level - j->n_rough;
+  quant_residual_func *qr = refh_get("quantize_residual", j->strategy);
+  pixels_calc_ssd_func *ssd = refh_get("pixels_calc_ssd", j->strategy);
+  fast_coeff_cost_func *fcc = refh_get("fast_coeff_cost", j->strategy);
+  if (!fcc) fcc = refh_get("fast_coeff_cost", "generic");
+  if (!qr) qr = refh_get("quantize_residual", "generic");
+  if (!ssd) ssd = refh_get("pixels_calc_ssd", "generic");
+  const int n = j->tu[l].n, cnt = j->tu[l].count;
+  for (int c = c0; c < c1; ++c) {
+    for (int b = 0; b < cnt; ++b) {
+      const size_t bi = (size_t)c * cnt + b;
+      const uvg_pixel *ref = j->tu_ref[l] + bi * n * n;
+      const uvg_pixel *pred = j->tu_pred[l] + bi * n * n;
+      uvg_pixel *rec = j->tu_rec[l] + bi * n * n;
+      int16_t *coeff = j->tu_coeff[l] + bi * n * n;
+      qr(g_state, &cu, n, n, COLOR_Y, SCAN_DIAG, 0, n, n, ref, pred, rec, coeff, false, 0,
+         UVG_BOTH_T);
+      j->tu_ssd[l][bi] = ssd(ref, rec, n, n, n, n);
+      j->tu_cost[l][bi] = fcc(coeff, n, n, j->weights);
     }
+  }
+}
+
+static void *ctu_pass_worker(void *arg)
+{
+  refh_job_t *j = arg;
+  const int n_ctu = j->ctu_end;
+  const int chunks = (n_ctu + CTU_CHUNK - 1) / CTU_CHUNK;
+  const int n_units = chunks * (j->n_rough + j->n_tu);
+  for (;;) {
+    const int u = __atomic_fetch_add(j->next_unit, 1, __ATOMIC_RELAXED);
+    if (u >= n_units) break;
+    const int level = u / chunks, ch = u % chunks;
+    const int c0 = ch * CTU_CHUNK, c1 = MIN(n_ctu, c0 + CTU_CHUNK);
+    ctu_pass_range(j, level, c0, c1);
   }
   return NULL;
 }
@@ -314,12 +334,14 @@ double refh_ctu_pass(const char *strategy, int threads, int n_ctu,
   pthread_t *th = calloc(threads, sizeof(*th));
   refh_job_t *jobs = calloc(threads, sizeof(*jobs));
   struct timespec t0, t1;
+  int next_unit = 0;
   clock_gettime(CLOCK_MONOTONIC, &t0);
   for (int t = 0; t < threads; ++t) {
     refh_job_t *j = &jobs[t];
     j->strategy = strategy;
-    j->ctu_begin = (int)((long long)n_ctu * t / threads);
-    j->ctu_end = (int)((long long)n_ctu * (t + 1) / threads);
+    j->ctu_begin = 0;
+    j->ctu_end = n_ctu;
+    j->next_unit = &next_unit;
     j->n_rough = n_rough; j->rough = rough;
     j->rough_orig = rough_orig; j->rough_pred = rough_pred; j->rough_cost = rough_cost;
     j->n_tu = n_tu; j->tu = tu;

@@ -12,6 +12,9 @@ namespace uvgb {
 
 int launch_rough_staged(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_items, int k, int n,
                         cudaStream_t st);
+int launch_sad_search_u8(const uint8_t *cur, const uint8_t *ref, int pic_w, int pic_h, int stride,
+                         const int32_t *cur_x, const int32_t *cur_y, const int32_t *mv_x, const int32_t *mv_y,
+                         int range, int w, int h, uint32_t *out, size_t n_blocks, cudaStream_t st);
 
 // -------------------------------------------------------------------------------------
 // pixel loads
@@ -691,6 +694,12 @@ extern "C" int uvg_b200_sad_search_dev(int bitdepth, int w, int h, const void *c
   if (check_dims(bitdepth, w, h, 1)) return 1;
   if (range < 0 || range > 64) { set_error("search range %d out of [0,64]", range); return 1; }
   if (n_blocks == 0) return 0;
+  if (bitdepth == 8) {
+    const int rc = launch_sad_search_u8(static_cast<const uint8_t *>(cur), static_cast<const uint8_t *>(ref), pic_w,
+                                        pic_h, stride, cur_x, cur_y, mv_x, mv_y, range, w, h, out, n_blocks,
+                                        static_cast<cudaStream_t>(stream));
+    if (rc >= 0) return rc;
+  }
   const int pix = bitdepth == 8 ? 1 : 2;
   const size_t smem = ((size_t)(w + 2 * range + 1) * (h + 2 * range) + (size_t)w * h) * pix;
   if (smem > 227 * 1024) { set_error("search window does not fit shared memory"); return 1; }
