@@ -347,9 +347,16 @@ def gpu_arm(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     di = int(np.argmax(per_kernel_ms))
+    traffic = None
+    try:   # DRAM bytes per launch of the same kernel on the same inputs, from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["bytes_per_launch"]
+        key = names[di].split("(")[1].rstrip(")").rstrip(">")          # e.g. "rough_staged_kernel<16"
+        traffic = next((v for k, v in tr.items() if key in k.replace("unsigned char, ", "")), None)
+    except (OSError, KeyError, IndexError):
+        pass
     achieved = kbytes[di] / (per_kernel_ms[di] * 1e-3) / 1e9
     roofline = {"kernel": names[di], "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": kbytes[di], "ms_per_launch": per_kernel_ms[di],
                 "share_of_step": per_kernel_ms[di] / (ms / args.steps),
                 "all_kernels_in_timed_region": [
