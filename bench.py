@@ -140,10 +140,31 @@ class RefLevel(C.Structure):
 
 
 def host_cores():
+    """Host threads the process can actually use: the affinity mask, capped by the container's
+    CPU bandwidth quota (cgroup cpu.max / cfs_quota). On the GPU boxes 128 logical CPUs are
+    visible but the quota is ~16 CPUs: running 128 busy threads just gets the process throttled
+    for the rest of every 100 ms period (measured: passes alternate between 170 k and 20 k CTU/s,
+    sustained 41 k CTU/s for any thread count >= 16; tools/cpu_scaling.py)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except (OSError, ValueError):
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except (OSError, ValueError):
+            pass
+    if quota:
+        n = max(1, min(n, int(quota + 0.999)))
+    return n
 
 
 class CpuArm:
@@ -400,7 +421,7 @@ def gpu_arm(args):
                        "ctus_per_step_per_gpu": n_ctu, "qp": QP, "sharding": "CTU-row bands, no collective",
                        "l2": "inputs %.0f MB per step >> 126 MB L2, no flush" % (step_bytes / 1e6),
                        "algorithmic_bytes_per_step": step_bytes},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches) * world,
             "clocks": clocks, "step_gbps": step_bytes * args.steps / (ms_max * 1e-3) / 1e9,
         }
         line.update(extra)

@@ -12,11 +12,14 @@
  * It is compiled against the reference headers where they lie; no reference source
  * is copied.
  */
+#define _GNU_SOURCE
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sched.h>
 #include <pthread.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "global.h"
 #include "uvg266.h"
@@ -235,6 +238,8 @@ typedef struct {
   uint32_t *const *tu_cost;             /* [level] -> [ctu][count] (fast_coeff_cost) */
   uint64_t weights;
   int *next_unit;                       /* shared work counter */
+  int pin_cpu;                          /* unused */
+  int static_threads, worker_id;        /* static_threads > 0: static CTU slices */
 } refh_job_t;
 
 /* Work is handed out dynamically: unit u = (level, chunk of CTU_CHUNK CTUs), popped from one
@@ -308,6 +313,14 @@ static void *ctu_pass_worker(void *arg)
 {
   refh_job_t *j = arg;
   const int n_ctu = j->ctu_end;
+  if (j->static_threads > 0) {
+    /* static partition: worker w always owns the same contiguous CTU slice (NUMA-friendly:
+     * with pinned workers the pages a slice touches stay on that worker's node) */
+    const int w = j->worker_id, nw = j->static_threads;
+    const int c0 = (int)((long long)n_ctu * w / nw), c1 = (int)((long long)n_ctu * (w + 1) / nw);
+    for (int level = 0; level < j->n_rough + j->n_tu; ++level) ctu_pass_range(j, level, c0, c1);
+    return NULL;
+  }
   const int chunks = (n_ctu + CTU_CHUNK - 1) / CTU_CHUNK;
   const int n_units = chunks * (j->n_rough + j->n_tu);
   for (;;) {
@@ -320,7 +333,50 @@ static void *ctu_pass_worker(void *arg)
   return NULL;
 }
 
-/* Runs the ctu_pass over `n_ctu` CTUs with `threads` pthreads; returns seconds. */
+/* Persistent worker pool (like the encoder's own threadqueue, threadqueue.c:275): threads are
+ * created once and parked on a condition variable; creating 128 fresh threads per pass made the
+ * pass time alternate 5x between consecutive calls on the 2-socket host. */
+#define POOL_MAX 512
+static struct {
+  pthread_t th[POOL_MAX];
+  int n_threads;                 /* created so far */
+  pthread_mutex_t mu;
+  pthread_cond_t cv_work, cv_done;
+  unsigned long generation;      /* bumped per job */
+  int active;                    /* workers taking part in the current job */
+  int remaining;                 /* workers still running the current job */
+  refh_job_t job;
+} g_pool = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv_work = PTHREAD_COND_INITIALIZER, .cv_done = PTHREAD_COND_INITIALIZER };
+
+static void *pool_main(void *arg)
+{
+  const int id = (int)(intptr_t)arg;
+  unsigned long seen = 0;
+  const char *pin_env = getenv("REFH_PIN");
+  if (pin_env && pin_env[0] == '1') {
+    cpu_set_t set;
+    CPU_ZERO(&set); CPU_SET(id % (int)sysconf(_SC_NPROCESSORS_ONLN), &set);
+    pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+  }
+  for (;;) {
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.generation == seen) pthread_cond_wait(&g_pool.cv_work, &g_pool.mu);
+    seen = g_pool.generation;
+    const int take_part = id < g_pool.active;
+    refh_job_t job = g_pool.job;
+    pthread_mutex_unlock(&g_pool.mu);
+    if (!take_part) continue;
+    job.pin_cpu = -1;
+    job.worker_id = id;
+    ctu_pass_worker(&job);
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.remaining == 0) pthread_cond_signal(&g_pool.cv_done);
+    pthread_mutex_unlock(&g_pool.mu);
+  }
+  return NULL;
+}
+
+/* Runs the ctu_pass over `n_ctu` CTUs on `threads` pool workers; returns seconds. */
 double refh_ctu_pass(const char *strategy, int threads, int n_ctu,
                      int n_rough, const refh_level_t *rough,
                      const uvg_pixel *const *rough_orig, const uvg_pixel *const *rough_pred,
@@ -331,27 +387,40 @@ double refh_ctu_pass(const char *strategy, int threads, int n_ctu,
                      uint32_t *const *tu_ssd, uint32_t *const *tu_cost, uint64_t weights)
 {
   if (threads < 1) threads = 1;
-  pthread_t *th = calloc(threads, sizeof(*th));
-  refh_job_t *jobs = calloc(threads, sizeof(*jobs));
+  if (threads > POOL_MAX) threads = POOL_MAX;
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.n_threads < threads) {
+    pthread_create(&g_pool.th[g_pool.n_threads], NULL, pool_main, (void *)(intptr_t)g_pool.n_threads);
+    ++g_pool.n_threads;
+  }
+  pthread_mutex_unlock(&g_pool.mu);
+
   struct timespec t0, t1;
   int next_unit = 0;
-  clock_gettime(CLOCK_MONOTONIC, &t0);
-  for (int t = 0; t < threads; ++t) {
-    refh_job_t *j = &jobs[t];
-    j->strategy = strategy;
-    j->ctu_begin = 0;
-    j->ctu_end = n_ctu;
-    j->next_unit = &next_unit;
-    j->n_rough = n_rough; j->rough = rough;
-    j->rough_orig = rough_orig; j->rough_pred = rough_pred; j->rough_cost = rough_cost;
-    j->n_tu = n_tu; j->tu = tu;
-    j->tu_ref = tu_ref; j->tu_pred = tu_pred; j->tu_rec = tu_rec; j->tu_coeff = tu_coeff;
-    j->tu_ssd = tu_ssd; j->tu_cost = tu_cost; j->weights = weights;
-    pthread_create(&th[t], NULL, ctu_pass_worker, j);
+  refh_job_t j;
+  memset(&j, 0, sizeof j);
+  j.strategy = strategy;
+  j.ctu_begin = 0; j.ctu_end = n_ctu;
+  j.next_unit = &next_unit;
+  j.n_rough = n_rough; j.rough = rough;
+  j.rough_orig = rough_orig; j.rough_pred = rough_pred; j.rough_cost = rough_cost;
+  j.n_tu = n_tu; j.tu = tu;
+  j.tu_ref = tu_ref; j.tu_pred = tu_pred; j.tu_rec = tu_rec; j.tu_coeff = tu_coeff;
+  j.tu_ssd = tu_ssd; j.tu_cost = tu_cost; j.weights = weights;
+  {
+    const char *st = getenv("REFH_STATIC");
+    j.static_threads = (st && st[0] == '1') ? threads : 0;
   }
-  for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_mutex_lock(&g_pool.mu);
+  g_pool.job = j;
+  g_pool.active = threads;
+  g_pool.remaining = threads;
+  ++g_pool.generation;
+  pthread_cond_broadcast(&g_pool.cv_work);
+  while (g_pool.remaining > 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
   clock_gettime(CLOCK_MONOTONIC, &t1);
-  free(th); free(jobs);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 

@@ -1,5 +1,5 @@
-"""CPU reference arm scaling sweep (threads x sample size) on the host; no GPU needed."""
-import sys, os, time
+"""CPU reference arm scaling sweep (threads x pinning) on the host; no GPU needed."""
+import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
@@ -7,9 +7,11 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2040
 arm = bench.CpuArm(n)
 cores = bench.host_cores()
 print("cores", cores, "ctus", n)
-for th in [1, 8, 16, 32, 64, 96, cores, 2 * cores]:
-    if th > 2 * cores:
-        continue
-    arm.run(th)
-    ts = [arm.run(th) for _ in range(5)]
-    print(th, "threads: CTU/s", [round(n / t) for t in ts])
+for pin, static in (("1", "1"), ("1", "0"), ("0", "1")):
+    os.environ["REFH_PIN"] = pin
+    os.environ["REFH_STATIC"] = static
+    print("pin", pin, "static", static)
+    for th in [32, 64, cores]:
+        arm.run(th)
+        ts = [arm.run(th) for _ in range(6)]
+        print("pin", pin, th, "threads: CTU/s", [round(n / t) for t in ts], "mean", round(n * len(ts) / sum(ts)))

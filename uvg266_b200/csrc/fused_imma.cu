@@ -24,11 +24,13 @@
 // 8x8 TUs: two TUs per warp, stacked in the M dimension with block-diagonal constant operands
 // (rows g <-> TU A, rows g+8 <-> TU B), so fragments are fully used.
 #include "quant.cuh"
+#include <mutex>
+#include <vector>
 
 namespace uvgb {
 
 struct ImmaParams {
-  const int8_t *th, *tv;          // device matrices T[k*N+i]
+  const uint32_t *tables;         // device: [AH | ANH | AVT | BV | BH] fragment words for (N, th, tv)
   int shift_f1, shift_f2, shift_i1, shift_i2;
   int cut1, cut2;                 // forward zero-out: frequencies >= cut are zero (hor, ver)
 };
@@ -57,13 +59,13 @@ __device__ __forceinline__ void split4(int v0, int v1, int v2, int v3, uint32_t 
   hi = __byte_perm(p01, p23, 0x7531);
 }
 
-__device__ __forceinline__ uint32_t pack4(int b0, int b1, int b2, int b3)
+__host__ __device__ __forceinline__ uint32_t pack4(int b0, int b1, int b2, int b3)
 {
   return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
 }
 
 // contraction slot -> column inside a 16-wide group (C-fragment pairs of two adjacent 8-wide tiles)
-__device__ __forceinline__ int pi_col(int t, int e) { return 8 * (e >> 1) + 2 * t + (e & 1); }
+__host__ __device__ __forceinline__ int pi_col(int t, int e) { return 8 * (e >> 1) + 2 * t + (e & 1); }
 
 template <int N> struct ImmaShape {
   static constexpr int MT = N >= 16 ? N / 16 : 1;
@@ -71,6 +73,82 @@ template <int N> struct ImmaShape {
   static constexpr int KT = N >= 16 ? N / 16 : 1;
   static constexpr int TUS = N >= 16 ? 1 : 2;        // TUs per warp
 };
+
+
+// Constant operand fragments for (N, th, tv), in the register/lane order mma.sync expects:
+//   AH  [mt][kt][r][lane]  F1 A =  Th   (natural contraction order = pixel columns)
+//   ANH                    F1 A = -Th
+//   AVT [mt][kt][r][lane]  I1 A = Tv^T  (contraction permuted by pi)
+//   BV  [kt][nt][lane]     F2 B = Tv^T  (contraction permuted by pi)
+//   BH  [kt][nt][lane]     I2 B = Th    (contraction pi, output columns sigma)
+// 8x8: two TUs per warp, block-diagonal A operands (row g <-> TU A, row g+8 <-> TU B).
+template <int N>
+static void build_tables(const int8_t *th, const int8_t *tv, std::vector<uint32_t> &out)
+{
+  using S = ImmaShape<N>;
+  constexpr int MT = S::MT, NT = S::NT, KT = S::KT;
+  constexpr int NA = MT * KT * 2 * 32, NB = KT * NT * 32;
+  out.assign(3 * NA + 2 * NB, 0);
+  for (int e0 = 0; e0 < NA; ++e0) {
+    const int ln = e0 & 31, r = (e0 >> 5) & 1, tile = e0 >> 6, kt = tile % KT, mt = tile / KT;
+    const int g = ln >> 2, t = ln & 3;
+    int bh[4], bv[4];
+    if (N >= 16) {
+      const int row = mt * 16 + g + 8 * r;
+      for (int e = 0; e < 4; ++e) {
+        bh[e] = th[row * N + kt * 16 + 4 * t + e];                       // Th[k=row][i]
+        bv[e] = tv[(kt * 16 + pi_col(t, e)) * N + row];                  // Tv[kv][iv=row]
+      }
+    } else {
+      for (int e = 0; e < 4; ++e) {
+        const int ks = 4 * t + e;                                        // F1 slot: K 0-7 TU A pixels, 8-15 TU B pixels
+        bh[e] = ((ks >> 3) == r) ? th[g * N + (ks & 7)] : 0;
+        bv[e] = ((e >> 1) == r) ? tv[(2 * t + (e & 1)) * N + g] : 0;    // I1 slot e<2 -> TU A, e>=2 -> TU B
+      }
+    }
+    out[e0] = pack4(bh[0], bh[1], bh[2], bh[3]);
+    out[NA + e0] = pack4(-bh[0], -bh[1], -bh[2], -bh[3]);
+    out[2 * NA + e0] = pack4(bv[0], bv[1], bv[2], bv[3]);
+  }
+  for (int e0 = 0; e0 < NB; ++e0) {
+    const int ln = e0 & 31, tile = e0 >> 5, nt = tile % NT, kt = tile / NT;
+    const int g = ln >> 2, t = ln & 3;
+    int bv[4], bh[4];
+    if (N >= 16) {
+      const int kv = nt * 8 + g;
+      const int ih = 16 * (nt >> 1) + 4 * (g >> 1) + 2 * (nt & 1) + (g & 1);   // sigma
+      for (int e = 0; e < 4; ++e) {
+        const int kk = kt * 16 + pi_col(t, e);
+        bv[e] = tv[kv * N + kk];                                         // B[j][kv] = Tv[kv][j]
+        bh[e] = th[kk * N + ih];                                         // B[kh][ih] = Th[kh][ih]
+      }
+    } else {
+      for (int e = 0; e < 4; ++e) {
+        bv[e] = e < 2 ? tv[g * N + 2 * t + e] : 0;                       // F2: A slots e>=2 are zero padding
+        bh[e] = e < 2 ? th[(2 * t + e) * N + g] : 0;                     // I2
+      }
+    }
+    out[3 * NA + e0] = pack4(bv[0], bv[1], bv[2], bv[3]);
+    out[3 * NA + NB + e0] = pack4(bh[0], bh[1], bh[2], bh[3]);
+  }
+}
+
+static const uint32_t *cached_tables(int N, int th, int tv)
+{
+  static std::mutex mu;
+  static const uint32_t *cache[3][3][3] = {};       // [size idx][th][tv]
+  const int si = N == 8 ? 0 : N == 16 ? 1 : 2;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache[si][th][tv]) return cache[si][th][tv];
+  std::vector<uint32_t> h;
+  const int8_t *mh = tr_matrix_host(th, N), *mv = tr_matrix_host(tv, N);
+  if (N == 8) build_tables<8>(mh, mv, h); else if (N == 16) build_tables<16>(mh, mv, h); else build_tables<32>(mh, mv, h);
+  uint32_t *d = nullptr;
+  if (cudaMalloc(&d, h.size() * 4) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  cache[si][th][tv] = d;
+  return d;
+}
 
 template <int N>
 __global__ void __launch_bounds__(128)
@@ -85,53 +163,16 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
   __shared__ uint32_t sAVT[MT * KT * 2 * 32];    // I1  A = Tv^T       (contraction permuted by pi)
   __shared__ uint32_t sBH[KT * NT * 32];         // I2  B = Th         (contraction pi, output columns sigma)
 
-  for (int e0 = threadIdx.x; e0 < MT * KT * 2 * 32; e0 += blockDim.x) {
-    const int ln = e0 & 31, r = (e0 >> 5) & 1, tile = e0 >> 6, kt = tile % KT, mt = tile / KT;
-    const int g = ln >> 2, t = ln & 3;
-    int bh[4], bv[4];
-    if (N >= 16) {
-      const int row = mt * 16 + g + 8 * r;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        bh[e] = p.th[row * N + kt * 16 + 4 * t + e];                       // Th[k=row][i]
-        bv[e] = p.tv[(kt * 16 + pi_col(t, e)) * N + row];                  // Tv[kv][iv=row]
-      }
-    } else {
-      // block diagonal: row g -> TU A (r = 0), row g+8 -> TU B (r = 1)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ks = 4 * t + e;                                          // F1 slot: K 0-7 TU A pixels, 8-15 TU B pixels
-        bh[e] = ((ks >> 3) == r) ? p.th[g * N + (ks & 7)] : 0;
-        // I1 slot e<2 -> (TU A, kv = 2t+e), e>=2 -> (TU B, kv = 2t+e-2)
-        bv[e] = ((e >> 1) == r) ? p.tv[(2 * t + (e & 1)) * N + g] : 0;
-      }
+  // fragment tables are built once per (N, type pair) on the host (build_tables below) and
+  // cached in device memory: a CTA only copies its 1-5 KB image
+  {
+    constexpr int NA = MT * KT * 2 * 32, NB = KT * NT * 32;
+    for (int e0 = threadIdx.x; e0 < NA; e0 += blockDim.x) {
+      sAH[e0] = p.tables[e0]; sANH[e0] = p.tables[NA + e0]; sAVT[e0] = p.tables[2 * NA + e0];
     }
-    sAH[e0] = pack4(bh[0], bh[1], bh[2], bh[3]);
-    sANH[e0] = pack4(-bh[0], -bh[1], -bh[2], -bh[3]);
-    sAVT[e0] = pack4(bv[0], bv[1], bv[2], bv[3]);
-  }
-  for (int e0 = threadIdx.x; e0 < KT * NT * 32; e0 += blockDim.x) {
-    const int ln = e0 & 31, tile = e0 >> 5, nt = tile % NT, kt = tile / NT;
-    const int g = ln >> 2, t = ln & 3;
-    int bv[4], bh[4];
-    if (N >= 16) {
-      const int kv = nt * 8 + g;
-      const int ih = 16 * (nt >> 1) + 4 * (g >> 1) + 2 * (nt & 1) + (g & 1);   // sigma: output column slot -> pixel column
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int kk = kt * 16 + pi_col(t, e);
-        bv[e] = p.tv[kv * N + kk];                                         // B[j][kv] = Tv[kv][j]
-        bh[e] = p.th[kk * N + ih];                                         // B[kh][ih] = Th[kh][ih]
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        bv[e] = e < 2 ? p.tv[g * N + 2 * t + e] : 0;                       // F2: A slots e>=2 are zero padding
-        bh[e] = e < 2 ? p.th[(2 * t + e) * N + g] : 0;                     // I2
-      }
+    for (int e0 = threadIdx.x; e0 < NB; e0 += blockDim.x) {
+      sBV[e0] = p.tables[3 * NA + e0]; sBH[e0] = p.tables[3 * NA + NB + e0];
     }
-    sBV[e0] = pack4(bv[0], bv[1], bv[2], bv[3]);
-    sBH[e0] = pack4(bh[0], bh[1], bh[2], bh[3]);
   }
   __syncthreads();
 
@@ -268,8 +309,8 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
     const bool hasA = __any_sync(0xffffffffu, nzA != 0);
     const bool hasB = N >= 16 ? false : __any_sync(0xffffffffu, nzB != 0);
     if (a.cost) {
-      costA = (unsigned)warp_sum((int)costA);
-      if (N < 16) costB = (unsigned)warp_sum((int)costB);
+      costA = __reduce_add_sync(0xffffffffu, costA);
+      if (N < 16) costB = __reduce_add_sync(0xffffffffu, costB);
       if (lane == 0) {
         a.cost[tu0] = (costA + 128u) >> 8;
         if (N < 16 && tu0 + 1 < n_tus) a.cost[tu0 + 1] = (costB + 128u) >> 8;
@@ -371,7 +412,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
           ssd = __dp4a(d4, d4, ssd);
         }
       if (a.ssd) {
-        ssd = (unsigned)warp_sum((int)ssd);
+        ssd = __reduce_add_sync(0xffffffffu, ssd);
         if (lane == 0) a.ssd[tu0] = (uint32_t)((int32_t)ssd >> q.ssd_shift);
       }
     } else {
@@ -403,7 +444,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
         if (tb) ssdB = __dp4a(d4, d4, ssdB); else ssdA = __dp4a(d4, d4, ssdA);
       }
       if (a.ssd) {
-        ssdA = (unsigned)warp_sum((int)ssdA); ssdB = (unsigned)warp_sum((int)ssdB);
+        ssdA = __reduce_add_sync(0xffffffffu, ssdA); ssdB = __reduce_add_sync(0xffffffffu, ssdB);
         if (lane == 0) {
           a.ssd[tu0] = (uint32_t)((int32_t)ssdA >> q.ssd_shift);
           if (tu0 + 1 < n_tus) a.ssd[tu0 + 1] = (uint32_t)((int32_t)ssdB >> q.ssd_shift);
@@ -442,7 +483,8 @@ int launch_fused_imma(const FusedArgs &a, size_t n_tus, const QParams &q, int bi
   if (!word_aligned(a.ref, q.w) || !word_aligned(a.pred, q.w) || !word_aligned(a.rec, q.w)) return -1;
   const int N = q.w, l2 = ilog2_host(N);
   ImmaParams p;
-  p.th = tr_matrix_dev(th, N); p.tv = tr_matrix_dev(tv, N);
+  p.tables = cached_tables(N, th, tv);
+  if (!p.tables) { set_error("fused_imma: fragment table allocation failed"); return 1; }
   p.shift_f1 = l2 - 1 + bitdepth - 8; p.shift_f2 = l2 + 6; p.shift_i1 = 7; p.shift_i2 = 20 - bitdepth;
   p.cut1 = (th == UVG_B200_DCT2 || N < 8) ? N : N - skip_w;
   p.cut2 = (tv == UVG_B200_DCT2 || N < 8) ? N : N - skip_h;
