@@ -52,8 +52,10 @@ __device__ __forceinline__ unsigned satd8_words_u8(const uint32_t (&wo)[8][2], c
           const int a = r[j][x], b = r[j + len][x];
           r[j][x] = a + b; r[j + len][x] = a - b;
         }
-  // remaining stage (distance 2, inside words) + abs-sum: |lo+hi| + |lo-hi| = 2*max(|lo|,|hi|)
-  int s = 0, dc = 0;
+  // remaining stage (distance 2, inside words) fused with the abs-sum: each word contributes
+  // |lo+hi| + |lo-hi|, two VABSDIFF-accumulate instructions
+  unsigned s = 0;
+  int dc = 0;
 #pragma unroll
   for (int y = 0; y < 8; ++y)
 #pragma unroll
@@ -61,12 +63,14 @@ __device__ __forceinline__ unsigned satd8_words_u8(const uint32_t (&wo)[8][2], c
       const int wv = r[y][x];
       const int lo = (int)(short)(wv & 0xffff);
       const int hi = (wv - lo) >> 16;
-      if (y == 0 && x == 0) dc = lo + hi;         // all-plus coefficient
-      s += max(abs(lo), abs(hi));
+      const int u = lo + hi;
+      if (y == 0 && x == 0) dc = u;               // all-plus coefficient
+      s = __sad(lo, hi, s);
+      s = __sad(u, 0, s);
     }
-  s = 2 * s - abs(dc) + (abs(dc) >> 2);
+  s = s - (unsigned)abs(dc) + ((unsigned)abs(dc) >> 2);
   sad = sd;
-  return (unsigned)((s + 2) >> 2);                 // :343-345
+  return (s + 2) >> 2;                             // :343-345
 }
 
 }  // namespace uvgb
