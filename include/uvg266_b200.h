@@ -178,6 +178,24 @@ UVG_B200_API int uvg_b200_fast_coeff_cost_dev(const int16_t *coeffs, int w, int 
                                               uint64_t weights, uint32_t *out, size_t n_tus,
                                               void *stream);
 
+/* ---- intra prediction (next row 8(f)-2): luma, multi_ref_idx 0, no ISP / MIP ------------------
+ * Replaces, for square n x n blocks (n = 4, 8, 16, 32), uvg_intra_predict -> intra_predict_regular
+ * (intra.c:660-753) and the strategies it dispatches to: uvg_angular_pred, uvg_intra_pred_planar,
+ * uvg_pdpc_planar_dc (strategies-intra.h:47-93, intra-generic.c:55-437) plus the reference
+ * smoothing (intra.c:190-225) and DC (intra.c:236-273).
+ * refs: per block, top[2n+1] then left[2n+1] (index 0 = corner sample, the layout of
+ *       uvg_intra_ref, intra.h:47-58), each row with a pitch of 2n+4 pixels; the samples past 2n are
+ *       ignored (the kernel continues the row with the last sample like intra.c:879-886).
+ * modes: k luma modes (0 planar, 1 DC, 2..66 angular), a HOST array, shared by all blocks.
+ * preds: dense [n_blocks][k][n*n].            costs: [n_blocks][k] = min(SATD, 2*SAD) against orig
+ *       (search_intra_rough's cost, search_intra.c:1055-1062 + get_cost :149-163).             */
+UVG_B200_API int uvg_b200_intra_predict_dev(int bitdepth, int n, const void *refs,
+                                            const int8_t *modes, int k, void *preds,
+                                            size_t n_blocks, void *stream);
+UVG_B200_API int uvg_b200_intra_rough_dev(int bitdepth, int n, const uvg_b200_blocks *orig,
+                                          const void *refs, const int8_t *modes, int k,
+                                          uint32_t *costs, size_t n_blocks, void *stream);
+
 /* ---------------------------------------------------------------------------------- */
 /* (3) Batched host entry points (H2D + kernels + D2H inside the call, synchronous)    */
 /* ---------------------------------------------------------------------------------- */
@@ -189,6 +207,13 @@ UVG_B200_API int uvg_b200_rough_cost_host(int bitdepth, int n, const uvg_b200_bl
                                           size_t orig_bytes, const uvg_b200_blocks *preds,
                                           size_t preds_bytes, uint32_t *out, size_t n_blocks,
                                           int k);
+UVG_B200_API int uvg_b200_intra_predict_host(int bitdepth, int n, const void *refs,
+                                             const int8_t *modes, int k, void *preds,
+                                             size_t n_blocks);
+UVG_B200_API int uvg_b200_intra_rough_host(int bitdepth, int n, const uvg_b200_blocks *orig,
+                                           size_t orig_bytes, const void *refs,
+                                           const int8_t *modes, int k, uint32_t *costs,
+                                           size_t n_blocks);
 UVG_B200_API int uvg_b200_transform_host(int inverse, int bitdepth, int w, int h, int type_hor,
                                          int type_ver, int skip_w, int skip_h,
                                          const int16_t *in, int16_t *out, size_t n_tus);

@@ -32,6 +32,8 @@
 #include "strategies/strategies-dct.h"
 #include "strategies/strategies-quant.h"
 #include "tables.h"
+#include "intra.h"
+#include "strategies/strategies-intra.h"
 
 static strategy_list_t g_list;
 static const uvg_api *g_api;
@@ -102,6 +104,7 @@ int refh_open(const char *opts)
   if (!uvg_strategy_register_picture(&g_list, UVG_BIT_DEPTH)) return 0;
   if (!uvg_strategy_register_dct(&g_list, UVG_BIT_DEPTH)) return 0;
   if (!uvg_strategy_register_quant(&g_list, UVG_BIT_DEPTH)) return 0;
+  if (!uvg_strategy_register_intra(&g_list, UVG_BIT_DEPTH)) return 0;
   refh_use("generic");
   return 1;
 }
@@ -201,6 +204,68 @@ unsigned refh_image_calc_sad(const uvg_pixel *pic_y, const uvg_pixel *ref_y, int
 const int8_t *refh_chroma_qp_map(void)
 {
   return g_state->encoder_control->qp_map[0];
+}
+
+/* uvg_intra_predict (intra.c:1372) on caller-supplied reference rows: top[2w+1], left[2h+1]
+ * (index 0 = corner), luma, mrl 0, no ISP / MIP - what search_intra_rough calls per mode. */
+void refh_intra_predict(int w, int h, int mode, const uvg_pixel *top, const uvg_pixel *left, uvg_pixel *dst)
+{
+  static uvg_intra_references refs;
+  memset(&refs, 0, sizeof(refs));
+  memcpy(refs.ref.top, top, (2 * w + 1) * sizeof(uvg_pixel));
+  memcpy(refs.ref.left, left, (2 * h + 1) * sizeof(uvg_pixel));
+  /* beyond the 2n+1 samples the encoder replicates the last one up to 2n + n + 2
+   * (uvg_intra_build_reference_any, intra.c:879-886, :1044-1051) */
+  for (int i = 2 * w + 1; i < 3 * w + 3; ++i) refs.ref.top[i] = top[2 * w];
+  for (int i = 2 * h + 1; i < 3 * h + 3; ++i) refs.ref.left[i] = left[2 * h];
+  cu_loc_t loc;
+  uvg_cu_loc_ctor(&loc, 0, 0, w, h);
+  intra_search_data_t data;
+  memset(&data, 0, sizeof(data));
+  data.pred_cu.type = CU_INTRA;
+  data.pred_cu.log2_width = uvg_g_convert_to_log2[w];
+  data.pred_cu.log2_height = uvg_g_convert_to_log2[h];
+  data.pred_cu.intra.mode = (int8_t)mode;
+  uvg_intra_predict(g_state, &refs, &loc, &loc, COLOR_Y, dst, &data, NULL);
+}
+
+/* Rough intra search of a slice of blocks, the way search_intra_rough scores candidates
+ * (search_intra.c:1055-1062 + get_cost :149-163): uvg_intra_predict for each of k modes, then
+ * min(SATD, 2 * SAD) against the original block. Re-entrant (one call per worker thread).
+ *   refs : [nb][2][2n+4] top / left rows as in uvg_b200_intra_rough_*;  orig : [nb][n*n] dense */
+void refh_intra_rough_batch(int n, const int8_t *modes, int k, const uvg_pixel *refs_in, const uvg_pixel *orig,
+                            long nb, uint32_t *costs)
+{
+  cost_pixel_nxn_multi_func *satd = uvg_pixels_get_satd_dual_func(n, n);
+  cost_pixel_nxn_multi_func *sad = uvg_pixels_get_sad_dual_func(n, n);
+  uvg_intra_references refs;
+  uvg_pixel *preds = NULL;
+  if (posix_memalign((void **)&preds, 64, 2 * 32 * 32 * sizeof(uvg_pixel))) abort();
+  memset(preds, 0, 2 * 32 * 32 * sizeof(uvg_pixel));
+  cu_loc_t loc;
+  uvg_cu_loc_ctor(&loc, 0, 0, n, n);
+  intra_search_data_t data;
+  memset(&data, 0, sizeof(data));
+  data.pred_cu.type = CU_INTRA;
+  data.pred_cu.log2_width = data.pred_cu.log2_height = uvg_g_convert_to_log2[n];
+  const int gp = 2 * n + 4;
+  for (long b = 0; b < nb; ++b) {
+    memset(&refs, 0, sizeof(refs));
+    const uvg_pixel *top = refs_in + b * 2 * gp, *left = top + gp;
+    memcpy(refs.ref.top, top, (2 * n + 1) * sizeof(uvg_pixel));
+    memcpy(refs.ref.left, left, (2 * n + 1) * sizeof(uvg_pixel));
+    for (int i = 2 * n + 1; i < 3 * n + 3; ++i) { refs.ref.top[i] = top[2 * n]; refs.ref.left[i] = left[2 * n]; }
+    for (int m = 0; m < k; ++m) {
+      data.pred_cu.intra.mode = modes[m];
+      uvg_intra_predict(g_state, &refs, &loc, &loc, COLOR_Y, preds, &data, NULL);
+      memcpy(preds + 32 * 32, preds, n * n * sizeof(uvg_pixel));
+      unsigned s[2], t[2];
+      satd((const uvg_pixel(*)[32 * 32])preds, orig + b * n * n, 2, s);
+      sad((const uvg_pixel(*)[32 * 32])preds, orig + b * n * n, 2, t);
+      costs[b * k + m] = s[0] < 2 * t[0] ? s[0] : 2 * t[0];
+    }
+  }
+  free(preds);
 }
 
 const uint32_t *refh_scan_table(int log2_w, int log2_h)

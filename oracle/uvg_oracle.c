@@ -770,3 +770,223 @@ uint32_t orc_fast_coeff_cost(const int16_t *coeff, int w, int h, uint64_t weight
   }
   return (sum + (1 << 7)) >> 8;
 }
+
+/* ===================================================================================
+ * strategies-intra: luma intra prediction of a w*h block from its
+ * reference rows, as the rough search calls it (search_intra.c:1043-1046 ->
+ * uvg_intra_predict intra.c:1372 -> intra_predict_regular :660), for multi_ref_idx = 0,
+ * no ISP, no MIP. ref_top / ref_left follow uvg_intra_ref: index 0 is the top-left corner,
+ * index 1.. the row above / column left of the block, 2*w+1 (2*h+1) samples.
+ * ================================================================================= */
+static const int16_t k_modedisp2sampledisp[32] = { 0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29, 32,
+  35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024 };
+static const int16_t k_modedisp2invsampledisp[32] = { 0, 16384, 8192, 5461, 4096, 2731, 2048, 1638, 1365, 1170,
+  1024, 910, 819, 712, 630, 565, 512, 468, 420, 364, 321, 287, 256, 224, 191, 161, 128, 96, 64, 48, 32, 16 };
+static const int8_t k_pre_scale[32] = { 8, 7, 6, 5, 5, 4, 4, 4, 3, 3, 3, 3, 3, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1,
+  0, 0, 0, -1, -1, -2, -3 };
+static const int8_t k_hor_ver_dist_thres[8] = { 24, 24, 24, 14, 2, 0, 0, 0 };
+/* VVC 4-tap cubic intra interpolation filter (intra-generic.c:77-111), rows = 1/32 phase */
+static const int8_t k_cubic[32][4] = {
+  { 0, 64, 0, 0 }, { -1, 63, 2, 0 }, { -2, 62, 4, 0 }, { -2, 60, 7, -1 }, { -2, 58, 10, -2 }, { -3, 57, 12, -2 },
+  { -4, 56, 14, -2 }, { -4, 55, 15, -2 }, { -4, 54, 16, -2 }, { -5, 53, 18, -2 }, { -6, 52, 20, -2 },
+  { -6, 49, 24, -3 }, { -6, 46, 28, -4 }, { -5, 44, 29, -4 }, { -4, 42, 30, -4 }, { -4, 39, 33, -4 },
+  { -4, 36, 36, -4 }, { -4, 33, 39, -4 }, { -4, 30, 42, -4 }, { -4, 29, 44, -5 }, { -4, 28, 46, -6 },
+  { -3, 24, 49, -6 }, { -2, 20, 52, -6 }, { -2, 18, 53, -5 }, { -2, 16, 54, -4 }, { -2, 15, 55, -4 },
+  { -2, 14, 56, -4 }, { -2, 12, 57, -3 }, { -2, 10, 58, -2 }, { -1, 7, 60, -2 }, { 0, 4, 62, -2 }, { 0, 2, 63, -1 } };
+
+/* uvg_angular_pred_generic, intra-generic.c:55-299, luma, multi_ref_idx = 0, isp = 0. */
+void orc_angular_pred(int w, int h, int pred_mode, const orc_pixel *ref_above, const orc_pixel *ref_left,
+                      orc_pixel *dst)
+{
+  const int l2w = ilog2(w), l2h = ilog2(h);
+  const int vertical = pred_mode >= 34;
+  const int mode_disp = vertical ? pred_mode - 50 : 18 - pred_mode;
+  const int ad = mode_disp < 0 ? -mode_disp : mode_disp;
+  const int sample_disp = (mode_disp < 0 ? -1 : 1) * k_modedisp2sampledisp[ad];
+  const int side_size = vertical ? l2h : l2w;
+  int scale = side_size - k_pre_scale[ad];
+  if (scale > 2) scale = 2;
+  orc_pixel main_buf[2 * 64 + 8 + 64], *ref_main;
+  const orc_pixel *ref_side;
+  orc_pixel work[32 * 32];
+  int W = w, H = h;
+  if (sample_disp < 0) {
+    /* project the side reference onto the negative part of the main reference (:145-156) */
+    const orc_pixel *m = vertical ? ref_above : ref_left, *sd = vertical ? ref_left : ref_above;
+    const int msz = vertical ? w : h, ssz = vertical ? h : w;
+    ref_main = main_buf + 64;
+    for (int i = 0; i < msz + 2; ++i) ref_main[i] = m[i];
+    for (int i = -ssz; i <= -1; ++i) {
+      int idx = (-i * k_modedisp2invsampledisp[ad] + 256) >> 9;
+      if (idx > ssz) idx = ssz;
+      ref_main[i] = sd[idx];
+    }
+    ref_side = sd;
+  } else {
+    ref_main = (orc_pixel *)(vertical ? ref_above : ref_left);
+    ref_side = vertical ? ref_left : ref_above;
+  }
+  if (!vertical) { int t = W; W = H; H = t; }
+  if (sample_disp != 0) {
+    int use_cubic = 1;
+    const int thr = k_hor_ver_dist_thres[(l2w + l2h) >> 1];
+    int d50 = pred_mode - 50, d18 = pred_mode - 18;
+    if (d50 < 0) d50 = -d50;
+    if (d18 < 0) d18 = -d18;
+    const int dist = d50 < d18 ? d50 : d18;
+    const int frac_mode = ((sample_disp < 0 ? -sample_disp : sample_disp) & 0x1f) != 0;
+    if (dist > thr && frac_mode) use_cubic = 0;
+    for (int y = 0, delta_pos = sample_disp; y < H; ++y, delta_pos += sample_disp) {
+      const int delta_int = delta_pos >> 5, fr = delta_pos & 31;
+      const int gauss[4] = { 16 - (fr >> 1), 32 - (fr >> 1), 16 + (fr >> 1), fr >> 1 };
+      if (frac_mode) {
+        for (int x = 0; x < W; ++x) {
+          const orc_pixel *p = &ref_main[delta_int + x];
+          int s = 32;
+          for (int k = 0; k < 4; ++k) s += (use_cubic ? k_cubic[fr][k] : gauss[k]) * (int)p[k];
+          work[y * W + x] = (orc_pixel)clip3(0, PIXEL_MAX, s >> 6);
+        }
+      } else {
+        for (int x = 0; x < W; ++x) work[y * W + x] = ref_main[x + delta_int + 1];
+      }
+      /* PDPC for angular modes (:234-252) */
+      int pdpc = (W >= 4 && H >= 4);
+      if (mode_disp < 0) pdpc = 0;
+      else if (mode_disp > 0) pdpc = pdpc && (scale >= 0);
+      if (pdpc) {
+        int inv_angle_sum = 256;
+        const int lim = (3 << scale) < W ? (3 << scale) : W;
+        for (int x = 0; x < lim; ++x) {
+          inv_angle_sum += k_modedisp2invsampledisp[ad];
+          const int wL = 32 >> ((2 * x) >> scale);
+          const int left = ref_side[y + (inv_angle_sum >> 9) + 1];
+          const int cur = work[y * W + x];
+          work[y * W + x] = (orc_pixel)(cur + ((wL * (left - cur) + 32) >> 6));
+        }
+      }
+    }
+  } else {
+    /* pure horizontal / vertical (:254-280) with PDPC */
+    const int do_pdpc = (W >= 4 && H >= 4);
+    const int sc = (l2w + l2h - 2) >> 2;
+    const int top_left = ref_main[0];
+    for (int y = 0; y < H; ++y) {
+      for (int x = 0; x < W; ++x) work[y * W + x] = ref_main[1 + x];
+      if (do_pdpc) {
+        const int left = ref_side[1 + y];
+        const int lim = (3 << sc) < W ? (3 << sc) : W;
+        for (int x = 0; x < lim; ++x) {
+          const int wL = 32 >> ((2 * x) >> sc);
+          work[y * W + x] = (orc_pixel)clip3(0, PIXEL_MAX, (int)work[y * W + x] + ((wL * (left - top_left) + 32) >> 6));
+        }
+      }
+    }
+  }
+  if (vertical) {
+    for (int i = 0; i < w * h; ++i) dst[i] = work[i];
+  } else {
+    /* horizontal modes were predicted transposed (:283-298) */
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) dst[y * w + x] = work[x * W + y];
+  }
+}
+
+/* uvg_intra_pred_planar_generic :306-360 */
+void orc_intra_pred_planar(int w, int h, const orc_pixel *ref_top, const orc_pixel *ref_left, orc_pixel *dst)
+{
+  const int l2w = ilog2(w), l2h = ilog2(h);
+  const int top_right = ref_top[w + 1], bottom_left = ref_left[h + 1];
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const int hor = ((int)ref_left[y + 1] << l2w) + (x + 1) * (top_right - (int)ref_left[y + 1]);
+      const int ver = ((int)ref_top[x + 1] << l2h) + (y + 1) * (bottom_left - (int)ref_top[x + 1]);
+      dst[y * w + x] = (orc_pixel)(((hor << l2h) + (ver << l2w) + (1 << (l2w + l2h))) >> (1 + l2w + l2h));
+    }
+}
+
+/* intra_pred_dc, intra.c:236-273 (multi_ref_idx = 0) */
+void orc_intra_pred_dc(int w, int h, const orc_pixel *ref_top, const orc_pixel *ref_left, orc_pixel *dst)
+{
+  int sum = 0;
+  if (w >= h) for (int i = 0; i < w; ++i) sum += ref_top[i + 1];
+  if (w <= h) for (int j = 0; j < h; ++j) sum += ref_left[j + 1];
+  const int denom = w == h ? w << 1 : (w > h ? w : h);
+  const int dc = (sum + (denom >> 1)) >> ilog2(denom);
+  for (int i = 0; i < w * h; ++i) dst[i] = (orc_pixel)dc;
+}
+
+/* uvg_pdpc_planar_dc_generic :414-437 */
+void orc_pdpc_planar_dc(int w, int h, const orc_pixel *ref_top, const orc_pixel *ref_left, orc_pixel *dst)
+{
+  const int scale = (ilog2(w) + ilog2(h) - 2) >> 2;
+  for (int y = 0; y < h; ++y) {
+    int sy = (y << 1) >> scale; if (sy > 31) sy = 31;
+    const int wT = 32 >> sy;
+    for (int x = 0; x < w; ++x) {
+      int sx = (x << 1) >> scale; if (sx > 31) sx = 31;
+      const int wL = 32 >> sx;
+      const int cur = dst[x + y * w];
+      dst[x + y * w] = (orc_pixel)(cur + ((wL * ((int)ref_left[y + 1] - cur) + wT * ((int)ref_top[x + 1] - cur) + 32) >> 6));
+    }
+  }
+}
+
+/* intra_filter_reference, intra.c:190-225: [1 2 1]/4 smoothing of the reference rows */
+void orc_intra_filter_reference(int w, int h, const orc_pixel *top, const orc_pixel *left, orc_pixel *ftop,
+                                orc_pixel *fleft)
+{
+  const int rw = 2 * w + 1, rh = 2 * h + 1;
+  fleft[0] = (orc_pixel)((left[1] + 2 * left[0] + top[1] + 2) >> 2);
+  ftop[0] = fleft[0];
+  for (int y = 1; y < rh - 1; ++y) fleft[y] = (orc_pixel)((left[y - 1] + 2 * left[y] + left[y + 1] + 2) >> 2);
+  fleft[rh - 1] = left[rh - 1];
+  for (int x = 1; x < rw - 1; ++x) ftop[x] = (orc_pixel)((top[x - 1] + 2 * top[x] + top[x + 1] + 2) >> 2);
+  ftop[rw - 1] = top[rw - 1];
+}
+
+/* intra_predict_regular, intra.c:660-753, luma, square or not, mrl = 0, isp = 0,
+ * intra_smoothing_disabled = 0: reference-smoothing decision + predictor + PDPC. */
+void orc_intra_predict(int w, int h, int mode, const orc_pixel *top, const orc_pixel *left, orc_pixel *dst)
+{
+  const int l2w = ilog2(w), l2h = ilog2(h);
+  int pred_mode = mode;
+  if (l2w != l2h && mode > 1 && mode <= 66) {                /* uvg_wide_angle_correction :637 */
+    static const int shift[] = { 0, 6, 10, 12, 14, 15 };
+    const int ds = l2w > l2h ? l2w - l2h : l2h - l2w;
+    if (l2w > l2h && mode < 2 + shift[ds]) pred_mode += 65;
+    else if (l2h > l2w && mode > 66 - shift[ds]) pred_mode -= 65;
+  }
+  int filtered = 0;
+  if (mode == 1 || (w == 4 && h == 4)) {
+  } else if (mode == 0) {
+    filtered = w * h > 32;
+  } else {
+    const int thr = k_hor_ver_dist_thres[(l2w + l2h) >> 1];
+    int d50 = pred_mode - 50, d18 = pred_mode - 18;
+    if (d50 < 0) d50 = -d50;
+    if (d18 < 0) d18 = -d18;
+    if ((d50 < d18 ? d50 : d18) > thr) {
+      const int md = pred_mode >= 34 ? pred_mode - 50 : 18 - pred_mode;
+      const int sd = k_modedisp2sampledisp[md < 0 ? -md : md];
+      if ((sd & 0x1f) == 0) filtered = 1;
+    }
+  }
+  /* The encoder's reference rows continue past their 2n+1 samples with the last sample
+   * replicated (uvg_intra_build_reference_any, intra.c:879-886, :1044-1051): the 4-tap filter
+   * of the steepest angles reads up to 2 samples beyond 2n. */
+  enum { PAD = 8 };
+  orc_pixel tp[2 * 64 + 1 + PAD], lp[2 * 64 + 1 + PAD], ftop[2 * 64 + 1 + PAD], fleft[2 * 64 + 1 + PAD];
+  for (int i = 0; i < 2 * w + 1 + PAD; ++i) tp[i] = top[i < 2 * w + 1 ? i : 2 * w];
+  for (int i = 0; i < 2 * h + 1 + PAD; ++i) lp[i] = left[i < 2 * h + 1 ? i : 2 * h];
+  const orc_pixel *ut = tp, *ul = lp;
+  if (filtered) {
+    orc_intra_filter_reference(w, h, tp, lp, ftop, fleft);
+    for (int i = 2 * w + 1; i < 2 * w + 1 + PAD; ++i) ftop[i] = ftop[2 * w];
+    for (int i = 2 * h + 1; i < 2 * h + 1 + PAD; ++i) fleft[i] = fleft[2 * h];
+    ut = ftop; ul = fleft;
+  }
+  if (mode == 0) orc_intra_pred_planar(w, h, ut, ul, dst);
+  else if (mode == 1) orc_intra_pred_dc(w, h, ut, ul, dst);
+  else orc_angular_pred(w, h, pred_mode, ut, ul, dst);
+  if ((mode == 0 || mode == 1) && w >= 4 && h >= 4) orc_pdpc_planar_dc(w, h, ut, ul, dst);
+}

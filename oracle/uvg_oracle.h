@@ -112,6 +112,16 @@ int orc_quantize_residual(const orc_quant_params *p, int cu_type, int tr_idx, in
 uint32_t orc_coeff_abs_sum(const int16_t *coeffs, size_t length);
 uint32_t orc_fast_coeff_cost(const int16_t *coeff, int w, int h, uint64_t weights);
 
+/* ---- strategies-intra (next row 8(f)-2), luma, mrl = 0, no ISP / MIP ----------------- */
+void orc_angular_pred(int w, int h, int pred_mode, const orc_pixel *ref_above, const orc_pixel *ref_left,
+                      orc_pixel *dst);
+void orc_intra_pred_planar(int w, int h, const orc_pixel *ref_top, const orc_pixel *ref_left, orc_pixel *dst);
+void orc_intra_pred_dc(int w, int h, const orc_pixel *ref_top, const orc_pixel *ref_left, orc_pixel *dst);
+void orc_pdpc_planar_dc(int w, int h, const orc_pixel *ref_top, const orc_pixel *ref_left, orc_pixel *dst);
+void orc_intra_filter_reference(int w, int h, const orc_pixel *top, const orc_pixel *left, orc_pixel *ftop,
+                                orc_pixel *fleft);
+void orc_intra_predict(int w, int h, int mode, const orc_pixel *top, const orc_pixel *left, orc_pixel *dst);
+
 #ifdef __cplusplus
 }
 #endif

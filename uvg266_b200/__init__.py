@@ -99,6 +99,10 @@ def lib():
     L.uvg_b200_transform_host.argtypes = [i] * 8 + [vp, vp, sz]
     L.uvg_b200_quantize_residual_host.argtypes = [QP, i, i, i, i, i, i, i, BP, sz, BP, sz, BP, sz, vp, vp,
                                                   vp, vp, C.c_uint64, sz]
+    L.uvg_b200_intra_predict_dev.argtypes = [i, i, vp, vp, i, vp, sz, vp]
+    L.uvg_b200_intra_rough_dev.argtypes = [i, i, BP, vp, vp, i, vp, sz, vp]
+    L.uvg_b200_intra_predict_host.argtypes = [i, i, vp, vp, i, vp, sz]
+    L.uvg_b200_intra_rough_host.argtypes = [i, i, BP, sz, vp, vp, i, vp, sz]
     # drop-ins
     for suf in ("8", "16"):
         for n in (4, 8, 16, 32, 64):

@@ -369,6 +369,48 @@ extern "C" int uvg_b200_rough_cost_host(int bitdepth, int n, const uvg_b200_bloc
   return 0;
 }
 
+extern "C" int uvg_b200_intra_predict_host(int bitdepth, int n, const void *refs, const int8_t *modes, int k,
+                                           void *preds, size_t n_blocks)
+{
+  if (ensure_init()) return 1;
+  if (n_blocks == 0) return 0;
+  if (n < 4 || n > 32 || k < 1 || k > 67) { set_error("intra_predict_host: bad n=%d or k=%d", n, k); return 1; }
+  Staging &s = tls_staging();
+  const size_t pix = bitdepth == 8 ? 1 : 2;
+  const size_t ref_bytes = n_blocks * (size_t)(2 * (2 * n + 4)) * pix, rb = align_up(ref_bytes, 256);
+  const size_t out_bytes = n_blocks * (size_t)k * n * n * pix;
+  if (s.ensure(0, rb + out_bytes)) return 1;
+  UVGB_TRY(cudaMemcpyAsync(s.d_buf, refs, ref_bytes, cudaMemcpyHostToDevice, s.stream));
+  if (uvg_b200_intra_predict_dev(bitdepth, n, s.d_buf, modes, k, s.d_buf + rb, n_blocks, s.stream)) return 1;
+  UVGB_TRY(cudaMemcpyAsync(preds, s.d_buf + rb, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+  UVGB_TRY(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
+extern "C" int uvg_b200_intra_rough_host(int bitdepth, int n, const uvg_b200_blocks *orig, size_t orig_bytes,
+                                         const void *refs, const int8_t *modes, int k, uint32_t *costs,
+                                         size_t n_blocks)
+{
+  if (ensure_init()) return 1;
+  if (n_blocks == 0) return 0;
+  if (n < 4 || n > 32 || k < 1 || k > 67) { set_error("intra_rough_host: bad n=%d or k=%d", n, k); return 1; }
+  Staging &s = tls_staging();
+  const size_t pix = bitdepth == 8 ? 1 : 2;
+  const size_t ref_bytes = n_blocks * (size_t)(2 * (2 * n + 4)) * pix;
+  const size_t bo = align_up(orig_bytes, 256), ro = bo + align_up(ref_bytes, 256);
+  const size_t out_bytes = n_blocks * (size_t)k * sizeof(uint32_t);
+  if (s.ensure(0, ro + out_bytes)) return 1;
+  UVGB_TRY(cudaMemcpyAsync(s.d_buf, orig->base, orig_bytes, cudaMemcpyHostToDevice, s.stream));
+  UVGB_TRY(cudaMemcpyAsync(s.d_buf + bo, refs, ref_bytes, cudaMemcpyHostToDevice, s.stream));
+  uvg_b200_blocks A = *orig;
+  A.base = s.d_buf;
+  uint32_t *d_out = reinterpret_cast<uint32_t *>(s.d_buf + ro);
+  if (uvg_b200_intra_rough_dev(bitdepth, n, &A, s.d_buf + bo, modes, k, d_out, n_blocks, s.stream)) return 1;
+  UVGB_TRY(cudaMemcpyAsync(costs, d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+  UVGB_TRY(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
 extern "C" int uvg_b200_transform_host(int inverse, int bitdepth, int w, int h, int type_hor, int type_ver,
                                        int skip_w, int skip_h, const int16_t *in, int16_t *out, size_t n_tus)
 {

@@ -1,0 +1,338 @@
+// intra.cu - luma intra prediction (planar / DC / 65 angular modes incl. wide angles, reference
+// smoothing, PDPC) on the device, and the fused "predict + score" rough-search kernel.
+// This is the first "next" row of the scope table: the producer of the
+// predictions the rough search scores with SATD/SAD, and the reference encoder's #1 CPU hotspot.
+//
+// Restates, for multi_ref_idx = 0, no ISP, no MIP, intra_smoothing enabled:
+//   intra_predict_regular            intra.c:660-753   (smoothing decision, dispatch, PDPC)
+//   uvg_wide_angle_correction        intra.c:637-658
+//   intra_filter_reference           intra.c:190-225   ([1 2 1]/4 reference smoothing)
+//   intra_pred_dc                    intra.c:236-273
+//   uvg_angular_pred_generic         intra-generic.c:55-299
+//   uvg_intra_pred_planar_generic    intra-generic.c:306-360
+//   uvg_pdpc_planar_dc_generic       intra-generic.c:414-437
+// Every output pixel is a pure function of the two reference rows, so a pixel (or an 8x8
+// sub-block) is one thread's work and the prediction never has to exist in HBM: the fused kernel
+// feeds predicted rows straight into the packed Hadamard of hadamard.cuh.
+//
+// Reference rows per block (`refs`): top[2n+1] then left[2n+1], index 0 = the top-left corner
+// sample, each row stored with a pitch of 2n+4 pixels; like the encoder's own buffers the rows
+// continue past 2n with the last sample replicated (intra.c:879-886).
+#include "common.cuh"
+#include "hadamard.cuh"
+
+namespace uvgb {
+
+// intra-generic.c:73-75 (tables of the VVC angular predictor)
+__constant__ short c_sampledisp[32] = { 0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29, 32,
+  35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024 };
+static const short h_sampledisp[32] = { 0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29, 32,
+  35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024 };
+static const short h_invsampledisp[32] = { 0, 16384, 8192, 5461, 4096, 2731, 2048, 1638, 1365, 1170,
+  1024, 910, 819, 712, 630, 565, 512, 468, 420, 364, 321, 287, 256, 224, 191, 161, 128, 96, 64, 48, 32, 16 };
+static const signed char h_pre_scale[32] = { 8, 7, 6, 5, 5, 4, 4, 4, 3, 3, 3, 3, 3, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1,
+  0, 0, 0, -1, -1, -2, -3 };
+static const signed char h_dist_thres[8] = { 24, 24, 24, 14, 2, 0, 0, 0 };
+// 4-tap cubic interpolation filter, one row per 1/32 phase (intra-generic.c:77-111)
+__constant__ signed char c_cubic[32][4] = {
+  { 0, 64, 0, 0 }, { -1, 63, 2, 0 }, { -2, 62, 4, 0 }, { -2, 60, 7, -1 }, { -2, 58, 10, -2 }, { -3, 57, 12, -2 },
+  { -4, 56, 14, -2 }, { -4, 55, 15, -2 }, { -4, 54, 16, -2 }, { -5, 53, 18, -2 }, { -6, 52, 20, -2 },
+  { -6, 49, 24, -3 }, { -6, 46, 28, -4 }, { -5, 44, 29, -4 }, { -4, 42, 30, -4 }, { -4, 39, 33, -4 },
+  { -4, 36, 36, -4 }, { -4, 33, 39, -4 }, { -4, 30, 42, -4 }, { -4, 29, 44, -5 }, { -4, 28, 46, -6 },
+  { -3, 24, 49, -6 }, { -2, 20, 52, -6 }, { -2, 18, 53, -5 }, { -2, 16, 54, -4 }, { -2, 15, 55, -4 },
+  { -2, 14, 56, -4 }, { -2, 12, 57, -3 }, { -2, 10, 58, -2 }, { -1, 7, 60, -2 }, { 0, 4, 62, -2 }, { 0, 2, 63, -1 } };
+
+// Everything about one intra mode that does not depend on the pixel, derived on the host.
+struct ModeParam {
+  signed char kind;         // 0 planar, 1 DC, 2 angular
+  signed char vertical;     // angular: pred_mode >= 34
+  signed char filtered;     // use the [1 2 1]-smoothed reference rows
+  signed char frac;         // angular: (|sample_disp| & 31) != 0 -> 4-tap interpolation
+  signed char cubic;        // angular: cubic (1) or the "gaussian" filter derived from the phase (0)
+  signed char pdpc;         // apply PDPC
+  signed char scale;        // PDPC scale
+  signed char pad;
+  short sample_disp;        // angular: displacement per line in 1/32 samples (signed)
+  short inv_angle;          // angular: modedisp2invsampledisp
+};
+constexpr int kMaxModes = 67;
+struct ModeTable { ModeParam m[kMaxModes]; int k; };
+
+// intra_predict_regular's decisions for an n x n luma block (square: no wide-angle remap).
+static ModeParam make_mode(int n, int mode)
+{
+  ModeParam p{};
+  const int l2 = ilog2_host(n);
+  if (mode == 0) {
+    p.kind = 0; p.filtered = n * n > 32; p.pdpc = n >= 4; p.scale = (signed char)((2 * l2 - 2) >> 2);
+    return p;
+  }
+  if (mode == 1) {
+    p.kind = 1; p.filtered = 0; p.pdpc = n >= 4; p.scale = (signed char)((2 * l2 - 2) >> 2);
+    return p;
+  }
+  p.kind = 2;
+  const int pred_mode = mode;
+  p.vertical = pred_mode >= 34;
+  const int mode_disp = p.vertical ? pred_mode - 50 : 18 - pred_mode;
+  const int ad = mode_disp < 0 ? -mode_disp : mode_disp;
+  p.sample_disp = (short)((mode_disp < 0 ? -1 : 1) * h_sampledisp[ad]);
+  p.inv_angle = h_invsampledisp[ad];
+  p.frac = (h_sampledisp[ad] & 31) != 0;
+  const int thr = h_dist_thres[l2];                         // (log2w + log2h) >> 1 = log2 n
+  int d50 = pred_mode - 50, d18 = pred_mode - 18;
+  if (d50 < 0) d50 = -d50;
+  if (d18 < 0) d18 = -d18;
+  const int dist = d50 < d18 ? d50 : d18;
+  p.cubic = !(dist > thr && p.frac);
+  p.filtered = (n != 4) && dist > thr && !p.frac;             // intra.c:691-712
+  int scale = l2 - h_pre_scale[ad];
+  if (scale > 2) scale = 2;
+  if (p.sample_disp == 0) {                                  // pure horizontal / vertical (:254-280)
+    p.pdpc = n >= 4; p.scale = (signed char)((2 * l2 - 2) >> 2);
+  } else {
+    p.pdpc = n >= 4 && mode_disp > 0 && scale >= 0;           // :234-243
+    p.scale = (signed char)scale;
+  }
+  return p;
+}
+
+__device__ __forceinline__ int ilog2_dev(int v) { return 31 - __clz(v); }
+
+// Reference rows of one block in shared memory: unfiltered and smoothed, top and left, each
+// `pitch` pixels long (>= 2n + 1 + 8, tail = last sample replicated).
+template <typename Pix>
+struct RefRows { const Pix *top, *left, *ftop, *fleft; };
+
+template <typename Pix>
+__device__ __forceinline__ int pred_pixel(const ModeParam &mp, const RefRows<Pix> &rr, int n, int l2, int X, int Y,
+                                          int dc_val, int pixel_max)
+{
+  const Pix *top = mp.filtered ? rr.ftop : rr.top, *left = mp.filtered ? rr.fleft : rr.left;
+  if (mp.kind != 2) {
+    int v;
+    if (mp.kind == 0) {                                      // planar :306-360
+      const int tr = top[n + 1], bl = left[n + 1];
+      const int hor = ((int)left[Y + 1] << l2) + (X + 1) * (tr - (int)left[Y + 1]);
+      const int ver = ((int)top[X + 1] << l2) + (Y + 1) * (bl - (int)top[X + 1]);
+      v = ((hor << l2) + (ver << l2) + (1 << (2 * l2))) >> (1 + 2 * l2);
+    } else {
+      v = dc_val;
+    }
+    if (mp.pdpc) {                                           // uvg_pdpc_planar_dc_generic :414-437
+      const int wT = 32 >> min(31, (Y << 1) >> mp.scale), wL = 32 >> min(31, (X << 1) >> mp.scale);
+      v = v + ((wL * ((int)left[Y + 1] - v) + wT * ((int)top[X + 1] - v) + 32) >> 6);
+      v &= (sizeof(Pix) == 1) ? 0xff : 0xffff;               // stored into uvg_pixel
+    }
+    return v;
+  }
+  // angular :55-299: horizontal modes are predicted transposed
+  const Pix *mainr = mp.vertical ? top : left, *side = mp.vertical ? left : top;
+  const int r = mp.vertical ? Y : X, c = mp.vertical ? X : Y;
+  int v;
+  if (mp.sample_disp == 0) {
+    v = mainr[1 + c];
+    if (mp.pdpc && c < min(3 << mp.scale, n)) {
+      const int wL = 32 >> ((2 * c) >> mp.scale);
+      v = clip3(0, pixel_max, v + ((wL * ((int)side[1 + r] - (int)mainr[0]) + 32) >> 6));
+    }
+    return v;
+  }
+  const int delta_pos = (r + 1) * mp.sample_disp;
+  const int di = delta_pos >> 5, fr = delta_pos & 31;
+  auto MAIN = [&](int i) -> int {
+    if (i >= 0) return mainr[i];
+    // negative part of the main reference = side reference projected through the inverse angle (:145-156)
+    return side[min((-i * mp.inv_angle + 256) >> 9, n)];
+  };
+  if (mp.frac) {
+    const int i0 = di + c;
+    int f0, f1, f2, f3;
+    if (mp.cubic) { f0 = c_cubic[fr][0]; f1 = c_cubic[fr][1]; f2 = c_cubic[fr][2]; f3 = c_cubic[fr][3]; }
+    else { f0 = 16 - (fr >> 1); f1 = 32 - (fr >> 1); f2 = 16 + (fr >> 1); f3 = fr >> 1; }
+    v = clip3(0, pixel_max, (f0 * MAIN(i0) + f1 * MAIN(i0 + 1) + f2 * MAIN(i0 + 2) + f3 * MAIN(i0 + 3) + 32) >> 6);
+  } else {
+    v = MAIN(c + di + 1);
+  }
+  if (mp.pdpc && c < min(3 << mp.scale, n)) {
+    const int inv_sum = 256 + (c + 1) * mp.inv_angle;
+    const int wL = 32 >> ((2 * c) >> mp.scale);
+    const int l = side[r + (inv_sum >> 9) + 1];
+    v = (v + ((wL * (l - v) + 32) >> 6)) & ((sizeof(Pix) == 1) ? 0xff : 0xffff);
+  }
+  return v;
+}
+
+// CTA-cooperative: stage the reference rows of block `b` (global layout: top then left, pitch
+// 2n+4) into shared memory with replication padding, build the smoothed rows and the DC value.
+template <typename Pix>
+__device__ __forceinline__ void stage_refs(const Pix *__restrict__ refs, size_t b, int n, int spitch, Pix *s_rows,
+                                           int *s_dc, int tid, int nthreads)
+{
+  const int gp = 2 * n + 4, len = 2 * n + 1;
+  const Pix *g = refs + b * (size_t)(2 * gp);
+  Pix *top = s_rows, *left = s_rows + spitch, *ftop = s_rows + 2 * spitch, *fleft = s_rows + 3 * spitch;
+  for (int i = tid; i < 2 * spitch; i += nthreads) {
+    const int row = i / spitch, x = i - row * spitch;
+    s_rows[i] = g[row * gp + min(x, len - 1)];
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * spitch; i += nthreads) {         // intra_filter_reference :190-225
+    const int row = i / spitch, x = i - row * spitch;
+    const Pix *src = row ? left : top;
+    int v;
+    if (x == 0) v = ((int)left[1] + 2 * (int)left[0] + (int)top[1] + 2) >> 2;
+    else if (x < len - 1) v = ((int)src[x - 1] + 2 * (int)src[x] + (int)src[x + 1] + 2) >> 2;
+    else v = src[len - 1];
+    (row ? fleft : ftop)[x] = (Pix)v;
+  }
+  if (tid == 0) {                                            // intra_pred_dc :236-273, square block
+    int sum = 0;
+    for (int i = 0; i < n; ++i) sum += (int)top[i + 1] + (int)left[i + 1];
+    *s_dc = (sum + n) >> (ilog2_dev(2 * n));
+  }
+  __syncthreads();
+}
+
+// ---- predictions out (generic: any n in 4..32, any bit depth) -------------------------------------
+template <typename Pix>
+__global__ void __launch_bounds__(256)
+intra_predict_kernel(const Pix *__restrict__ refs, Pix *__restrict__ preds, size_t n_blocks, int n, ModeTable mt,
+                     int pixel_max)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int spitch = 2 * n + 12;
+  Pix *s_rows = reinterpret_cast<Pix *>(smem_raw);
+  __shared__ int s_dc;
+  const int l2 = ilog2_dev(n);
+  for (size_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+    __syncthreads();
+    stage_refs<Pix>(refs, b, n, spitch, s_rows, &s_dc, threadIdx.x, blockDim.x);
+    RefRows<Pix> rr{ s_rows, s_rows + spitch, s_rows + 2 * spitch, s_rows + 3 * spitch };
+    const int total = mt.k * n * n;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int m = e / (n * n), p = e - m * n * n, Y = p / n, X = p - Y * n;
+      preds[(b * mt.k + m) * (size_t)(n * n) + p] = (Pix)pred_pixel<Pix>(mt.m[m], rr, n, l2, X, Y, s_dc, pixel_max);
+    }
+  }
+}
+
+// ---- fused rough search: predict + min(SATD, 2*SAD), 8-bit, n in {8, 16, 32} ----------------------
+// One CTA per block. Items = (mode, 8x8 sub-block); the original block is staged once in shared
+// memory, normal and transposed: horizontal modes are generated in their natural (transposed)
+// orientation and scored against the transposed original (a 2-D Hadamard abs-sum and a SAD do
+// not change under transposition), so every thread always produces 8 consecutive pixels of a row.
+template <int N>
+__global__ void __launch_bounds__(128)
+intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restrict__ out, size_t n_blocks, ModeTable mt)
+{
+  constexpr int NS = N / 8, NSUB = NS * NS, SP = 2 * N + 12;
+  __shared__ __align__(16) uint8_t s_rows[4 * SP];
+  __shared__ __align__(16) uint8_t s_orig[N * N], s_origT[N * N];
+  __shared__ int s_dc;
+  constexpr int l2 = N == 8 ? 3 : N == 16 ? 4 : 5;
+  for (size_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+    __syncthreads();
+    const uint8_t *pa = static_cast<const uint8_t *>(A.base) + A.offset(b);
+    for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
+      const int y = i / N, x = i - y * N;
+      const uint8_t v = __ldg(pa + (size_t)y * A.stride + x);
+      s_orig[i] = v; s_origT[x * N + y] = v;
+    }
+    stage_refs<uint8_t>(refs, b, N, SP, s_rows, &s_dc, threadIdx.x, blockDim.x);
+    RefRows<uint8_t> rr{ s_rows, s_rows + SP, s_rows + 2 * SP, s_rows + 3 * SP };
+    const int items = mt.k * NSUB;
+    for (int it0 = 0; it0 < items; it0 += blockDim.x) {
+      const int it = it0 + threadIdx.x;
+      unsigned satd = 0, sad = 0;
+      if (it < items) {
+        const int m = it / NSUB, sub = it - m * NSUB, sy = sub / NS, sx = sub - sy * NS;
+        const ModeParam mp = mt.m[m];
+        const bool transposed = mp.kind == 2 && !mp.vertical;
+        const uint8_t *orig = transposed ? s_origT : s_orig;
+        uint32_t wo[8][2], wc[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const uint2 o = *reinterpret_cast<const uint2 *>(orig + (sy * 8 + r) * N + sx * 8);
+          wo[r][0] = o.x; wo[r][1] = o.y;
+          uint32_t lo = 0, hi = 0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            // row (sy*8+r), column (sx*8+c) of the (possibly transposed) prediction
+            const int rowc = sy * 8 + r, colc = sx * 8 + c;
+            const int X = transposed ? rowc : colc, Y = transposed ? colc : rowc;
+            const uint32_t v = (uint32_t)pred_pixel<uint8_t>(mp, rr, N, l2, X, Y, s_dc, 255);
+            if (c < 4) lo |= v << (8 * c); else hi |= v << (8 * (c - 4));
+          }
+          wc[r][0] = lo; wc[r][1] = hi;
+        }
+        satd = satd8_words_u8<true>(wo, wc, sad);
+      }
+      if (NSUB > 1) { satd = group_sum<NSUB>(satd); sad = group_sum<NSUB>(sad); }
+      if (it < items && (it % NSUB) == 0) out[b * mt.k + it / NSUB] = min(satd, 2 * sad);
+    }
+  }
+}
+
+static int fill_modes(ModeTable &mt, int n, const int8_t *modes, int k)
+{
+  if (n != 4 && n != 8 && n != 16 && n != 32) { set_error("intra: block size %d unsupported", n); return 1; }
+  if (k < 1 || k > kMaxModes) { set_error("intra: 1..67 modes per call (got %d)", k); return 1; }
+  mt.k = k;
+  for (int i = 0; i < k; ++i) {
+    if (modes[i] < 0 || modes[i] > 66) { set_error("intra: mode %d out of range", modes[i]); return 1; }
+    mt.m[i] = make_mode(n, modes[i]);
+  }
+  return 0;
+}
+
+}  // namespace uvgb
+
+using namespace uvgb;
+
+extern "C" int uvg_b200_intra_predict_dev(int bitdepth, int n, const void *refs, const int8_t *modes, int k,
+                                          void *preds, size_t n_blocks, void *stream)
+{
+  if (ensure_init()) return 1;
+  if (bitdepth < 8 || bitdepth > 16) { set_error("bitdepth %d out of range", bitdepth); return 1; }
+  ModeTable mt;
+  if (fill_modes(mt, n, modes, k)) return 1;
+  if (n_blocks == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int pix = bitdepth == 8 ? 1 : 2;
+  const size_t smem = (size_t)4 * (2 * n + 12) * pix;
+  size_t grid = n_blocks;
+  const size_t cap = (size_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (bitdepth == 8)
+    intra_predict_kernel<uint8_t><<<(unsigned)grid, 256, smem, st>>>(static_cast<const uint8_t *>(refs),
+                                                                     static_cast<uint8_t *>(preds), n_blocks, n, mt, 255);
+  else
+    intra_predict_kernel<uint16_t><<<(unsigned)grid, 256, smem, st>>>(static_cast<const uint16_t *>(refs),
+                                                                      static_cast<uint16_t *>(preds), n_blocks, n, mt,
+                                                                      (1 << bitdepth) - 1);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int uvg_b200_intra_rough_dev(int bitdepth, int n, const uvg_b200_blocks *orig, const void *refs,
+                                        const int8_t *modes, int k, uint32_t *out, size_t n_blocks, void *stream)
+{
+  if (ensure_init()) return 1;
+  if (bitdepth != 8) { set_error("intra_rough: fused kernel is 8-bit; use intra_predict_dev + rough_cost_dev"); return 1; }
+  if (n != 8 && n != 16 && n != 32) { set_error("intra_rough: n must be 8, 16 or 32"); return 1; }
+  ModeTable mt;
+  if (fill_modes(mt, n, modes, k)) return 1;
+  if (n_blocks == 0) return 0;
+  const Blocks A = to_blocks(orig);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t grid = n_blocks;
+  const size_t cap = (size_t)sm_count() * 32;
+  if (grid > cap) grid = cap;
+  const uint8_t *r = static_cast<const uint8_t *>(refs);
+  if (n == 8) intra_rough_kernel<8><<<(unsigned)grid, 128, 0, st>>>(A, r, out, n_blocks, mt);
+  else if (n == 16) intra_rough_kernel<16><<<(unsigned)grid, 128, 0, st>>>(A, r, out, n_blocks, mt);
+  else intra_rough_kernel<32><<<(unsigned)grid, 128, 0, st>>>(A, r, out, n_blocks, mt);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
