@@ -28,7 +28,8 @@ import uvg266_b200 as U
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--no-cpu", action="store_true")
-ap.add_argument("--cpu-blocks", type=int, default=20000)
+ap.add_argument("--cpu-blocks", type=int, default=400000)
+ap.add_argument("--cpu-seconds", type=float, default=3.0)
 args = ap.parse_args()
 
 U.init(0)
@@ -118,13 +119,16 @@ for n, modes in LEVELS:
             if hi > lo:
                 R.H.refh_intra_rough_batch(n, m8.ctypes.data, k, srefs[lo:hi].ctypes.data, orig[lo:hi].ctypes.data,
                                            int(hi - lo), costs[lo * k:].ctypes.data)
-        t0 = time.perf_counter()
-        th = [threading.Thread(target=work, args=(t,)) for t in range(nt)]
-        [t.start() for t in th]; [t.join() for t in th]
-        dt = time.perf_counter() - t0
+        reps, dt = 0, 0.0
+        while dt < args.cpu_seconds:                      # repeat the sample until the leg ran long enough
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=work, args=(t,)) for t in range(nt)]
+            [t.start() for t in th]; [t.join() for t in th]
+            dt += time.perf_counter() - t0; reps += 1
+        dt /= reps
         g = d_cost.cpu().numpy().astype(np.uint32).reshape(nb, k)[sel].ravel()
         lvl.update({"cpu_threads": nt, "cpu_sample_blocks": int(ns), "cpu_candidates_per_s": round(ns * k / dt),
-                    "cpu_sample_s": round(dt, 2), "gpu_equals_reference_on_sample": bool((g == costs).all()),
+                    "cpu_sample_s": round(dt, 3), "cpu_reps": reps, "gpu_equals_reference_on_sample": bool((g == costs).all()),
                     "speedup_vs_cpu": round((nb * k / t_f * 1e3) / (ns * k / dt), 1)})
     res["levels"].append(lvl)
 tot = sum(l["fused_ms"] for l in res["levels"])

@@ -218,59 +218,209 @@ intra_predict_kernel(const Pix *__restrict__ refs, Pix *__restrict__ preds, size
 }
 
 // ---- fused rough search: predict + min(SATD, 2*SAD), 8-bit, n in {8, 16, 32} ----------------------
-// One CTA per block. Items = (mode, 8x8 sub-block); the original block is staged once in shared
-// memory, normal and transposed: horizontal modes are generated in their natural (transposed)
-// orientation and scored against the transposed original (a 2-D Hadamard abs-sum and a SAD do
-// not change under transposition), so every thread always produces 8 consecutive pixels of a row.
+// The predictions never exist in HBM: each thread generates 8x8 sub-blocks of a prediction row by
+// row in registers and feeds them to the packed Hadamard of hadamard.cuh.
+//
+// Work mapping. A CTA of 4 warps owns BPC = 32 / (N/8) consecutive blocks, staged once in shared
+// memory (reference rows + their smoothed copies, the original block and its transpose). Lane =
+// (block, 8-pixel column strip sx); the lane walks its strip top to bottom (sy = 0..N/8-1). Warp w
+// takes modes w, w+4, ...: a warp is always inside ONE mode and ONE row index, so the mode
+// decisions (direction, filter, PDPC), the row's displacement (delta_int, delta_fract) and the
+// interpolation filter are warp-uniform - no divergence.
+// Horizontal modes are generated in their natural transposed orientation (main = left row) and
+// scored against the transposed original: SAD and the 2-D Hadamard abs-sum do not change under
+// transposition, so there is no transposing store (intra-generic.c:286-298 flips a temp block).
+// One output pixel of the 4-tap interpolation is one dp4a: the row's 11-byte window of the main
+// reference is fetched as 4 aligned words and funnel-shifted; the filter is a packed s8x4 word.
+// Negative angles extend the main reference with the projected side reference (:145-156) into a
+// small per-warp scratch row that ends exactly where index 0 of the main row begins.
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
+{
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+template <int N>
+struct RoughCfg {
+  static constexpr int NS = N / 8;                   // 8-pixel strips per block row
+  static constexpr int BPC = 32 / NS;                // blocks per CTA
+  static constexpr int RS = 2 * N + 12;              // shared-memory pitch of one reference row
+  static constexpr int BS = 4 * RS + 4;              // per-block stride of the 4 rows: odd word count
+  static constexpr int HEAD = N + 8;                 // scratch for main-reference indices -HEAD..-1
+  static constexpr int OP = N * N + 8 * NS;          // per-block stride of the original (bank spread)
+};
+
+// One row (8 pixels: work-row r, work-columns 8*sx..8*sx+7) of an angular prediction.
+template <int N>
+__device__ __forceinline__ void angular_row8(const ModeParam &mp, const uint8_t *mainr, const uint8_t *side,
+                                             const uint8_t *ext0, int r, int sx, int lim, uint32_t &lo, uint32_t &hi)
+{
+  const int dpos = (r + 1) * mp.sample_disp, di = dpos >> 5, fr = dpos & 31;
+  int cw;
+  if (!mp.frac) cw = 64 << 8;                                              // integer slope: copy tap 1
+  else if (mp.cubic) cw = *reinterpret_cast<const int *>(c_cubic[fr]);
+  else { const int h = fr >> 1; cw = (16 - h) | ((32 - h) << 8) | ((16 + h) << 16) | (h << 24); }
+  const int i0 = di + 8 * sx, b0 = i0 & ~3, sh = (i0 & 3) * 8;
+  uint32_t W[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int b = b0 + 4 * j;
+    W[j] = *reinterpret_cast<const uint32_t *>((b >= 0 ? mainr : ext0) + b);
+  }
+  const uint32_t A0 = __funnelshift_r(W[0], W[1], sh), A1 = __funnelshift_r(W[1], W[2], sh),
+                 A2 = __funnelshift_r(W[2], W[3], sh);
+  int v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t a = c < 4 ? A0 : A1, b = c < 4 ? A1 : A2;
+    const uint32_t win = (c & 3) ? __funnelshift_r(a, b, 8 * (c & 3)) : a;
+    v[c] = min(max(dp4a_us(win, cw, 32) >> 6, 0), 255);
+  }
+  if (mp.pdpc) {
+    if (mp.sample_disp == 0) {                                            // :254-280
+      const int d = (int)side[1 + r] - (int)mainr[0];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int cc = 8 * sx + c;
+        if (cc < lim) v[c] = min(max(v[c] + (((32 >> ((2 * cc) >> mp.scale)) * d + 32) >> 6), 0), 255);
+      }
+    } else {                                                               // :234-251
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int cc = 8 * sx + c;
+        if (cc < lim) {
+          const int l = side[r + ((256 + (cc + 1) * mp.inv_angle) >> 9) + 1];
+          v[c] = (v[c] + (((32 >> ((2 * cc) >> mp.scale)) * (l - v[c]) + 32) >> 6)) & 255;
+        }
+      }
+    }
+  }
+  lo = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+  hi = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+}
+
 template <int N>
 __global__ void __launch_bounds__(128)
 intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restrict__ out, size_t n_blocks, ModeTable mt)
 {
-  constexpr int NS = N / 8, NSUB = NS * NS, SP = 2 * N + 12;
-  __shared__ __align__(16) uint8_t s_rows[4 * SP];
-  __shared__ __align__(16) uint8_t s_orig[N * N], s_origT[N * N];
-  __shared__ int s_dc;
-  constexpr int l2 = N == 8 ? 3 : N == 16 ? 4 : 5;
-  for (size_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
-    __syncthreads();
-    const uint8_t *pa = static_cast<const uint8_t *>(A.base) + A.offset(b);
-    for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
-      const int y = i / N, x = i - y * N;
-      const uint8_t v = __ldg(pa + (size_t)y * A.stride + x);
-      s_orig[i] = v; s_origT[x * N + y] = v;
-    }
-    stage_refs<uint8_t>(refs, b, N, SP, s_rows, &s_dc, threadIdx.x, blockDim.x);
-    RefRows<uint8_t> rr{ s_rows, s_rows + SP, s_rows + 2 * SP, s_rows + 3 * SP };
-    const int items = mt.k * NSUB;
-    for (int it0 = 0; it0 < items; it0 += blockDim.x) {
-      const int it = it0 + threadIdx.x;
-      unsigned satd = 0, sad = 0;
-      if (it < items) {
-        const int m = it / NSUB, sub = it - m * NSUB, sy = sub / NS, sx = sub - sy * NS;
-        const ModeParam mp = mt.m[m];
-        const bool transposed = mp.kind == 2 && !mp.vertical;
-        const uint8_t *orig = transposed ? s_origT : s_orig;
+  using Cfg = RoughCfg<N>;
+  constexpr int NS = Cfg::NS, BPC = Cfg::BPC, RS = Cfg::RS, BS = Cfg::BS, HEAD = Cfg::HEAD, OP = Cfg::OP;
+  constexpr int GP = 2 * N + 4, L2 = N == 8 ? 3 : N == 16 ? 4 : 5;
+  __shared__ __align__(16) uint8_t s_rows[BPC * BS];
+  __shared__ __align__(16) uint8_t s_ext[4][BPC][HEAD];
+  __shared__ __align__(16) uint8_t s_orig[BPC * OP], s_origT[BPC * OP];
+  __shared__ int s_dc[BPC];
+  const size_t first = (size_t)blockIdx.x * BPC;
+  const int tid = threadIdx.x;
+  // reference rows (tail replicated)
+  for (int i = tid; i < BPC * 2 * RS; i += 128) {
+    const int blk = i / (2 * RS), rem = i - blk * 2 * RS, row = rem / RS, x = rem - row * RS;
+    const size_t gb = min(first + blk, n_blocks - 1);
+    s_rows[blk * BS + row * RS + x] = __ldg(refs + gb * (size_t)(2 * GP) + row * GP + min(x, 2 * N));
+  }
+  // original blocks, as they are and transposed
+  for (int i = tid; i < BPC * N * N; i += 128) {
+    const int blk = i / (N * N), p = i - blk * N * N, y = p / N, x = p - y * N;
+    const size_t gb = min(first + blk, n_blocks - 1);
+    const uint8_t v = __ldg(static_cast<const uint8_t *>(A.base) + A.offset(gb) + (size_t)y * A.stride + x);
+    s_orig[blk * OP + p] = v;
+    s_origT[blk * OP + x * N + y] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < BPC * 2 * RS; i += 128) {                         // intra_filter_reference :190-225
+    const int blk = i / (2 * RS), rem = i - blk * 2 * RS, row = rem / RS, x = rem - row * RS;
+    const uint8_t *top = s_rows + blk * BS, *left = top + RS, *src = row ? left : top;
+    int v;
+    if (x == 0) v = ((int)left[1] + 2 * (int)left[0] + (int)top[1] + 2) >> 2;
+    else if (x < 2 * N) v = ((int)src[x - 1] + 2 * (int)src[x] + (int)src[x + 1] + 2) >> 2;
+    else v = src[2 * N];
+    s_rows[blk * BS + (2 + row) * RS + x] = (uint8_t)v;
+  }
+  if (tid < BPC) {                                                         // intra_pred_dc :236-273
+    const uint8_t *top = s_rows + tid * BS, *left = top + RS;
+    int sum = 0;
+    for (int i = 1; i <= N; ++i) sum += (int)top[i] + (int)left[i];
+    s_dc[tid] = (sum + N) >> (L2 + 1);
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31, blk = lane / NS, sx = lane % NS;
+  const size_t gb = first + blk;
+  const uint8_t *rows = s_rows + blk * BS;
+  uint8_t *ext0 = &s_ext[warp][blk][0] + HEAD;
+  for (int m = warp; m < mt.k; m += 4) {
+    const ModeParam mp = mt.m[m];
+    const uint8_t *top = rows + (mp.filtered ? 2 * RS : 0), *left = top + RS;
+    unsigned satd = 0, sad = 0;
+    if (mp.kind == 2) {
+      const uint8_t *mainr = mp.vertical ? top : left, *side = mp.vertical ? left : top;
+      const uint8_t *orig = (mp.vertical ? s_orig : s_origT) + blk * OP + 8 * sx;
+      if (mp.sample_disp < 0) {
+        __syncwarp();                                                     // previous mode's reads of the scratch
+        uint32_t e[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t w = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = 8 * sx + 8 - (4 * h + q);                      // main index -j
+            w |= (uint32_t)side[min((j * mp.inv_angle + 256) >> 9, N)] << (8 * q);
+          }
+          e[h] = w;
+        }
+        *reinterpret_cast<uint2 *>(ext0 - 8 * sx - 8) = make_uint2(e[0], e[1]);
+        __syncwarp();
+      }
+      const int lim = min(3 << mp.scale, N);
+#pragma unroll 1
+      for (int sy = 0; sy < NS; ++sy) {
         uint32_t wo[8][2], wc[8][2];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const uint2 o = *reinterpret_cast<const uint2 *>(orig + (sy * 8 + r) * N + sx * 8);
-          wo[r][0] = o.x; wo[r][1] = o.y;
-          uint32_t lo = 0, hi = 0;
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = sy * 8 + rr;
+          const uint2 o = *reinterpret_cast<const uint2 *>(orig + r * N);
+          wo[rr][0] = o.x; wo[rr][1] = o.y;
+          angular_row8<N>(mp, mainr, side, ext0, r, sx, lim, wc[rr][0], wc[rr][1]);
+        }
+        unsigned s1 = 0;
+        satd += satd8_words_u8<true>(wo, wc, s1);
+        sad += s1;
+      }
+    } else {
+      const uint8_t *orig = s_orig + blk * OP + 8 * sx;
+      const int dc = s_dc[blk], tr = top[N + 1], bl = left[N + 1];
+#pragma unroll 1
+      for (int sy = 0; sy < NS; ++sy) {
+        uint32_t wo[8][2], wc[8][2];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int Y = sy * 8 + rr, lY = left[Y + 1];
+          const uint2 o = *reinterpret_cast<const uint2 *>(orig + Y * N);
+          wo[rr][0] = o.x; wo[rr][1] = o.y;
+          const int wT = 32 >> min(31, (Y << 1) >> mp.scale);
+          uint32_t w2[2] = { 0, 0 };
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            // row (sy*8+r), column (sx*8+c) of the (possibly transposed) prediction
-            const int rowc = sy * 8 + r, colc = sx * 8 + c;
-            const int X = transposed ? rowc : colc, Y = transposed ? colc : rowc;
-            const uint32_t v = (uint32_t)pred_pixel<uint8_t>(mp, rr, N, l2, X, Y, s_dc, 255);
-            if (c < 4) lo |= v << (8 * c); else hi |= v << (8 * (c - 4));
+            const int X = 8 * sx + c, tX = top[X + 1];
+            int v = dc;
+            if (mp.kind == 0) {                                           // planar :306-360
+              const int hor = (lY << L2) + (X + 1) * (tr - lY), ver = (tX << L2) + (Y + 1) * (bl - tX);
+              v = ((hor << L2) + (ver << L2) + (1 << (2 * L2))) >> (1 + 2 * L2);
+            }
+            const int wL = 32 >> min(31, (X << 1) >> mp.scale);           // PDPC :414-437 (n >= 4 always)
+            v = (v + ((wL * (lY - v) + wT * (tX - v) + 32) >> 6)) & 255;
+            w2[c >> 2] |= (uint32_t)v << (8 * (c & 3));
           }
-          wc[r][0] = lo; wc[r][1] = hi;
+          wc[rr][0] = w2[0]; wc[rr][1] = w2[1];
         }
-        satd = satd8_words_u8<true>(wo, wc, sad);
+        unsigned s1 = 0;
+        satd += satd8_words_u8<true>(wo, wc, s1);
+        sad += s1;
       }
-      if (NSUB > 1) { satd = group_sum<NSUB>(satd); sad = group_sum<NSUB>(sad); }
-      if (it < items && (it % NSUB) == 0) out[b * mt.k + it / NSUB] = min(satd, 2 * sad);
     }
+    if (NS > 1) { satd = group_sum<NS>(satd); sad = group_sum<NS>(sad); }
+    if (sx == 0 && gb < n_blocks) out[gb * mt.k + m] = min(satd, 2 * sad);
   }
 }
 
@@ -326,13 +476,11 @@ extern "C" int uvg_b200_intra_rough_dev(int bitdepth, int n, const uvg_b200_bloc
   if (n_blocks == 0) return 0;
   const Blocks A = to_blocks(orig);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  size_t grid = n_blocks;
-  const size_t cap = (size_t)sm_count() * 32;
-  if (grid > cap) grid = cap;
   const uint8_t *r = static_cast<const uint8_t *>(refs);
-  if (n == 8) intra_rough_kernel<8><<<(unsigned)grid, 128, 0, st>>>(A, r, out, n_blocks, mt);
-  else if (n == 16) intra_rough_kernel<16><<<(unsigned)grid, 128, 0, st>>>(A, r, out, n_blocks, mt);
-  else intra_rough_kernel<32><<<(unsigned)grid, 128, 0, st>>>(A, r, out, n_blocks, mt);
+  auto grid = [&](int bpc) { return (unsigned)((n_blocks + bpc - 1) / bpc); };
+  if (n == 8) intra_rough_kernel<8><<<grid(RoughCfg<8>::BPC), 128, 0, st>>>(A, r, out, n_blocks, mt);
+  else if (n == 16) intra_rough_kernel<16><<<grid(RoughCfg<16>::BPC), 128, 0, st>>>(A, r, out, n_blocks, mt);
+  else intra_rough_kernel<32><<<grid(RoughCfg<32>::BPC), 128, 0, st>>>(A, r, out, n_blocks, mt);
   UVGB_LAUNCH_CHECK();
   return 0;
 }
