@@ -354,7 +354,7 @@ def test_batched_rough_cost(bd):
     rng = np.random.default_rng(1700 + bd)
     W, H = 128, 64
     plane = rnd_pix(rng, bd, W * H)
-    for (n, k) in ((4, 6), (8, 23), (16, 24), (32, 5), (64, 2)):
+    for (n, k) in ((4, 6), (8, 23), (16, 24), (32, 5), (64, 2), (8, 67), (16, 31), (32, 16), (8, 1), (8, 15)):
         nb = (W // n) * (H // n)
         a_desc = U.Blocks.plane(plane.ctypes.data, W, W, n, n)
         # predictions close to the source, like real intra candidates
@@ -494,3 +494,16 @@ def test_full_size_properties():
     U.check(L.uvg_b200_distortion_dev(U.SSD, 8, n, n, C.byref(A), C.byref(B), out1.data_ptr(), N, 1, None))
     d = (a.int() - b.int()).long()
     assert torch.equal(out1.long(), (d * d).sum(1))
+
+
+@pytest.mark.parametrize("mode", ["staged", "mma", "umma", "tma"])
+def test_rough_cost_kernel_variants(mode):
+    """The interchangeable rough-cost kernels (packed ALU, mma.sync IMMA, tcgen05/TMEM, TMA-fed) are
+    selected once per process by UVG266_B200_ROUGH: run the batched parity test under each."""
+    import os, subprocess, sys
+    env = dict(os.environ, UVG266_B200_ROUGH=mode)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-x", "-q",
+                        "-k", "test_batched_rough_cost or test_full_size_properties"], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

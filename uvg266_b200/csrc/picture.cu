@@ -10,6 +10,8 @@
 
 namespace uvgb {
 
+int launch_rough_umma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_items, int k, int n, cudaStream_t st);
+int launch_rough_mma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_items, int k, int n, cudaStream_t st);
 int launch_rough_staged(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_items, int k, int n,
                         cudaStream_t st);
 int launch_sad_search_u8(const uint8_t *cur, const uint8_t *ref, int pic_w, int pic_h, int stride,
@@ -637,7 +639,24 @@ extern "C" int uvg_b200_rough_cost_dev(int bitdepth, int n, const uvg_b200_block
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n_items = n_blocks * (size_t)k;
   if (bitdepth == 8) {
-    // dense, 16-byte aligned candidates: shared-memory staged kernel (rough.cu)
+    // dense candidates, three interchangeable kernels (all bit-exact, all in the GPU tests):
+    //   default           packed-ALU shared-memory staged kernel (rough.cu)       8x8 0.075 ms  16x16 0.081 ms
+    //   ROUGH=umma        Hadamard as tcgen05.mma kind::i8 into TMEM (rough_umma.cu)   0.082 ms        0.107 ms
+    //   ROUGH=mma         Hadamard as mma.sync IMMA (rough_mma.cu)                     0.090 ms        0.072 ms
+    //   ROUGH=tma         the staged kernel fed by cp.async.bulk                       0.081 ms        0.083 ms
+    // (one 4K frame of the bench workload on a B200, CUDA events). The default is the fastest
+    // measured per size: staged for 8x8, mma.sync for 16x16 / 32x32.
+    static const char *mode = getenv("UVG266_B200_ROUGH");
+    const bool want_umma = mode && !strcmp(mode, "umma");
+    const bool want_mma = mode ? !strcmp(mode, "mma") : n >= 16;
+    if (want_umma) {
+      const int ru = launch_rough_umma(A, B, out, n_items, k, n, st);
+      if (ru >= 0) return ru;
+    }
+    if (want_mma) {
+      const int rm = launch_rough_mma(A, B, out, n_items, k, n, st);
+      if (rm >= 0) return rm;
+    }
     const int rc = launch_rough_staged(A, B, out, n_items, k, n, st);
     if (rc >= 0) return rc;
   }
