@@ -125,12 +125,6 @@ __device__ __forceinline__ uint32_t fdivk(uint32_t x, const FastDivK &d)
 
 }  // namespace
 
-#ifdef UVGB_UMMA_DEBUG
-__device__ unsigned long long g_dbg[1024];
-#define DBG(slot, i) do { if (blockIdx.x == 0 && (i) >= 8 && (i) < 24) g_dbg[((i) - 8) * 16 + (slot)] = clock64(); } while (0)
-#else
-#define DBG(slot, i) do { } while (0)
-#endif
 
 template <int N, bool DENSE>      // DENSE: the original blocks are dense N x N, one after the other
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -225,11 +219,8 @@ rough_umma_kernel(Blocks A, const uint8_t *__restrict__ cand, uint32_t *__restri
       const uint32_t tile = tile0 + i * tstep, st = i % kStages, u = tile * kTileRows + r;
       const bool live = u < n_units;
       const uint8_t *tileA = sA + st * kTileBytes;
-      if (r == 0) DBG(0, i);
       fetch_orig(i + 2);                                 // this group's next tile
-      if (r == 0) DBG(1, i);
       bar_wait(&full_bar[st], (i / kStages) & 1);
-      if (r == 0) DBG(2, i);
       unsigned sd[4] = { 0, 0, 0, 0 };
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -239,9 +230,7 @@ rough_umma_kernel(Blocks A, const uint8_t *__restrict__ cand, uint32_t *__restri
         sd[2] = __vsadu4(p.z, o.z) + sd[2]; sd[3] = __vsadu4(p.w, o.w) + sd[3];
       }
       unsigned sad = (sd[0] + sd[1]) + (sd[2] + sd[3]);
-      if (r == 0) DBG(3, i);
       bar_wait(&acc_full[i & 1], (i >> 1) & 1);
-      if (r == 0) DBG(4, i);
       fence_after_sync();
       unsigned ac[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, dc = 0;
 #pragma unroll
@@ -267,18 +256,14 @@ rough_umma_kernel(Blocks A, const uint8_t *__restrict__ cand, uint32_t *__restri
       if (!live) sad = 0;
       if (NSUB > 1) { satd = group_sum<NSUB>(satd); sad = group_sum<NSUB>(sad); }
       if (live && (u & (NSUB - 1)) == 0) out[u >> LOG_NSUB] = min(satd, 2 * sad);
-      if (r == 0) DBG(5, i);
     }
   } else if (warp == 8 && lane == 0) {
     // ===== MMA issuer (one thread) =====
     const uint64_t bd = smem_desc_sw128(s32addr(sB));
     for (uint32_t i = 0; i < my_tiles; ++i) {
       const uint32_t st = i % kStages;
-      DBG(8, i);
       bar_wait(&full_bar[st], (i / kStages) & 1);
-      DBG(9, i);
       if (i >= 2) bar_wait(&acc_empty[i & 1], ((i >> 1) - 1) & 1);
-      DBG(10, i);
       fence_async_smem();                               // cp.async wrote the stage through the generic proxy
       fence_after_sync();
       const uint64_t ad = smem_desc_sw128(s32addr(sA + st * kTileBytes));
@@ -286,7 +271,6 @@ rough_umma_kernel(Blocks A, const uint8_t *__restrict__ cand, uint32_t *__restri
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) umma_i8(d, ad + 2 * ks, bd + 2 * ks, kIdesc, ks > 0);   // 32 bytes of K per MMA
       umma_commit(&acc_full[i & 1]);
-      DBG(11, i);
     }
   }
   fence_before_sync();
@@ -332,21 +316,6 @@ int launch_rough_umma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_
   else { if (dense) UVGB_UMMA_GO(32, true); else UVGB_UMMA_GO(32, false); }
 #undef UVGB_UMMA_GO
   UVGB_LAUNCH_CHECK();
-#ifdef UVGB_UMMA_DEBUG
-  if (getenv("UVG266_B200_UMMA_DBG")) {
-    static unsigned long long h[1024];
-    cudaStreamSynchronize(st);
-    cudaMemcpyFromSymbol(h, g_dbg, sizeof(h));
-    unsigned long long t0 = h[0];
-    for (int i = 0; i < 16; ++i) {
-      fprintf(stderr, "tile %2d  epi: start %6lld fetched %6lld full %6lld sad %6lld accfull %6lld end %6lld | mma: loop %6lld full %6lld accempty %6lld issued %6lld\n",
-              i + 8, (long long)(h[i * 16 + 0] - t0), (long long)(h[i * 16 + 1] - t0), (long long)(h[i * 16 + 2] - t0),
-              (long long)(h[i * 16 + 3] - t0), (long long)(h[i * 16 + 4] - t0), (long long)(h[i * 16 + 5] - t0),
-              (long long)(h[i * 16 + 8] - t0), (long long)(h[i * 16 + 9] - t0), (long long)(h[i * 16 + 10] - t0),
-              (long long)(h[i * 16 + 11] - t0));
-    }
-  }
-#endif
   return 0;
 }
 
