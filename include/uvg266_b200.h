@@ -288,6 +288,21 @@ UVG_B200_API void uvg_b200_set_dropin_bitdepth(int bitdepth);
 UVG_B200_DECL_PICTURE(8, uint8_t)
 UVG_B200_DECL_PICTURE(16, uint16_t)
 
+/* strategies-intra.h:46-80 (row 8(f)-2): the three leaves intra_predict_regular dispatches to
+ * (intra.c:729, :733, :751), with cu_loc_t flattened to the w x h of the predicted plane block
+ * (cu_loc->width/height for luma, chroma_width/chroma_height otherwise). `above` / `left` / `top` are
+ * the rows of uvg_intra_ref (intra.h:47-50: 2*128+3+33*3 samples each, index 0 = corner). */
+#define UVG_B200_DECL_INTRA(SUF, PIX)                                                           \
+  UVG_B200_API void uvg_b200_angular_pred_##SUF(int w, int h, int intra_mode, int channel_type, \
+                                                const PIX *above, const PIX *left, PIX *dst,    \
+                                                int multi_ref_idx, int isp_mode);               \
+  UVG_B200_API void uvg_b200_intra_pred_planar_##SUF(int w, int h, const PIX *top,              \
+                                                     const PIX *left, PIX *dst);                \
+  UVG_B200_API void uvg_b200_pdpc_planar_dc_##SUF(int mode, int w, int h, const PIX *top,       \
+                                                  const PIX *left, PIX *dst);
+UVG_B200_DECL_INTRA(8, uint8_t)
+UVG_B200_DECL_INTRA(16, uint16_t)
+
 /* strategies-dct.h:44 dct_func (the typedef's unsigned return is never used; void here) */
 UVG_B200_API void uvg_b200_dct_4x4(int8_t bitdepth, const int16_t *in, int16_t *out);
 UVG_B200_API void uvg_b200_dct_8x8(int8_t bitdepth, const int16_t *in, int16_t *out);

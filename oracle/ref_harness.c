@@ -229,6 +229,40 @@ void refh_intra_predict(int w, int h, int mode, const uvg_pixel *top, const uvg_
   uvg_intra_predict(g_state, &refs, &loc, &loc, COLOR_Y, dst, &data, NULL);
 }
 
+/* The three intra strategy leaves with their own arguments (strategies-intra.h:46-80). w x h is the
+ * block in the plane that is predicted: for chroma the cu_loc is built twice as large so that its
+ * chroma_width / chroma_height are w x h. `above` / `left` must hold 2*128+3+33*3 samples like
+ * uvg_intra_ref (intra.h:47-50). */
+static void leaf_loc(cu_loc_t *loc, int w, int h, int channel_type)
+{
+  if (channel_type == 0) uvg_cu_loc_ctor(loc, 0, 0, w, h);
+  else uvg_cu_loc_ctor(loc, 0, 0, 2 * w, 2 * h);
+}
+void refh_angular_pred_leaf(int w, int h, int mode, int channel_type, const uvg_pixel *above, const uvg_pixel *left,
+                            uvg_pixel *dst, int mrl, int isp)
+{
+  cu_loc_t loc;
+  leaf_loc(&loc, w, h, channel_type);
+  uvg_angular_pred(&loc, (int_fast8_t)mode, (int_fast8_t)channel_type, above, left, dst, (uint8_t)mrl, (uint8_t)isp, w * h);
+}
+void refh_intra_pred_planar_leaf(int w, int h, int channel_type, const uvg_pixel *top, const uvg_pixel *left, uvg_pixel *dst)
+{
+  cu_loc_t loc;
+  leaf_loc(&loc, w, h, channel_type);
+  uvg_intra_pred_planar(&loc, (color_t)channel_type, top, left, dst);
+}
+void refh_pdpc_planar_dc_leaf(int mode, int w, int h, int channel_type, const uvg_pixel *top, const uvg_pixel *left,
+                              uvg_pixel *dst)
+{
+  static __thread uvg_intra_ref ref;
+  cu_loc_t loc;
+  leaf_loc(&loc, w, h, channel_type);
+  memcpy(ref.top, top, sizeof(ref.top));
+  memcpy(ref.left, left, sizeof(ref.left));
+  uvg_pdpc_planar_dc(mode, &loc, (color_t)channel_type, &ref, dst);
+}
+int refh_intra_ref_len(void) { return (int)(sizeof(((uvg_intra_ref *)0)->top) / sizeof(uvg_pixel)); }
+
 /* Rough intra search of a slice of blocks, the way search_intra_rough scores candidates
  * (search_intra.c:1055-1062 + get_cost :149-163): uvg_intra_predict for each of k modes, then
  * min(SATD, 2 * SAD) against the original block. Re-entrant (one call per worker thread).

@@ -795,27 +795,31 @@ static const int8_t k_cubic[32][4] = {
   { -2, 14, 56, -4 }, { -2, 12, 57, -3 }, { -2, 10, 58, -2 }, { -1, 7, 60, -2 }, { 0, 4, 62, -2 }, { 0, 2, 63, -1 } };
 
 /* uvg_angular_pred_generic, intra-generic.c:55-299, luma, multi_ref_idx = 0, isp = 0. */
-void orc_angular_pred(int w, int h, int pred_mode, const orc_pixel *ref_above, const orc_pixel *ref_left,
-                      orc_pixel *dst)
+/* The strategy leaf uvg_angular_pred_generic (intra-generic.c:55-299) with all its arguments:
+ * w x h = the block in the plane that is predicted (chroma dims for channel_type != 0),
+ * intra_mode already wide-angle corrected (may be < 2 or > 66), multi_ref_idx, isp_mode. */
+void orc_angular_pred_leaf(int w, int h, int intra_mode, int channel_type, const orc_pixel *ref_above,
+                           const orc_pixel *ref_left, orc_pixel *dst, int mrl, int isp)
 {
   const int l2w = ilog2(w), l2h = ilog2(h);
-  const int vertical = pred_mode >= 34;
+  const int pred_mode = intra_mode;
+  const int vertical = intra_mode >= 34;
   const int mode_disp = vertical ? pred_mode - 50 : 18 - pred_mode;
   const int ad = mode_disp < 0 ? -mode_disp : mode_disp;
   const int sample_disp = (mode_disp < 0 ? -1 : 1) * k_modedisp2sampledisp[ad];
   const int side_size = vertical ? l2h : l2w;
   int scale = side_size - k_pre_scale[ad];
   if (scale > 2) scale = 2;
-  orc_pixel main_buf[2 * 64 + 8 + 64], *ref_main;
+  orc_pixel main_buf[2 * 128 + 3 + 33 * 3 + 128], *ref_main;
   const orc_pixel *ref_side;
-  orc_pixel work[32 * 32];
+  orc_pixel work[64 * 64];
   int W = w, H = h;
   if (sample_disp < 0) {
     /* project the side reference onto the negative part of the main reference (:145-156) */
     const orc_pixel *m = vertical ? ref_above : ref_left, *sd = vertical ? ref_left : ref_above;
     const int msz = vertical ? w : h, ssz = vertical ? h : w;
-    ref_main = main_buf + 64;
-    for (int i = 0; i < msz + 2; ++i) ref_main[i] = m[i];
+    ref_main = main_buf + 128;
+    for (int i = 0; i < msz + 2 + mrl; ++i) ref_main[i] = m[i];
     for (int i = -ssz; i <= -1; ++i) {
       int idx = (-i * k_modedisp2invsampledisp[ad] + 256) >> 9;
       if (idx > ssz) idx = ssz;
@@ -826,6 +830,8 @@ void orc_angular_pred(int w, int h, int pred_mode, const orc_pixel *ref_above, c
     ref_main = (orc_pixel *)(vertical ? ref_above : ref_left);
     ref_side = vertical ? ref_left : ref_above;
   }
+  ref_main += mrl;                                     /* line offset in the reference buffers (:158-160) */
+  ref_side += mrl;
   if (!vertical) { int t = W; W = H; H = t; }
   if (sample_disp != 0) {
     int use_cubic = 1;
@@ -836,24 +842,34 @@ void orc_angular_pred(int w, int h, int pred_mode, const orc_pixel *ref_above, c
     const int dist = d50 < d18 ? d50 : d18;
     const int frac_mode = ((sample_disp < 0 ? -sample_disp : sample_disp) & 0x1f) != 0;
     if (dist > thr && frac_mode) use_cubic = 0;
-    for (int y = 0, delta_pos = sample_disp; y < H; ++y, delta_pos += sample_disp) {
+    if (mrl || isp) use_cubic = 1;                     /* :176-179 */
+    for (int y = 0, delta_pos = sample_disp * (1 + mrl); y < H; ++y, delta_pos += sample_disp) {
       const int delta_int = delta_pos >> 5, fr = delta_pos & 31;
       const int gauss[4] = { 16 - (fr >> 1), 32 - (fr >> 1), 16 + (fr >> 1), fr >> 1 };
       if (frac_mode) {
-        for (int x = 0; x < W; ++x) {
-          const orc_pixel *p = &ref_main[delta_int + x];
-          int s = 32;
-          for (int k = 0; k < 4; ++k) s += (use_cubic ? k_cubic[fr][k] : gauss[k]) * (int)p[k];
-          work[y * W + x] = (orc_pixel)clip3(0, PIXEL_MAX, s >> 6);
+        if (channel_type == 0) {
+          for (int x = 0; x < W; ++x) {
+            const orc_pixel *p = &ref_main[delta_int + x];
+            int s = 32;
+            for (int k = 0; k < 4; ++k) s += (use_cubic ? k_cubic[fr][k] : gauss[k]) * (int)p[k];
+            work[y * W + x] = (orc_pixel)clip3(0, PIXEL_MAX, s >> 6);
+          }
+        } else {                                       /* chroma: 2-tap linear (:207-214) */
+          for (int x = 0; x < W; ++x) {
+            const int r1 = ref_main[x + delta_int + 1], r2 = ref_main[x + delta_int + 2];
+            work[y * W + x] = (orc_pixel)(r1 + ((fr * (r2 - r1) + 16) >> 5));
+          }
         }
       } else {
         for (int x = 0; x < W; ++x) work[y * W + x] = ref_main[x + delta_int + 1];
       }
-      /* PDPC for angular modes (:234-252) */
-      int pdpc = (W >= 4 && H >= 4);
-      if (mode_disp < 0) pdpc = 0;
-      else if (mode_disp > 0) pdpc = pdpc && (scale >= 0);
-      if (pdpc) {
+      /* PDPC for angular modes (:226-251); wide-angle modes (outside 2..66) skip the mode tests */
+      int pdpc = (W >= 4 && H >= 4) && mrl == 0;
+      if (pred_mode > 1 && pred_mode < 67) {
+        if (mode_disp < 0 || mrl) pdpc = 0;
+        else if (mode_disp > 0) pdpc = pdpc && (scale >= 0);
+      }
+      if (pdpc && scale >= 0) {
         int inv_angle_sum = 256;
         const int lim = (3 << scale) < W ? (3 << scale) : W;
         for (int x = 0; x < lim; ++x) {
@@ -867,7 +883,7 @@ void orc_angular_pred(int w, int h, int pred_mode, const orc_pixel *ref_above, c
     }
   } else {
     /* pure horizontal / vertical (:254-280) with PDPC */
-    const int do_pdpc = (W >= 4 && H >= 4);
+    const int do_pdpc = (W >= 4 && H >= 4) && mrl == 0;
     const int sc = (l2w + l2h - 2) >> 2;
     const int top_left = ref_main[0];
     for (int y = 0; y < H; ++y) {
@@ -889,6 +905,13 @@ void orc_angular_pred(int w, int h, int pred_mode, const orc_pixel *ref_above, c
     for (int y = 0; y < h; ++y)
       for (int x = 0; x < w; ++x) dst[y * w + x] = work[x * W + y];
   }
+}
+
+/* luma, reference line 0, no ISP */
+void orc_angular_pred(int w, int h, int pred_mode, const orc_pixel *ref_above, const orc_pixel *ref_left,
+                      orc_pixel *dst)
+{
+  orc_angular_pred_leaf(w, h, pred_mode, 0, ref_above, ref_left, dst, 0, 0);
 }
 
 /* uvg_intra_pred_planar_generic :306-360 */

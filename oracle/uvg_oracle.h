@@ -115,6 +115,8 @@ uint32_t orc_fast_coeff_cost(const int16_t *coeff, int w, int h, uint64_t weight
 /* ---- strategies-intra (next row 8(f)-2), luma, mrl = 0, no ISP / MIP ----------------- */
 void orc_angular_pred(int w, int h, int pred_mode, const orc_pixel *ref_above, const orc_pixel *ref_left,
                       orc_pixel *dst);
+void orc_angular_pred_leaf(int w, int h, int intra_mode, int channel_type, const orc_pixel *ref_above,
+                           const orc_pixel *ref_left, orc_pixel *dst, int multi_ref_idx, int isp_mode);
 void orc_intra_pred_planar(int w, int h, const orc_pixel *ref_top, const orc_pixel *ref_left, orc_pixel *dst);
 void orc_intra_pred_dc(int w, int h, const orc_pixel *ref_top, const orc_pixel *ref_left, orc_pixel *dst);
 void orc_pdpc_planar_dc(int w, int h, const orc_pixel *ref_top, const orc_pixel *ref_left, orc_pixel *dst);

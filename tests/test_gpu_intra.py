@@ -95,3 +95,46 @@ def test_intra_errors():
     assert L.uvg_b200_intra_predict_host(8, 12, ptr(buf), ptr(modes), 2, ptr(buf), 1) != 0
     desc = U.Blocks.dense(buf.ctypes.data, 8, 8)
     assert L.uvg_b200_intra_rough_host(10, 8, C.byref(desc), 64, ptr(buf), ptr(modes), 2, ptr(buf), 1) != 0
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_intra_leaf_dropins(bd):
+    """The strategy-leaf drop-ins (angular_pred / intra_pred_planar / pdpc_planar_dc signatures) with every
+    argument the encoder passes: non-square, wide angles, chroma, multi_ref_idx, ISP."""
+    O = load_oracle(bd)
+    O.orc_angular_pred_leaf.argtypes = [ci, ci, ci, ci, vp, vp, vp, ci, ci]
+    O.orc_intra_pred_planar.argtypes = [ci, ci, vp, vp, vp]
+    O.orc_pdpc_planar_dc.argtypes = [ci, ci, vp, vp, vp]
+    L = U.lib()
+    L.uvg_b200_set_dropin_bitdepth(10)
+    suf = U.suffix(bd)
+    ang, pla, pdp = (getattr(L, "uvg_b200_%s_%s" % (n, suf)) for n in ("angular_pred", "intra_pred_planar", "pdpc_planar_dc"))
+    rng = np.random.default_rng(5300 + bd)
+    hi = (1 << bd) - 1
+    RL = 2 * 128 + 3 + 33 * 3
+    # ISP predicts strips of a CU with the CU's (uncorrected) mode: every mode on every shape, sizes down to 2
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (16, 4), (4, 16), (32, 8), (8, 32), (64, 64), (8, 2), (2, 8),
+                   (16, 2), (2, 16), (32, 2), (2, 32), (4, 2), (8, 4), (4, 8), (32, 4), (4, 32), (16, 8), (32, 16)]:
+        above = rng.integers(0, hi + 1, RL).astype(pix_dtype(bd)); left = rng.integers(0, hi + 1, RL).astype(pix_dtype(bd))
+        left[0] = above[0]
+        ratio = abs(int(np.log2(w)) - int(np.log2(h)))
+        extra = 0 if w == h else (6 if ratio == 1 else 10 if ratio == 2 else 12 if ratio == 3 else 14)
+        modes = list(range(2, 67))
+        if w > h: modes += list(range(67, 67 + extra))
+        if h > w: modes += list(range(2 - extra, 2))
+        for mode in modes[::2] if w * h >= 256 else modes:
+            for (ch, mrl, isp) in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1), (0, 0, 2)):
+                if max(w, h) > 32 and ch == 0:
+                    continue
+                d1 = np.zeros(w * h, pix_dtype(bd)); d2 = np.zeros(w * h, pix_dtype(bd))
+                O.orc_angular_pred_leaf(w, h, mode, ch, ptr(above), ptr(left), ptr(d1), mrl, isp)
+                ang(w, h, mode, ch, ptr(above), ptr(left), ptr(d2), mrl, isp)
+                assert (d1 == d2).all(), (bd, w, h, mode, ch, mrl, isp)
+        if max(w, h) <= 32:
+            d1 = np.zeros(w * h, pix_dtype(bd)); d2 = np.zeros(w * h, pix_dtype(bd))
+            O.orc_intra_pred_planar(w, h, ptr(above), ptr(left), ptr(d1)); pla(w, h, ptr(above), ptr(left), ptr(d2))
+            assert (d1 == d2).all(), ("planar", bd, w, h)
+        if max(w, h) <= 32 and min(w, h) >= 4:
+            d1[:] = rng.integers(0, hi + 1, w * h); d2[:] = d1
+            O.orc_pdpc_planar_dc(w, h, ptr(above), ptr(left), ptr(d1)); pdp(1, w, h, ptr(above), ptr(left), ptr(d2))
+            assert (d1 == d2).all(), ("pdpc", bd, w, h)

@@ -71,3 +71,50 @@ def test_intra_rough_batch_matches_oracle():
                 O.orc_intra_predict(n, n, m, ptr(top), ptr(left), ptr(d))
                 e = min(O.orc_satd_nxn(n, ptr(orig[b]), ptr(d)), 2 * O.orc_sad_nxn(n, ptr(orig[b]), ptr(d)))
                 assert costs[b * 67 + m] == e, (n, b, m)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_intra_leaves_all_arguments(bd):
+    """The strategy leaves with every argument the encoder can pass: wide-angle corrected modes
+    (-14..80), chroma (2-tap filter), multi_ref_idx 1..2 (luma), ISP, non-square blocks."""
+    O, R = load_oracle(bd), load_ref(bd)
+    L = R.H.refh_intra_ref_len()
+    O.orc_angular_pred_leaf.argtypes = [ci, ci, ci, ci, vp, vp, vp, ci, ci]
+    R.H.refh_angular_pred_leaf.argtypes = [ci, ci, ci, ci, vp, vp, vp, ci, ci]
+    O.orc_intra_pred_planar.argtypes = [ci, ci, vp, vp, vp]
+    R.H.refh_intra_pred_planar_leaf.argtypes = [ci, ci, ci, vp, vp, vp]
+    O.orc_pdpc_planar_dc.argtypes = [ci, ci, vp, vp, vp]
+    R.H.refh_pdpc_planar_dc_leaf.argtypes = [ci, ci, ci, ci, vp, vp, vp]
+    rng = np.random.default_rng(4400 + bd)
+    hi = (1 << bd) - 1
+    shapes = [(4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 8), (16, 4), (4, 16), (32, 8), (8, 32), (16, 32), (64, 64)]
+    n = 0
+    for (w, h) in shapes:
+        above = rng.integers(0, hi + 1, L).astype(pix_dtype(bd)); left = rng.integers(0, hi + 1, L).astype(pix_dtype(bd))
+        left[0] = above[0]
+        # legal wide-angle range for this shape (uvg_wide_angle_correction, intra.c:637-658)
+        ratio = abs(int(np.log2(w)) - int(np.log2(h)))
+        extra = 0 if w == h else (6 if ratio == 1 else 10 if ratio == 2 else 12 if ratio == 3 else 14)
+        modes = list(range(2, 67))
+        if w > h: modes = [m for m in modes if m >= 2 + extra] + list(range(67, 67 + extra))
+        if h > w: modes = [m for m in modes if m <= 66 - extra] + list(range(2 - extra, 2))
+        for mode in modes:
+            for (ch, mrl, isp) in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1)):
+                if max(w, h) > 32 and ch == 0:
+                    continue                    # 64-wide luma blocks are never predicted in one piece
+                d1 = np.zeros(w * h, pix_dtype(bd)); d2 = np.zeros(w * h, pix_dtype(bd))
+                O.orc_angular_pred_leaf(w, h, mode, ch, ptr(above), ptr(left), ptr(d1), mrl, isp)
+                R.H.refh_angular_pred_leaf(w, h, mode, ch, ptr(above), ptr(left), ptr(d2), mrl, isp)
+                assert (d1 == d2).all(), (bd, w, h, mode, ch, mrl, isp)
+                n += 1
+        if max(w, h) <= 32:
+            d1 = np.zeros(w * h, pix_dtype(bd)); d2 = np.zeros(w * h, pix_dtype(bd))
+            O.orc_intra_pred_planar(w, h, ptr(above), ptr(left), ptr(d1))
+            R.H.refh_intra_pred_planar_leaf(w, h, 0, ptr(above), ptr(left), ptr(d2))
+            assert (d1 == d2).all(), ("planar", bd, w, h)
+            if w >= 4 and h >= 4:
+                d1[:] = rng.integers(0, hi + 1, w * h); d2[:] = d1
+                O.orc_pdpc_planar_dc(w, h, ptr(above), ptr(left), ptr(d1))
+                R.H.refh_pdpc_planar_dc_leaf(1, w, h, 0, ptr(above), ptr(left), ptr(d2))
+                assert (d1 == d2).all(), ("pdpc", bd, w, h)
+    assert n > 2000

@@ -122,6 +122,9 @@ def lib():
         f = getattr(L, "uvg_b200_hor_sad_" + suf); f.argtypes = [vp, vp, i, i] + [C.c_uint32] * 4; f.restype = C.c_uint32
         f = getattr(L, "uvg_b200_generate_residual_" + suf); f.argtypes = [vp, vp, vp, i, i, i, i]; f.restype = None
         f = getattr(L, "uvg_b200_get_optimized_sad_" + suf); f.argtypes = [C.c_int32]; f.restype = vp
+        f = getattr(L, "uvg_b200_angular_pred_" + suf); f.argtypes = [i, i, i, i, vp, vp, vp, i, i]; f.restype = None
+        f = getattr(L, "uvg_b200_intra_pred_planar_" + suf); f.argtypes = [i, i, vp, vp, vp]; f.restype = None
+        f = getattr(L, "uvg_b200_pdpc_planar_dc_" + suf); f.argtypes = [i, i, i, vp, vp, vp]; f.restype = None
         f = getattr(L, "uvg_b200_quantize_residual_" + suf)
         f.argtypes = [QP, i, i, i, i, i, i, i, i, vp, vp, vp, vp, i]; f.restype = i
     for n in (4, 8, 16, 32):

@@ -160,6 +160,7 @@ static unsigned dropin_pair(int metric, int bitdepth, int w, int h, const Pix *a
   return r;
 }
 
+int dropin_bitdepth(size_t pixel_size) { return pixel_size == 1 ? 8 : g_dropin_bd.load(); }
 template <typename Pix> static int bd_of() { return sizeof(Pix) == 1 ? 8 : g_dropin_bd.load(); }
 
 // hor_sad_generic / ver_sad_generic (picture-generic.c:1266-1331) replicate one reference

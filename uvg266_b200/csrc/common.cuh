@@ -43,6 +43,7 @@ extern std::atomic<uint64_t> g_launches;
   } while (0)
 
 int ensure_init();      // 0 ok; sets device, tables
+int dropin_bitdepth(size_t pixel_size);   // bit depth the leaf drop-ins assume for this pixel type (api.cu)
 int sm_count();
 
 // ---- block addressing ---------------------------------------------------------------

@@ -28,6 +28,11 @@ __constant__ short c_sampledisp[32] = { 0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18,
   35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024 };
 static const short h_sampledisp[32] = { 0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29, 32,
   35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024 };
+__constant__ short c_invsampledisp[32] = { 0, 16384, 8192, 5461, 4096, 2731, 2048, 1638, 1365, 1170,
+  1024, 910, 819, 712, 630, 565, 512, 468, 420, 364, 321, 287, 256, 224, 191, 161, 128, 96, 64, 48, 32, 16 };
+__constant__ signed char c_pre_scale[32] = { 8, 7, 6, 5, 5, 4, 4, 4, 3, 3, 3, 3, 3, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1,
+  0, 0, 0, -1, -1, -2, -3 };
+__constant__ signed char c_dist_thres[8] = { 24, 24, 24, 14, 2, 0, 0, 0 };
 static const short h_invsampledisp[32] = { 0, 16384, 8192, 5461, 4096, 2731, 2048, 1638, 1365, 1170,
   1024, 910, 819, 712, 630, 565, 512, 468, 420, 364, 321, 287, 256, 224, 191, 161, 128, 96, 64, 48, 32, 16 };
 static const signed char h_pre_scale[32] = { 8, 7, 6, 5, 5, 4, 4, 4, 3, 3, 3, 3, 3, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1,
@@ -424,6 +429,95 @@ intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restr
   }
 }
 
+// ---- strategy leaves with all their arguments (drop-ins, one block per call) ------------------------
+// uvg_angular_pred (intra-generic.c:55-299), uvg_intra_pred_planar (:306-360), uvg_pdpc_planar_dc
+// (:414-437) exactly as the encoder calls them from intra_predict_regular: any w x h in 4..64 (2..64
+// for chroma), wide-angle corrected modes, chroma's 2-tap filter, multi_ref_idx, isp_mode.
+struct LeafParams { int kind, w, h, mode, channel, mrl, isp, pixel_max, ref_len; };   // kind 0 angular, 1 planar, 2 pdpc
+
+template <typename Pix>
+__global__ void __launch_bounds__(256)
+intra_leaf_kernel(LeafParams p, const Pix *__restrict__ above_g, const Pix *__restrict__ left_g, Pix *__restrict__ dst)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Pix *above = reinterpret_cast<Pix *>(smem_raw), *left = above + p.ref_len;
+  for (int i = threadIdx.x; i < p.ref_len; i += blockDim.x) { above[i] = above_g[i]; left[i] = left_g[i]; }
+  __syncthreads();
+  const int w = p.w, h = p.h, l2w = ilog2_dev(w), l2h = ilog2_dev(h);
+  const int pmask = sizeof(Pix) == 1 ? 0xff : 0xffff;
+  if (p.kind == 1) {
+    const int tr = above[w + 1], bl = left[h + 1];
+    for (int e = threadIdx.x; e < w * h; e += blockDim.x) {
+      const int y = e / w, x = e - y * w;
+      const int hor = ((int)left[y + 1] << l2w) + (x + 1) * (tr - (int)left[y + 1]);
+      const int ver = ((int)above[x + 1] << l2h) + (y + 1) * (bl - (int)above[x + 1]);
+      dst[e] = (Pix)(((hor << l2h) + (ver << l2w) + (1 << (l2w + l2h))) >> (1 + l2w + l2h));
+    }
+    return;
+  }
+  if (p.kind == 2) {
+    const int scale = (l2w + l2h - 2) >> 2;
+    for (int e = threadIdx.x; e < w * h; e += blockDim.x) {
+      const int y = e / w, x = e - y * w;
+      const int wT = 32 >> min(31, (y << 1) >> scale), wL = 32 >> min(31, (x << 1) >> scale);
+      const int cur = dst[e];
+      dst[e] = (Pix)((cur + ((wL * ((int)left[y + 1] - cur) + wT * ((int)above[x + 1] - cur) + 32) >> 6)) & pmask);
+    }
+    return;
+  }
+  const int mode = p.mode, mrl = p.mrl;
+  const bool vertical = mode >= 34;
+  const int mode_disp = vertical ? mode - 50 : 18 - mode, ad = abs(mode_disp);
+  const int sd = (mode_disp < 0 ? -1 : 1) * c_sampledisp[ad], inv = c_invsampledisp[ad];
+  const int scale = min(2, (vertical ? l2h : l2w) - c_pre_scale[ad]);
+  const int W = vertical ? w : h, H = vertical ? h : w;              // work block: horizontal modes are transposed
+  const Pix *main_in = vertical ? above : left, *side_in = vertical ? left : above;
+  auto MAINP = [&](int j) -> int {                                    // ref_main[j] after "ref_main += mrl"
+    const int idx = j + mrl;
+    return idx >= 0 ? main_in[idx] : side_in[min((-idx * inv + 256) >> 9, H)];
+  };
+  const bool frac = (abs(sd) & 31) != 0;
+  bool cubic = true;
+  if (min(abs(mode - 50), abs(mode - 18)) > c_dist_thres[(l2w + l2h) >> 1] && frac) cubic = false;
+  if (mrl || p.isp) cubic = true;
+  bool pdpc = W >= 4 && H >= 4 && mrl == 0;
+  if (sd != 0) {
+    if (mode > 1 && mode < 67) {
+      if (mode_disp < 0) pdpc = false;
+      else if (mode_disp > 0) pdpc = pdpc && scale >= 0;
+    }
+    pdpc = pdpc && scale >= 0;                                        // (3 << negative) is undefined in the reference
+  }
+  const int sc0 = (l2w + l2h - 2) >> 2;
+  for (int e = threadIdx.x; e < W * H; e += blockDim.x) {
+    const int r = e / W, c = e - r * W;
+    int v;
+    if (sd == 0) {
+      v = MAINP(1 + c);
+      if (pdpc && c < min(3 << sc0, W))
+        v = clip3(0, p.pixel_max, v + (((32 >> ((2 * c) >> sc0)) * ((int)side_in[1 + r + mrl] - MAINP(0)) + 32) >> 6));
+    } else {
+      const int dpos = (r + 1 + mrl) * sd, di = dpos >> 5, fr = dpos & 31;
+      if (!frac) {
+        v = MAINP(c + di + 1);
+      } else if (p.channel == 0) {
+        int f0, f1, f2, f3;
+        if (cubic) { f0 = c_cubic[fr][0]; f1 = c_cubic[fr][1]; f2 = c_cubic[fr][2]; f3 = c_cubic[fr][3]; }
+        else { f0 = 16 - (fr >> 1); f1 = 32 - (fr >> 1); f2 = 16 + (fr >> 1); f3 = fr >> 1; }
+        v = clip3(0, p.pixel_max, (f0 * MAINP(di + c) + f1 * MAINP(di + c + 1) + f2 * MAINP(di + c + 2) + f3 * MAINP(di + c + 3) + 32) >> 6);
+      } else {
+        const int r1 = MAINP(c + di + 1), r2 = MAINP(c + di + 2);
+        v = (r1 + ((fr * (r2 - r1) + 16) >> 5)) & pmask;
+      }
+      if (pdpc && c < min(3 << scale, W)) {
+        const int l = side_in[r + ((256 + (c + 1) * inv) >> 9) + 1 + mrl];
+        v = (v + (((32 >> ((2 * c) >> scale)) * (l - v) + 32) >> 6)) & pmask;
+      }
+    }
+    dst[vertical ? r * w + c : c * w + r] = (Pix)v;
+  }
+}
+
 static int fill_modes(ModeTable &mt, int n, const int8_t *modes, int k)
 {
   if (n != 4 && n != 8 && n != 16 && n != 32) { set_error("intra: block size %d unsupported", n); return 1; }
@@ -484,3 +578,60 @@ extern "C" int uvg_b200_intra_rough_dev(int bitdepth, int n, const uvg_b200_bloc
   UVGB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- drop-in leaves (host pointers, synchronous, per-thread stream + staging) -----------------------
+namespace {
+constexpr int kRefLen = 2 * 128 + 3 + 33 * 3;      // uvg_intra_ref rows (intra.h:47-50)
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename Pix>
+void leaf_call(const LeafParams &lp, const void *above, const void *left, void *dst, bool dst_in)
+{
+  if (ensure_init()) { fprintf(stderr, "uvg266_b200: %s\n", uvg_b200_last_error()); abort(); }
+  Staging &s = tls_staging();
+  const size_t rb = align_up(kRefLen * sizeof(Pix), 256), db = (size_t)lp.w * lp.h * sizeof(Pix);
+  if (s.ensure(0, 2 * rb + align_up(db, 256))) { fprintf(stderr, "uvg266_b200: %s\n", uvg_b200_last_error()); abort(); }
+  UVGB_MUST(cudaMemcpyAsync(s.d_buf, above, kRefLen * sizeof(Pix), cudaMemcpyHostToDevice, s.stream));
+  UVGB_MUST(cudaMemcpyAsync(s.d_buf + rb, left, kRefLen * sizeof(Pix), cudaMemcpyHostToDevice, s.stream));
+  Pix *d_dst = reinterpret_cast<Pix *>(s.d_buf + 2 * rb);
+  if (dst_in) UVGB_MUST(cudaMemcpyAsync(d_dst, dst, db, cudaMemcpyHostToDevice, s.stream));
+  intra_leaf_kernel<Pix><<<1, 256, 2 * kRefLen * sizeof(Pix), s.stream>>>(lp, reinterpret_cast<const Pix *>(s.d_buf),
+                                                                        reinterpret_cast<const Pix *>(s.d_buf + rb), d_dst);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  UVGB_MUST(cudaGetLastError());
+  UVGB_MUST(cudaMemcpyAsync(dst, d_dst, db, cudaMemcpyDeviceToHost, s.stream));
+  UVGB_MUST(cudaStreamSynchronize(s.stream));
+}
+void leaf_check(int w, int h, const char *what)
+{
+  const bool okw = w == 2 || w == 4 || w == 8 || w == 16 || w == 32 || w == 64;
+  const bool okh = h == 2 || h == 4 || h == 8 || h == 16 || h == 32 || h == 64;
+  if (!okw || !okh) { fprintf(stderr, "uvg266_b200: %s: block %dx%d unsupported\n", what, w, h); abort(); }
+}
+}  // namespace
+
+#define UVGB_INTRA_LEAVES(SUF, PIX)                                                                              \
+  extern "C" void uvg_b200_angular_pred_##SUF(int w, int h, int intra_mode, int channel_type, const PIX *above,   \
+                                              const PIX *left, PIX *dst, int multi_ref_idx, int isp_mode)         \
+  {                                                                                                              \
+    leaf_check(w, h, "angular_pred");                                                                            \
+    if (intra_mode < -14 || intra_mode > 80 || multi_ref_idx < 0 || multi_ref_idx > 3) {                          \
+      fprintf(stderr, "uvg266_b200: angular_pred: mode %d / ref line %d out of range\n", intra_mode, multi_ref_idx); abort(); \
+    }                                                                                                            \
+    const LeafParams lp{ 0, w, h, intra_mode, channel_type, multi_ref_idx, isp_mode, (1 << dropin_bitdepth(sizeof(PIX))) - 1, kRefLen }; \
+    leaf_call<PIX>(lp, above, left, dst, false);                                                                 \
+  }                                                                                                              \
+  extern "C" void uvg_b200_intra_pred_planar_##SUF(int w, int h, const PIX *top, const PIX *left, PIX *dst)       \
+  {                                                                                                              \
+    leaf_check(w, h, "intra_pred_planar");                                                                       \
+    const LeafParams lp{ 1, w, h, 0, 0, 0, 0, (1 << dropin_bitdepth(sizeof(PIX))) - 1, kRefLen };                 \
+    leaf_call<PIX>(lp, top, left, dst, false);                                                                   \
+  }                                                                                                              \
+  extern "C" void uvg_b200_pdpc_planar_dc_##SUF(int mode, int w, int h, const PIX *top, const PIX *left, PIX *dst) \
+  {                                                                                                              \
+    leaf_check(w, h, "pdpc_planar_dc");                                                                          \
+    const LeafParams lp{ 2, w, h, mode, 0, 0, 0, (1 << dropin_bitdepth(sizeof(PIX))) - 1, kRefLen };              \
+    leaf_call<PIX>(lp, top, left, dst, true);                                                                    \
+  }
+UVGB_INTRA_LEAVES(8, uint8_t)
+UVGB_INTRA_LEAVES(16, uint16_t)

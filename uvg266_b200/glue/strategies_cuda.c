@@ -29,6 +29,7 @@
 #include "strategies/strategies-picture.h"
 #include "strategies/strategies-dct.h"
 #include "strategies/strategies-quant.h"
+#include "strategies/strategies-intra.h"
 #include "transform.h"
 #include "rdo.h"
 #include "dep_quant.h"
@@ -257,6 +258,33 @@ static uint32_t coeff_abs_sum_cuda(const coeff_t *coeffs, size_t length)
 static uint32_t fast_coeff_cost_cuda(const coeff_t *coeff, int32_t w, int32_t h, uint64_t weights)
 { return uvg_b200_fast_coeff_cost(coeff, w, h, weights); }
 
+/* ---- intra (row 8(f)-2): strategies-intra.h:46-80; cu_loc_t is flattened to the w x h of the plane
+ * block that is predicted, exactly what the generic leaves derive first (intra-generic.c:66-67,
+ * :313-314, :421-422) ------------------------------------------------------------------- */
+static void angular_pred_cuda(const cu_loc_t *const cu_loc, const int_fast8_t intra_mode, const int_fast8_t channel_type,
+                              const uvg_pixel *const in_ref_above, const uvg_pixel *const in_ref_left,
+                              uvg_pixel *const dst, const uint8_t multi_ref_idx, const uint8_t isp_mode, const int cu_dim)
+{
+  (void)cu_dim;
+  const int w = channel_type == COLOR_Y ? cu_loc->width : cu_loc->chroma_width;
+  const int h = channel_type == COLOR_Y ? cu_loc->height : cu_loc->chroma_height;
+  B200(angular_pred)(w, h, intra_mode, channel_type, in_ref_above, in_ref_left, dst, multi_ref_idx, isp_mode);
+}
+static void intra_pred_planar_cuda(const cu_loc_t *const cu_loc, color_t color, const uvg_pixel *const ref_top,
+                                   const uvg_pixel *const ref_left, uvg_pixel *const dst)
+{
+  const int w = color == COLOR_Y ? cu_loc->width : cu_loc->chroma_width;
+  const int h = color == COLOR_Y ? cu_loc->height : cu_loc->chroma_height;
+  B200(intra_pred_planar)(w, h, ref_top, ref_left, dst);
+}
+static void pdpc_planar_dc_cuda(const int mode, const cu_loc_t *const cu_loc, const color_t color,
+                                const uvg_intra_ref *const used_ref, uvg_pixel *const dst)
+{
+  const int w = color == COLOR_Y ? cu_loc->width : cu_loc->chroma_width;
+  const int h = color == COLOR_Y ? cu_loc->height : cu_loc->chroma_height;
+  B200(pdpc_planar_dc)(mode, w, h, used_ref->top, used_ref->left, dst);
+}
+
 /* ---- registration ---------------------------------------------------------------- */
 static int device_ready(uint8_t bitdepth)
 {
@@ -309,6 +337,16 @@ int uvg_strategy_register_dct_cuda(void *opaque, uint8_t bitdepth)
   REG("idct_32x32", idct_32x32_cuda);
   REG("fast_forward_dst_4x4", fast_forward_dst_4x4_cuda); REG("fast_inverse_dst_4x4", fast_inverse_dst_4x4_cuda);
   REG("mts_dct", mts_dct_cuda); REG("mts_idct", mts_idct_cuda);
+  return ok;
+}
+
+/* mip_predict and the unused intra_pred_filtered_dc stay with the reference's implementations */
+int uvg_strategy_register_intra_cuda(void *opaque, uint8_t bitdepth)
+{
+  if (!device_ready(bitdepth)) return 0;
+  int ok = 1;
+  REG("angular_pred", angular_pred_cuda); REG("intra_pred_planar", intra_pred_planar_cuda);
+  REG("pdpc_planar_dc", pdpc_planar_dc_cuda);
   return ok;
 }
 
