@@ -196,6 +196,29 @@ UVG_B200_API int uvg_b200_intra_rough_dev(int bitdepth, int n, const uvg_b200_bl
                                           const void *refs, const int8_t *modes, int k,
                                           uint32_t *costs, size_t n_blocks, void *stream);
 
+/* ---- motion-compensation sample interpolation (next row 8(f)-1) ------------------------------
+ * Replaces uvg_sample_quarterpel_luma(_hi) / uvg_sample_octpel_chroma(_hi) (strategies-ipol.h:105-108,
+ * generic/ipol-generic.c:134-210, :681-759) for a batch of blocks read straight from the reference
+ * picture plane; samples outside the plane are the replicated border (what uvg_get_extended_block
+ * builds, ipol-generic.c:761-811).
+ * chroma 0: 8 taps, MV in 1/16 luma samples; chroma 1: 4 taps, MV in 1/32 chroma samples.
+ * hi 0: dst = pixels (uni-prediction rounding); hi 1: dst = int16 14-bit intermediates (bi-pred).
+ * bx, by, mvx, mvy: DEVICE arrays [n_blocks]: block origin in the plane and its motion vector.
+ * dst: dense [n_blocks][h*w]. */
+UVG_B200_API int uvg_b200_ipol_dev(int bitdepth, int chroma, int hi, const void *plane, int stride,
+                                   int plane_w, int plane_h, int w, int h, const int32_t *bx,
+                                   const int32_t *by, const int32_t *mvx, const int32_t *mvy,
+                                   void *dst, size_t n_blocks, void *stream);
+/* Fused fractional motion search (search_inter.c:1085-1250 search_frac: interpolate the sub-pel
+ * neighbours of the best integer MV, score them with satd_any_size): for every block, k candidates
+ * mv + offsets[c] (HOST array [k][2], 1/16 luma samples, each in -16..15), 8-bit luma, w and h
+ * multiples of 8: out[b*k + c] = satd_any_size(original block, interpolated block). */
+UVG_B200_API int uvg_b200_frac_search_dev(int bitdepth, int w, int h, const void *cur,
+                                          const void *ref, int stride, int plane_w, int plane_h,
+                                          const int32_t *bx, const int32_t *by, const int32_t *mvx,
+                                          const int32_t *mvy, const int8_t *offsets, int k,
+                                          uint32_t *out, size_t n_blocks, void *stream);
+
 /* ---------------------------------------------------------------------------------- */
 /* (3) Batched host entry points (H2D + kernels + D2H inside the call, synchronous)    */
 /* ---------------------------------------------------------------------------------- */
@@ -302,6 +325,25 @@ UVG_B200_DECL_PICTURE(16, uint16_t)
                                                   const PIX *left, PIX *dst);
 UVG_B200_DECL_INTRA(8, uint8_t)
 UVG_B200_DECL_INTRA(16, uint16_t)
+
+/* strategies-ipol.h:105-108 (row 8(f)-1): the four MC sample-interpolation leaves; the unused
+ * encoder_control_t / hor_flag / ver_flag arguments are dropped and mv[2] is passed as two ints
+ * (only mv & 15 / mv & 31 is used, like the reference). src = the block's top-left integer sample. */
+#define UVG_B200_DECL_IPOL(SUF, PIX)                                                            \
+  UVG_B200_API void uvg_b200_sample_quarterpel_luma_##SUF(const PIX *src, int src_stride, int w, \
+                                                          int h, PIX *dst, int dst_stride,      \
+                                                          int mvx, int mvy);                    \
+  UVG_B200_API void uvg_b200_sample_quarterpel_luma_hi_##SUF(const PIX *src, int src_stride,     \
+                                                             int w, int h, int16_t *dst,        \
+                                                             int dst_stride, int mvx, int mvy); \
+  UVG_B200_API void uvg_b200_sample_octpel_chroma_##SUF(const PIX *src, int src_stride, int w,   \
+                                                        int h, PIX *dst, int dst_stride,        \
+                                                        int mvx, int mvy);                      \
+  UVG_B200_API void uvg_b200_sample_octpel_chroma_hi_##SUF(const PIX *src, int src_stride,       \
+                                                           int w, int h, int16_t *dst,          \
+                                                           int dst_stride, int mvx, int mvy);
+UVG_B200_DECL_IPOL(8, uint8_t)
+UVG_B200_DECL_IPOL(16, uint16_t)
 
 /* strategies-dct.h:44 dct_func (the typedef's unsigned return is never used; void here) */
 UVG_B200_API void uvg_b200_dct_4x4(int8_t bitdepth, const int16_t *in, int16_t *out);

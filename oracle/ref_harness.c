@@ -34,6 +34,7 @@
 #include "tables.h"
 #include "intra.h"
 #include "strategies/strategies-intra.h"
+#include "strategies/strategies-ipol.h"
 
 static strategy_list_t g_list;
 static const uvg_api *g_api;
@@ -105,6 +106,7 @@ int refh_open(const char *opts)
   if (!uvg_strategy_register_dct(&g_list, UVG_BIT_DEPTH)) return 0;
   if (!uvg_strategy_register_quant(&g_list, UVG_BIT_DEPTH)) return 0;
   if (!uvg_strategy_register_intra(&g_list, UVG_BIT_DEPTH)) return 0;
+  if (!uvg_strategy_register_ipol(&g_list, UVG_BIT_DEPTH)) return 0;
   refh_use("generic");
   return 1;
 }
@@ -262,6 +264,19 @@ void refh_pdpc_planar_dc_leaf(int mode, int w, int h, int channel_type, const uv
   uvg_pdpc_planar_dc(mode, &loc, (color_t)channel_type, &ref, dst);
 }
 int refh_intra_ref_len(void) { return (int)(sizeof(((uvg_intra_ref *)0)->top) / sizeof(uvg_pixel)); }
+
+/* strategies-ipol.h:105-108: the four MC sample-interpolation leaves. kind 0 luma, 1 luma_hi,
+ * 2 chroma, 3 chroma_hi; src points at the block's top-left integer sample inside a padded window. */
+void refh_sample(int kind, const uvg_pixel *src, int src_stride, int w, int h, void *dst, int dst_stride, int mvx, int mvy)
+{
+  const mv_t mv[2] = { mvx, mvy };
+  switch (kind) {
+  case 0: uvg_sample_quarterpel_luma(g_state->encoder_control, (uvg_pixel *)src, (int16_t)src_stride, w, h, (uvg_pixel *)dst, (int16_t)dst_stride, 1, 1, mv); break;
+  case 1: uvg_sample_quarterpel_luma_hi(g_state->encoder_control, (uvg_pixel *)src, (int16_t)src_stride, w, h, (int16_t *)dst, (int16_t)dst_stride, 1, 1, mv); break;
+  case 2: uvg_sample_octpel_chroma(g_state->encoder_control, (uvg_pixel *)src, (int16_t)src_stride, w, h, (uvg_pixel *)dst, (int16_t)dst_stride, 1, 1, mv); break;
+  default: uvg_sample_octpel_chroma_hi(g_state->encoder_control, (uvg_pixel *)src, (int16_t)src_stride, w, h, (int16_t *)dst, (int16_t)dst_stride, 1, 1, mv); break;
+  }
+}
 
 /* Rough intra search of a slice of blocks, the way search_intra_rough scores candidates
  * (search_intra.c:1055-1062 + get_cost :149-163): uvg_intra_predict for each of k modes, then

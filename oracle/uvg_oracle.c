@@ -1013,3 +1013,72 @@ void orc_intra_predict(int w, int h, int mode, const orc_pixel *top, const orc_p
   else orc_angular_pred(w, h, pred_mode, ut, ul, dst);
   if ((mode == 0 || mode == 1) && w >= 4 && h >= 4) orc_pdpc_planar_dc(w, h, ut, ul, dst);
 }
+
+/* =====================================================================================
+ * strategies-ipol (next row 8(f)-1): motion-compensation sample interpolation,
+ * generic/ipol-generic.c:134-210 (luma, 8 taps, 1/16 phases) and :681-759 (chroma, 4 taps,
+ * 1/32 phases). `src` points at the integer sample of the block's top-left; the filters reach 3
+ * (1) samples up/left and 4 (2) down/right. Horizontal pass into int16 (>> BD-8), vertical pass
+ * (>> 6), then either the uni-prediction rounding to a pixel (>> 14-BD with offset, clipped) or,
+ * for the "_hi" variants, the 14-bit intermediate itself.
+ * ===================================================================================== */
+/* VVC luma interpolation filter, phases 0..8 of 16 (filter.c:62-80); phases 9..15 mirror 7..1 */
+static const int8_t k_luma_half[9][8] = {
+  { 0, 0, 0, 64, 0, 0, 0, 0 },     { 0, 1, -3, 63, 4, -2, 1, 0 },    { -1, 2, -5, 62, 8, -3, 1, 0 },
+  { -1, 3, -8, 60, 13, -4, 1, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 52, 26, -8, 3, -1 },
+  { -1, 3, -9, 47, 31, -10, 4, -1 }, { -1, 4, -11, 45, 34, -10, 4, -1 }, { -1, 4, -11, 40, 40, -11, 4, -1 } };
+static void luma_filter(int phase, int f[8])
+{
+  for (int i = 0; i < 8; ++i) f[i] = phase <= 8 ? k_luma_half[phase][i] : k_luma_half[16 - phase][7 - i];
+}
+
+static void orc_sample(int taps, int w, int h, const orc_pixel *src, int src_stride, const int *fh, const int *fv,
+                       orc_pixel *dst, int16_t *dst_hi, int dst_stride)
+{
+  const int off = taps == 8 ? 3 : 1, pad = taps - 1;
+  const int shift1 = BD - 8, shift2 = 6, wp_shift = 14 - BD, wp_off = 1 << (wp_shift - 1);
+  static __thread int16_t hor[(64 + 7) * 64];
+  for (int y = 0; y < h + pad; ++y)
+    for (int x = 0; x < w; ++x) {
+      int s = 0;
+      for (int i = 0; i < taps; ++i) s += fh[i] * (int)src[(y - off) * src_stride + (x - off) + i];
+      hor[y * 64 + x] = (int16_t)(s >> shift1);
+    }
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int s = 0;
+      for (int i = 0; i < taps; ++i) s += fv[i] * (int)hor[(y + i) * 64 + x];
+      s >>= shift2;
+      if (dst_hi) dst_hi[y * dst_stride + x] = (int16_t)s;
+      else dst[y * dst_stride + x] = (orc_pixel)clip3(0, PIXEL_MAX, (s + wp_off) >> wp_shift);
+    }
+}
+
+void orc_sample_quarterpel_luma(int w, int h, const orc_pixel *src, int src_stride, orc_pixel *dst, int dst_stride,
+                                int mvx, int mvy)
+{
+  int fh[8], fv[8];
+  luma_filter(mvx & 15, fh); luma_filter(mvy & 15, fv);
+  orc_sample(8, w, h, src, src_stride, fh, fv, dst, NULL, dst_stride);
+}
+void orc_sample_quarterpel_luma_hi(int w, int h, const orc_pixel *src, int src_stride, int16_t *dst, int dst_stride,
+                                   int mvx, int mvy)
+{
+  int fh[8], fv[8];
+  luma_filter(mvx & 15, fh); luma_filter(mvy & 15, fv);
+  orc_sample(8, w, h, src, src_stride, fh, fv, NULL, dst, dst_stride);
+}
+void orc_sample_octpel_chroma(int w, int h, const orc_pixel *src, int src_stride, orc_pixel *dst, int dst_stride,
+                              int mvx, int mvy)
+{
+  int fh[4], fv[4];
+  for (int i = 0; i < 4; ++i) { fh[i] = k_cubic[mvx & 31][i]; fv[i] = k_cubic[mvy & 31][i]; }   /* filter.c:82-116 = the intra cubic table */
+  orc_sample(4, w, h, src, src_stride, fh, fv, dst, NULL, dst_stride);
+}
+void orc_sample_octpel_chroma_hi(int w, int h, const orc_pixel *src, int src_stride, int16_t *dst, int dst_stride,
+                                 int mvx, int mvy)
+{
+  int fh[4], fv[4];
+  for (int i = 0; i < 4; ++i) { fh[i] = k_cubic[mvx & 31][i]; fv[i] = k_cubic[mvy & 31][i]; }
+  orc_sample(4, w, h, src, src_stride, fh, fv, NULL, dst, dst_stride);
+}

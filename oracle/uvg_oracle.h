@@ -124,6 +124,16 @@ void orc_intra_filter_reference(int w, int h, const orc_pixel *top, const orc_pi
                                 orc_pixel *fleft);
 void orc_intra_predict(int w, int h, int mode, const orc_pixel *top, const orc_pixel *left, orc_pixel *dst);
 
+/* ---- strategies-ipol (next row 8(f)-1): MC sample interpolation ------------------------------ */
+void orc_sample_quarterpel_luma(int w, int h, const orc_pixel *src, int src_stride, orc_pixel *dst, int dst_stride,
+                                int mvx, int mvy);
+void orc_sample_quarterpel_luma_hi(int w, int h, const orc_pixel *src, int src_stride, int16_t *dst, int dst_stride,
+                                   int mvx, int mvy);
+void orc_sample_octpel_chroma(int w, int h, const orc_pixel *src, int src_stride, orc_pixel *dst, int dst_stride,
+                              int mvx, int mvy);
+void orc_sample_octpel_chroma_hi(int w, int h, const orc_pixel *src, int src_stride, int16_t *dst, int dst_stride,
+                                 int mvx, int mvy);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,10 @@ INTRA_CASES = [
     ("intra_only_group", 8, 64, 64, 1, ["--preset=ultrafast", "-p", "1"], "intra"),
     ("all_groups_medium", 8, 64, 64, 1, ["--preset=medium", "-p", "1"], "picture,dct,quant,intra"),
     ("intra_mrl_isp_10bit", 10, 64, 64, 1, ["--preset=ultrafast", "-p", "1", "--mrl", "--isp", "--rd=2"], "intra"),
+    # row 8(f)-1: the MC sample-interpolation leaves (uni- and bi-prediction, luma and chroma)
+    ("ipol_ldp", 8, 128, 64, 3, ["--preset=ultrafast", "--gop=lp-g4d3t1", "--me=hexbs"], "ipol"),
+    ("ipol_ra_bipred_10bit", 10, 64, 64, 4, ["--preset=ultrafast", "--gop=8", "--bipred"], "ipol"),
+    ("all_five_groups_ldp", 8, 64, 64, 2, ["--preset=ultrafast", "--gop=lp-g4d3t1"], "picture,dct,quant,intra,ipol"),
 ]
 
 

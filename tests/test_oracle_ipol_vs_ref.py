@@ -1,0 +1,43 @@
+"""Pins the MC sample-interpolation restatement (next row 8(f)-1: orc_sample_quarterpel_luma(_hi),
+orc_sample_octpel_chroma(_hi)) to the unmodified reference's generic strategies
+(generic/ipol-generic.c:134-210, :681-759): every fractional phase pair, several block sizes,
+8-bit and 10-bit, random and extreme windows. CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from _libs import load_oracle, load_ref, ref_available, ptr, pix_dtype
+
+pytestmark = pytest.mark.skipif(not ref_available(8), reason="oracle/_ref not built")
+vp, ci = C.c_void_p, C.c_int
+KINDS = [(0, "orc_sample_quarterpel_luma", 8, 16, False), (1, "orc_sample_quarterpel_luma_hi", 8, 16, True),
+         (2, "orc_sample_octpel_chroma", 4, 32, False), (3, "orc_sample_octpel_chroma_hi", 4, 32, True)]
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_sample_interpolation_all_phases(bd):
+    O, R = load_oracle(bd), load_ref(bd)
+    R.H.refh_sample.argtypes = [ci, vp, ci, ci, ci, vp, ci, ci, ci]
+    rng = np.random.default_rng(6100 + bd)
+    hi = (1 << bd) - 1
+    n = 0
+    for kind, name, taps, phases, is_hi in KINDS:
+        f = getattr(O, name); f.argtypes = [ci, ci, vp, ci, vp, ci, ci, ci]
+        off = 3 if taps == 8 else 1
+        for (w, h) in ((4, 4), (8, 8), (16, 8), (8, 16), (32, 32), (64, 64), (4, 16)) if taps == 8 else ((2, 2), (4, 4), (8, 4), (16, 16), (32, 32), (2, 8)):
+            S = w + taps + 5
+            for ex in (False, True):
+                win = (rng.choice([0, hi], (h + taps + 3, S)) if ex else rng.integers(0, hi + 1, (h + taps + 3, S))).astype(pix_dtype(bd))
+                src = win[off:, off:]                       # top-left integer sample of the block
+                p0 = win.ctypes.data + (off * S + off) * win.itemsize
+                step = 1 if w * h <= 64 else 3
+                for my in range(0, phases, step):
+                    for mx in range(0, phases, step):
+                        odt = np.int16 if is_hi else pix_dtype(bd)
+                        d1 = np.zeros((h, w), odt); d2 = np.zeros((h, w), odt)
+                        f(w, h, p0, S, ptr(d1), w, mx - 64, my + 32)       # integer parts must be ignored (& 15 / & 31)
+                        R.H.refh_sample(kind, p0, S, w, h, ptr(d2), w, mx - 64, my + 32)
+                        assert (d1 == d2).all(), (bd, name, w, h, mx, my, ex)
+                        n += 1
+    assert n > 3000

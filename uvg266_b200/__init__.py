@@ -99,6 +99,8 @@ def lib():
     L.uvg_b200_transform_host.argtypes = [i] * 8 + [vp, vp, sz]
     L.uvg_b200_quantize_residual_host.argtypes = [QP, i, i, i, i, i, i, i, BP, sz, BP, sz, BP, sz, vp, vp,
                                                   vp, vp, C.c_uint64, sz]
+    L.uvg_b200_ipol_dev.argtypes = [i, i, i, vp, i, i, i, i, i, vp, vp, vp, vp, vp, sz, vp]
+    L.uvg_b200_frac_search_dev.argtypes = [i, i, i, vp, vp, i, i, i, vp, vp, vp, vp, vp, i, vp, sz, vp]
     L.uvg_b200_intra_predict_dev.argtypes = [i, i, vp, vp, i, vp, sz, vp]
     L.uvg_b200_intra_rough_dev.argtypes = [i, i, BP, vp, vp, i, vp, sz, vp]
     L.uvg_b200_intra_predict_host.argtypes = [i, i, vp, vp, i, vp, sz]
@@ -122,6 +124,8 @@ def lib():
         f = getattr(L, "uvg_b200_hor_sad_" + suf); f.argtypes = [vp, vp, i, i] + [C.c_uint32] * 4; f.restype = C.c_uint32
         f = getattr(L, "uvg_b200_generate_residual_" + suf); f.argtypes = [vp, vp, vp, i, i, i, i]; f.restype = None
         f = getattr(L, "uvg_b200_get_optimized_sad_" + suf); f.argtypes = [C.c_int32]; f.restype = vp
+        for nm in ("sample_quarterpel_luma_", "sample_quarterpel_luma_hi_", "sample_octpel_chroma_", "sample_octpel_chroma_hi_"):
+            f = getattr(L, "uvg_b200_" + nm + suf); f.argtypes = [vp, i, i, i, vp, i, i, i]; f.restype = None
         f = getattr(L, "uvg_b200_angular_pred_" + suf); f.argtypes = [i, i, i, i, vp, vp, vp, i, i]; f.restype = None
         f = getattr(L, "uvg_b200_intra_pred_planar_" + suf); f.argtypes = [i, i, vp, vp, vp]; f.restype = None
         f = getattr(L, "uvg_b200_pdpc_planar_dc_" + suf); f.argtypes = [i, i, i, vp, vp, vp]; f.restype = None

@@ -1,0 +1,297 @@
+// ipol.cu - motion-compensation sample interpolation (next row 8(f)-1) and the fused fractional
+// motion-search scoring kernel.
+//
+// Restates generic/ipol-generic.c:134-210 (uvg_sample_quarterpel_luma(_hi): 8 taps, 1/16 phases) and
+// :681-759 (uvg_sample_octpel_chroma(_hi): 4 taps, 1/32 phases): horizontal pass into int16
+// (>> bitdepth-8), vertical pass (>> 6), then the uni-prediction rounding to a pixel
+// ((v + offset) >> (14 - bitdepth), clipped) or, for the "_hi" variants, the 14-bit intermediate.
+// Out-of-frame samples are the replicated border, which is what uvg_get_extended_block builds for
+// the encoder (ipol-generic.c:761-811); here it is a clamp of the read coordinates.
+//
+// Kernels: one CTA per block. The (w + taps - 1) x (h + taps - 1) window is staged once in shared
+// memory, the horizontal pass writes int16 rows next to it, the vertical pass reads those.
+// The fused kernel (uvg_b200_frac_search_dev) stages a window one sample larger on every side, and
+// for each of the k fractional candidates around the block's motion vector interpolates into shared
+// memory and scores SATD against the original with the packed Hadamard of hadamard.cuh - the
+// interpolated blocks never reach HBM (search_inter.c:1085-1250 interpolates into 4+4 block buffers
+// per step and scores them with satd_any_size_quad).
+#include "common.cuh"
+#include "hadamard.cuh"
+
+namespace uvgb {
+
+// VVC interpolation filters (filter.c:62-116). Luma: phases 0..8 of 16, phases 9..15 mirror 7..1.
+// Chroma: 32 phases; the same table as the intra cubic filter.
+__constant__ signed char c_luma_half[9][8] = {
+  { 0, 0, 0, 64, 0, 0, 0, 0 },     { 0, 1, -3, 63, 4, -2, 1, 0 },    { -1, 2, -5, 62, 8, -3, 1, 0 },
+  { -1, 3, -8, 60, 13, -4, 1, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 52, 26, -8, 3, -1 },
+  { -1, 3, -9, 47, 31, -10, 4, -1 }, { -1, 4, -11, 45, 34, -10, 4, -1 }, { -1, 4, -11, 40, 40, -11, 4, -1 } };
+__constant__ signed char c_chroma[32][4] = {
+  { 0, 64, 0, 0 }, { -1, 63, 2, 0 }, { -2, 62, 4, 0 }, { -2, 60, 7, -1 }, { -2, 58, 10, -2 }, { -3, 57, 12, -2 },
+  { -4, 56, 14, -2 }, { -4, 55, 15, -2 }, { -4, 54, 16, -2 }, { -5, 53, 18, -2 }, { -6, 52, 20, -2 },
+  { -6, 49, 24, -3 }, { -6, 46, 28, -4 }, { -5, 44, 29, -4 }, { -4, 42, 30, -4 }, { -4, 39, 33, -4 },
+  { -4, 36, 36, -4 }, { -4, 33, 39, -4 }, { -4, 30, 42, -4 }, { -4, 29, 44, -5 }, { -4, 28, 46, -6 },
+  { -3, 24, 49, -6 }, { -2, 20, 52, -6 }, { -2, 18, 53, -5 }, { -2, 16, 54, -4 }, { -2, 15, 55, -4 },
+  { -2, 14, 56, -4 }, { -2, 12, 57, -3 }, { -2, 10, 58, -2 }, { -1, 7, 60, -2 }, { 0, 4, 62, -2 }, { 0, 2, 63, -1 } };
+
+template <int TAPS>
+__device__ __forceinline__ void load_filter(int phase, int (&f)[TAPS])
+{
+  if (TAPS == 8) {
+#pragma unroll
+    for (int i = 0; i < TAPS; ++i) f[i] = phase <= 8 ? c_luma_half[phase][i] : c_luma_half[16 - phase][7 - i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < TAPS; ++i) f[i] = c_chroma[phase][i];
+  }
+}
+
+struct IpolArgs {
+  const void *plane; int stride, plane_w, plane_h;      // reference picture plane (pixels)
+  int w, h;                                              // block
+  const int32_t *bx, *by, *mvx, *mvy;                    // per block: origin in the plane, MV in filter units
+  void *dst;                                             // dense [n][h*w] pixels (or int16 when hi)
+  int hi, shift1, wp_shift, pixel_max;
+};
+
+// ---- plain interpolation: one CTA per block -----------------------------------------------------
+template <typename Pix, int TAPS>
+__global__ void __launch_bounds__(128)
+ipol_kernel(IpolArgs a, size_t n_blocks)
+{
+  constexpr int OFF = TAPS == 8 ? 3 : 1, PAD = TAPS - 1, FRAC = TAPS == 8 ? 4 : 5, MASK = (1 << FRAC) - 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = a.w, h = a.h, ww = w + PAD, wh = h + PAD;
+  Pix *win = reinterpret_cast<Pix *>(smem_raw);                                  // [wh][ww]
+  int16_t *hor = reinterpret_cast<int16_t *>(smem_raw + (((size_t)ww * wh * sizeof(Pix) + 15) & ~(size_t)15));   // [wh][w]
+  const Pix *plane = static_cast<const Pix *>(a.plane);
+  for (size_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+    const int mvx = a.mvx[b], mvy = a.mvy[b];
+    const int x0 = a.bx[b] + (mvx >> FRAC) - OFF, y0 = a.by[b] + (mvy >> FRAC) - OFF;
+    int fh[TAPS], fv[TAPS];
+    load_filter<TAPS>(mvx & MASK, fh); load_filter<TAPS>(mvy & MASK, fv);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ww * wh; i += blockDim.x) {
+      const int r = i / ww, c = i - r * ww;
+      const int yy = min(max(y0 + r, 0), a.plane_h - 1), xx = min(max(x0 + c, 0), a.plane_w - 1);
+      win[i] = plane[(size_t)yy * a.stride + xx];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < wh * w; i += blockDim.x) {
+      const int r = i / w, c = i - r * w;
+      int s = 0;
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) s += fh[t] * (int)win[r * ww + c + t];
+      hor[i] = (int16_t)(s >> a.shift1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+      const int r = i / w, c = i - r * w;
+      int s = 0;
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) s += fv[t] * (int)hor[(r + t) * w + c];
+      s >>= 6;
+      if (a.hi) static_cast<int16_t *>(a.dst)[b * (size_t)(w * h) + i] = (int16_t)s;
+      else static_cast<Pix *>(a.dst)[b * (size_t)(w * h) + i] =
+          (Pix)min(max((s + (1 << (a.wp_shift - 1))) >> a.wp_shift, 0), a.pixel_max);
+    }
+  }
+}
+
+// ---- fused fractional search: interpolate k candidates around the MV and score SATD, 8-bit luma ----
+struct FracArgs {
+  const uint8_t *cur, *ref; int stride, plane_w, plane_h;
+  int w, h;                                              // multiples of 8, <= 64
+  const int32_t *bx, *by, *mvx, *mvy;                    // block origin, base MV in 1/16 samples
+  int k;
+  signed char dx[64], dy[64];                            // candidate offsets in 1/16 samples, -16..15
+  uint32_t *out;                                         // [n][k] satd_any_size(orig, interpolated)
+};
+
+__global__ void __launch_bounds__(128)
+frac_search_kernel(FracArgs a, size_t n_blocks)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = a.w, h = a.h, ww = w + 9, wh = h + 9;      // window: 1 sample of search margin + 3 / 4 of filter reach
+  uint8_t *win = smem_raw;                                                       // [wh][ww]
+  uint8_t *orig = win + ((ww * wh + 15) & ~15);                                  // [h][w]
+  uint8_t *pred = orig + w * h;                                                  // [h][w]
+  int16_t *hor = reinterpret_cast<int16_t *>(pred + w * h);                      // [h + 7][w]
+  __shared__ unsigned s_sum;
+  const int nsx = w / 8, nsub = nsx * (h / 8);
+  for (size_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+    const int bx = a.bx[b], by = a.by[b], mvx = a.mvx[b], mvy = a.mvy[b];
+    __syncthreads();
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+      const int r = i / w, c = i - r * w;
+      orig[i] = a.cur[(size_t)min(by + r, a.plane_h - 1) * a.stride + min(bx + c, a.plane_w - 1)];
+    }
+    for (int kk = 0; kk < a.k; ++kk) {
+      const int cx = mvx + a.dx[kk], cy = mvy + a.dy[kk];                        // candidate MV, 1/16 samples
+      const int x0 = bx + (cx >> 4) - 3, y0 = by + (cy >> 4) - 3;
+      int fh[8], fv[8];
+      load_filter<8>(cx & 15, fh); load_filter<8>(cy & 15, fv);
+      __syncthreads();
+      // (re)stage the window for this candidate's integer position: candidates share most of it, the
+      // reads hit L1/L2; only w + 7 columns are needed
+      for (int i = threadIdx.x; i < (h + 7) * (w + 7); i += blockDim.x) {
+        const int r = i / (w + 7), c = i - r * (w + 7);
+        const int yy = min(max(y0 + r, 0), a.plane_h - 1), xx = min(max(x0 + c, 0), a.plane_w - 1);
+        win[r * ww + c] = a.ref[(size_t)yy * a.stride + xx];
+      }
+      if (threadIdx.x == 0) s_sum = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < (h + 7) * w; i += blockDim.x) {
+        const int r = i / w, c = i - r * w;
+        int s = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s += fh[t] * (int)win[r * ww + c + t];
+        hor[i] = (int16_t)s;                                                     // 8-bit: shift1 = 0
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+        const int r = i / w, c = i - r * w;
+        int s = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s += fv[t] * (int)hor[(r + t) * w + c];
+        pred[i] = (uint8_t)min(max(((s >> 6) + 32) >> 6, 0), 255);
+      }
+      __syncthreads();
+      unsigned part = 0;
+      for (int sb = threadIdx.x; sb < nsub; sb += blockDim.x) {
+        const int sy = sb / nsx, sx = sb - sy * nsx;
+        uint32_t wo[8][2], wc[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const uint2 o = *reinterpret_cast<const uint2 *>(orig + (sy * 8 + r) * w + sx * 8);
+          const uint2 p = *reinterpret_cast<const uint2 *>(pred + (sy * 8 + r) * w + sx * 8);
+          wo[r][0] = o.x; wo[r][1] = o.y; wc[r][0] = p.x; wc[r][1] = p.y;
+        }
+        unsigned dummy;
+        part += satd8_words_u8<false>(wo, wc, dummy);
+      }
+      if (part) atomicAdd(&s_sum, part);
+      __syncthreads();
+      if (threadIdx.x == 0) a.out[b * a.k + kk] = s_sum;
+    }
+  }
+}
+
+}  // namespace uvgb
+
+using namespace uvgb;
+
+static int ipol_launch(int bitdepth, int chroma, int hi, const void *plane, int stride, int plane_w, int plane_h, int w,
+                       int h, const int32_t *bx, const int32_t *by, const int32_t *mvx, const int32_t *mvy, void *dst,
+                       size_t n, cudaStream_t st)
+{
+  if (bitdepth < 8 || bitdepth > 14) { set_error("ipol: bitdepth %d out of range", bitdepth); return 1; }
+  if (w < 1 || h < 1 || w > 64 || h > 64) { set_error("ipol: block %dx%d unsupported", w, h); return 1; }
+  if (n == 0) return 0;
+  IpolArgs a{ plane, stride, plane_w, plane_h, w, h, bx, by, mvx, mvy, dst, hi, bitdepth - 8, 14 - bitdepth,
+              (1 << bitdepth) - 1 };
+  const int pad = chroma ? 3 : 7, pix = bitdepth == 8 ? 1 : 2;
+  const size_t smem = (((size_t)(w + pad) * (h + pad) * pix + 15) & ~(size_t)15) + (size_t)(h + pad) * w * 2;
+  size_t grid = n;
+  const size_t cap = (size_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (bitdepth == 8) {
+    if (chroma) ipol_kernel<uint8_t, 4><<<(unsigned)grid, 128, smem, st>>>(a, n);
+    else ipol_kernel<uint8_t, 8><<<(unsigned)grid, 128, smem, st>>>(a, n);
+  } else {
+    if (chroma) ipol_kernel<uint16_t, 4><<<(unsigned)grid, 128, smem, st>>>(a, n);
+    else ipol_kernel<uint16_t, 8><<<(unsigned)grid, 128, smem, st>>>(a, n);
+  }
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int uvg_b200_ipol_dev(int bitdepth, int chroma, int hi, const void *plane, int stride, int plane_w,
+                                 int plane_h, int w, int h, const int32_t *bx, const int32_t *by, const int32_t *mvx,
+                                 const int32_t *mvy, void *dst, size_t n_blocks, void *stream)
+{
+  if (ensure_init()) return 1;
+  return ipol_launch(bitdepth, chroma, hi, plane, stride, plane_w, plane_h, w, h, bx, by, mvx, mvy, dst, n_blocks,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int uvg_b200_frac_search_dev(int bitdepth, int w, int h, const void *cur, const void *ref, int stride,
+                                        int plane_w, int plane_h, const int32_t *bx, const int32_t *by,
+                                        const int32_t *mvx, const int32_t *mvy, const int8_t *offsets, int k,
+                                        uint32_t *out, size_t n_blocks, void *stream)
+{
+  if (ensure_init()) return 1;
+  if (bitdepth != 8) { set_error("frac_search: 8-bit only; use ipol_dev + distortion_dev"); return 1; }
+  if (w % 8 || h % 8 || w < 8 || h < 8 || w > 64 || h > 64) { set_error("frac_search: block %dx%d unsupported", w, h); return 1; }
+  if (k < 1 || k > 64) { set_error("frac_search: 1..64 candidates (got %d)", k); return 1; }
+  if (n_blocks == 0) return 0;
+  FracArgs a;
+  a.cur = static_cast<const uint8_t *>(cur); a.ref = static_cast<const uint8_t *>(ref);
+  a.stride = stride; a.plane_w = plane_w; a.plane_h = plane_h; a.w = w; a.h = h;
+  a.bx = bx; a.by = by; a.mvx = mvx; a.mvy = mvy; a.k = k; a.out = out;
+  for (int i = 0; i < k; ++i) {
+    a.dx[i] = offsets[2 * i]; a.dy[i] = offsets[2 * i + 1];
+    if (a.dx[i] < -16 || a.dx[i] > 15 || a.dy[i] < -16 || a.dy[i] > 15) { set_error("frac_search: offset out of -16..15"); return 1; }
+  }
+  const size_t smem = (((size_t)(w + 9) * (h + 9) + 15) & ~(size_t)15) + 2 * (size_t)w * h + (size_t)(h + 7) * w * 2;
+  static bool attr = false;
+  if (!attr) { UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+  size_t grid = n_blocks;
+  const size_t cap = (size_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  frac_search_kernel<<<(unsigned)grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(a, n_blocks);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- drop-in leaves: strategies-ipol.h:105-108 (host pointers, synchronous) -----------------------------
+namespace {
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename Pix>
+void sample_leaf(int chroma, int hi, const Pix *src, int src_stride, int w, int h, void *dst, int dst_stride, int mvx, int mvy)
+{
+  if (ensure_init()) { fprintf(stderr, "uvg266_b200: %s\n", uvg_b200_last_error()); abort(); }
+  if (w < 1 || h < 1 || w > 64 || h > 64) { fprintf(stderr, "uvg266_b200: sample interpolation: block %dx%d unsupported\n", w, h); abort(); }
+  const int off = chroma ? 1 : 3, pad = chroma ? 3 : 7, frac = chroma ? 5 : 4;
+  const int ww = w + pad, wh = h + pad;
+  Staging &s = tls_staging();
+  const size_t win_bytes = align_up((size_t)ww * wh * sizeof(Pix), 256), out_elem = hi ? 2 : sizeof(Pix);
+  const size_t out_bytes = align_up((size_t)w * h * out_elem, 256);
+  if (s.ensure(win_bytes + out_bytes + 64, win_bytes + out_bytes + 256)) { fprintf(stderr, "uvg266_b200: %s\n", uvg_b200_last_error()); abort(); }
+  // pack the window rows (the caller's buffer is strided), one copy in, one kernel, one copy out
+  Pix *hw = reinterpret_cast<Pix *>(s.h_pin);
+  for (int r = 0; r < wh; ++r) memcpy(hw + (size_t)r * ww, src + (ptrdiff_t)(r - off) * src_stride - off, (size_t)ww * sizeof(Pix));
+  UVGB_MUST(cudaMemcpyAsync(s.d_buf, hw, (size_t)ww * wh * sizeof(Pix), cudaMemcpyHostToDevice, s.stream));
+  int32_t *d_job = reinterpret_cast<int32_t *>(s.d_buf + win_bytes + out_bytes);
+  const int32_t job[4] = { off, off, mvx & ((1 << frac) - 1), mvy & ((1 << frac) - 1) };
+  int32_t *h_job = reinterpret_cast<int32_t *>(s.h_pin + win_bytes + out_bytes);
+  memcpy(h_job, job, sizeof(job));
+  UVGB_MUST(cudaMemcpyAsync(d_job, h_job, sizeof(job), cudaMemcpyHostToDevice, s.stream));
+  const int bd = dropin_bitdepth(sizeof(Pix));
+  if (ipol_launch(bd, chroma, hi, s.d_buf, ww, ww, wh, w, h, d_job, d_job + 1, d_job + 2, d_job + 3, s.d_buf + win_bytes, 1, s.stream)) {
+    fprintf(stderr, "uvg266_b200: %s\n", uvg_b200_last_error()); abort();
+  }
+  uint8_t *ho = s.h_pin + win_bytes;
+  UVGB_MUST(cudaMemcpyAsync(ho, s.d_buf + win_bytes, (size_t)w * h * out_elem, cudaMemcpyDeviceToHost, s.stream));
+  UVGB_MUST(cudaStreamSynchronize(s.stream));
+  for (int r = 0; r < h; ++r)
+    memcpy(static_cast<uint8_t *>(dst) + (size_t)r * dst_stride * out_elem, ho + (size_t)r * w * out_elem, (size_t)w * out_elem);
+}
+}  // namespace
+
+#define UVGB_IPOL_LEAVES(SUF, PIX)                                                                                   \
+  extern "C" void uvg_b200_sample_quarterpel_luma_##SUF(const PIX *src, int src_stride, int w, int h, PIX *dst,       \
+                                                        int dst_stride, int mvx, int mvy)                           \
+  { sample_leaf<PIX>(0, 0, src, src_stride, w, h, dst, dst_stride, mvx, mvy); }                                      \
+  extern "C" void uvg_b200_sample_quarterpel_luma_hi_##SUF(const PIX *src, int src_stride, int w, int h, int16_t *dst, \
+                                                           int dst_stride, int mvx, int mvy)                        \
+  { sample_leaf<PIX>(0, 1, src, src_stride, w, h, dst, dst_stride, mvx, mvy); }                                      \
+  extern "C" void uvg_b200_sample_octpel_chroma_##SUF(const PIX *src, int src_stride, int w, int h, PIX *dst,         \
+                                                      int dst_stride, int mvx, int mvy)                             \
+  { sample_leaf<PIX>(1, 0, src, src_stride, w, h, dst, dst_stride, mvx, mvy); }                                      \
+  extern "C" void uvg_b200_sample_octpel_chroma_hi_##SUF(const PIX *src, int src_stride, int w, int h, int16_t *dst,  \
+                                                         int dst_stride, int mvx, int mvy)                          \
+  { sample_leaf<PIX>(1, 1, src, src_stride, w, h, dst, dst_stride, mvx, mvy); }
+UVGB_IPOL_LEAVES(8, uint8_t)
+UVGB_IPOL_LEAVES(16, uint16_t)

@@ -8,7 +8,7 @@
  * registrations - the same effect as the 3-line source patch shown in INTEGRATION.md.
  *
  *   LD_PRELOAD=libuvg266_b200_glue8.so uvg266 -i in.yuv ...
- *   UVG266_B200_GROUPS=picture,dct,quant[,intra]  (default picture,dct,quant)   UVG266_B200_DISABLE=1 (off)
+ *   UVG266_B200_GROUPS=picture,dct,quant[,intra][,ipol]  (default picture,dct,quant)   UVG266_B200_DISABLE=1 (off)
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -21,6 +21,7 @@ int uvg_strategy_register_picture_cuda(void *opaque, uint8_t bitdepth);
 int uvg_strategy_register_dct_cuda(void *opaque, uint8_t bitdepth);
 int uvg_strategy_register_quant_cuda(void *opaque, uint8_t bitdepth);
 int uvg_strategy_register_intra_cuda(void *opaque, uint8_t bitdepth);
+int uvg_strategy_register_ipol_cuda(void *opaque, uint8_t bitdepth);
 
 typedef int (*registrar_t)(void *, uint8_t);
 unsigned long long uvg_b200_launch_count(void);
@@ -37,7 +38,7 @@ static int group_enabled(const char *name)
 {
   if (getenv("UVG266_B200_DISABLE")) return 0;
   const char *g = getenv("UVG266_B200_GROUPS");
-  if (!g) g = "picture,dct,quant";                    /* intra is opt-in: one launch per predicted block */
+  if (!g) g = "picture,dct,quant";                    /* intra and ipol are opt-in: one launch per predicted block */
   return strstr(g, name) != NULL;
 }
 
@@ -56,5 +57,7 @@ int uvg_strategy_register_dct(void *opaque, uint8_t bitdepth)
 { return forward("uvg_strategy_register_dct", "dct", uvg_strategy_register_dct_cuda, opaque, bitdepth); }
 int uvg_strategy_register_quant(void *opaque, uint8_t bitdepth)
 { return forward("uvg_strategy_register_quant", "quant", uvg_strategy_register_quant_cuda, opaque, bitdepth); }
+int uvg_strategy_register_ipol(void *opaque, uint8_t bitdepth)
+{ return forward("uvg_strategy_register_ipol", "ipol", uvg_strategy_register_ipol_cuda, opaque, bitdepth); }
 int uvg_strategy_register_intra(void *opaque, uint8_t bitdepth)
 { return forward("uvg_strategy_register_intra", "intra", uvg_strategy_register_intra_cuda, opaque, bitdepth); }

@@ -30,6 +30,7 @@
 #include "strategies/strategies-dct.h"
 #include "strategies/strategies-quant.h"
 #include "strategies/strategies-intra.h"
+#include "strategies/strategies-ipol.h"
 #include "transform.h"
 #include "rdo.h"
 #include "dep_quant.h"
@@ -285,6 +286,25 @@ static void pdpc_planar_dc_cuda(const int mode, const cu_loc_t *const cu_loc, co
   B200(pdpc_planar_dc)(mode, w, h, used_ref->top, used_ref->left, dst);
 }
 
+/* ---- ipol (row 8(f)-1): strategies-ipol.h:105-108, the MC sample-interpolation leaves. The FME block
+ * filters (filter_*pel_blocks_*) and get_extended_block stay with the reference. ---------------------- */
+static void sample_quarterpel_luma_cuda(const encoder_control_t *const encoder, uvg_pixel *src, int16_t src_stride, int width,
+                                        int height, uvg_pixel *dst, int16_t dst_stride, int8_t hor_flag, int8_t ver_flag,
+                                        const mv_t mv[2])
+{ (void)encoder; (void)hor_flag; (void)ver_flag; B200(sample_quarterpel_luma)(src, src_stride, width, height, dst, dst_stride, mv[0], mv[1]); }
+static void sample_quarterpel_luma_hi_cuda(const encoder_control_t *const encoder, uvg_pixel *src, int16_t src_stride, int width,
+                                           int height, int16_t *dst, int16_t dst_stride, int8_t hor_flag, int8_t ver_flag,
+                                           const mv_t mv[2])
+{ (void)encoder; (void)hor_flag; (void)ver_flag; B200(sample_quarterpel_luma_hi)(src, src_stride, width, height, dst, dst_stride, mv[0], mv[1]); }
+static void sample_octpel_chroma_cuda(const encoder_control_t *const encoder, uvg_pixel *src, int16_t src_stride, int width,
+                                      int height, uvg_pixel *dst, int16_t dst_stride, int8_t hor_flag, int8_t ver_flag,
+                                      const mv_t mv[2])
+{ (void)encoder; (void)hor_flag; (void)ver_flag; B200(sample_octpel_chroma)(src, src_stride, width, height, dst, dst_stride, mv[0], mv[1]); }
+static void sample_octpel_chroma_hi_cuda(const encoder_control_t *const encoder, uvg_pixel *src, int16_t src_stride, int width,
+                                         int height, int16_t *dst, int16_t dst_stride, int8_t hor_flag, int8_t ver_flag,
+                                         const mv_t mv[2])
+{ (void)encoder; (void)hor_flag; (void)ver_flag; B200(sample_octpel_chroma_hi)(src, src_stride, width, height, dst, dst_stride, mv[0], mv[1]); }
+
 /* ---- registration ---------------------------------------------------------------- */
 static int device_ready(uint8_t bitdepth)
 {
@@ -347,6 +367,15 @@ int uvg_strategy_register_intra_cuda(void *opaque, uint8_t bitdepth)
   int ok = 1;
   REG("angular_pred", angular_pred_cuda); REG("intra_pred_planar", intra_pred_planar_cuda);
   REG("pdpc_planar_dc", pdpc_planar_dc_cuda);
+  return ok;
+}
+
+int uvg_strategy_register_ipol_cuda(void *opaque, uint8_t bitdepth)
+{
+  if (!device_ready(bitdepth)) return 0;
+  int ok = 1;
+  REG("sample_quarterpel_luma", sample_quarterpel_luma_cuda); REG("sample_quarterpel_luma_hi", sample_quarterpel_luma_hi_cuda);
+  REG("sample_octpel_chroma", sample_octpel_chroma_cuda); REG("sample_octpel_chroma_hi", sample_octpel_chroma_hi_cuda);
   return ok;
 }
 
