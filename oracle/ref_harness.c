@@ -278,6 +278,29 @@ void refh_sample(int kind, const uvg_pixel *src, int src_stride, int w, int h, v
   }
 }
 
+/* Fractional motion-search scoring the way search_frac does it (search_inter.c:1085-1250), with the
+ * reference's own leaves: uvg_sample_quarterpel_luma into a block buffer, then satd_any_size against
+ * the original. `ref` is the reference plane with a replicated border of `margin` samples (what
+ * uvg_get_extended_block provides); bx/by are positions inside the un-padded plane. Re-entrant. */
+void refh_frac_search_batch(int w, int h, const uvg_pixel *cur, int cur_stride, const uvg_pixel *ref, int ref_stride,
+                            int margin, const int32_t *bx, const int32_t *by, const int32_t *mvx, const int32_t *mvy,
+                            const int8_t *offs, int k, long n, uint32_t *out)
+{
+  uvg_pixel *pred = NULL;
+  if (posix_memalign((void **)&pred, 64, 64 * 64 * sizeof(uvg_pixel))) abort();
+  for (long i = 0; i < n; ++i) {
+    const uvg_pixel *o = cur + (long)by[i] * cur_stride + bx[i];
+    for (int c = 0; c < k; ++c) {
+      const int cx = mvx[i] + offs[2 * c], cy = mvy[i] + offs[2 * c + 1];
+      const mv_t mv[2] = { cx, cy };
+      const uvg_pixel *src = ref + (long)(by[i] + (cy >> 4) + margin) * ref_stride + bx[i] + (cx >> 4) + margin;
+      uvg_sample_quarterpel_luma(g_state->encoder_control, (uvg_pixel *)src, (int16_t)ref_stride, w, h, pred, (int16_t)w, 1, 1, mv);
+      out[i * k + c] = uvg_satd_any_size(w, h, o, cur_stride, pred, w);
+    }
+  }
+  free(pred);
+}
+
 /* Rough intra search of a slice of blocks, the way search_intra_rough scores candidates
  * (search_intra.c:1055-1062 + get_cost :149-163): uvg_intra_predict for each of k modes, then
  * min(SATD, 2 * SAD) against the original block. Re-entrant (one call per worker thread).

@@ -41,3 +41,34 @@ def test_sample_interpolation_all_phases(bd):
                         assert (d1 == d2).all(), (bd, name, w, h, mx, my, ex)
                         n += 1
     assert n > 3000
+
+
+def test_frac_search_batch_matches_oracle():
+    """The CPU-baseline leg of tools/ipol_bench.py (refh_frac_search_batch: the reference's
+    sample_quarterpel_luma + satd_any_size) against the oracle's interpolation + SATD."""
+    bd = 8
+    O, R = load_oracle(bd), load_ref(bd)
+    f = O.orc_sample_quarterpel_luma; f.argtypes = [ci, ci, vp, ci, vp, ci, ci, ci]
+    O.orc_satd_any_size.argtypes = [ci, ci, vp, ci, vp, ci]
+    R.H.refh_frac_search_batch.argtypes = [ci, ci, vp, ci, vp, ci, ci, vp, vp, vp, vp, vp, ci, C.c_long, vp]
+    rng = np.random.default_rng(6500)
+    PW, PH, M = 96, 64, 40
+    ref = rng.integers(0, 256, (PH, PW)).astype(np.uint8); cur = rng.integers(0, 256, (PH, PW)).astype(np.uint8)
+    padded = np.ascontiguousarray(np.pad(ref, M, mode="edge"))
+    offs = np.array([(0, 0), (8, 0), (-8, 8), (4, -4), (-16, 15), (15, -16)], dtype=np.int8)
+    k = len(offs)
+    for (w, h) in ((8, 8), (16, 16), (32, 16)):
+        n = 12
+        bx = rng.integers(0, PW - w + 1, n).astype(np.int32); by = rng.integers(0, PH - h + 1, n).astype(np.int32)
+        mvx = rng.integers(-20 * 16, 20 * 16, n).astype(np.int32); mvy = rng.integers(-20 * 16, 20 * 16, n).astype(np.int32)
+        out = np.zeros(n * k, np.uint32)
+        R.H.refh_frac_search_batch(w, h, ptr(cur), PW, ptr(padded), padded.shape[1], M, ptr(bx), ptr(by), ptr(mvx), ptr(mvy),
+                                   ptr(offs), k, n, ptr(out))
+        for i in range(n):
+            orig = np.ascontiguousarray(cur[by[i]:by[i] + h, bx[i]:bx[i] + w])
+            for c in range(k):
+                cx, cy = int(mvx[i]) + int(offs[c, 0]), int(mvy[i]) + int(offs[c, 1])
+                ix, iy = int(bx[i]) + (cx >> 4) + M, int(by[i]) + (cy >> 4) + M
+                pred = np.zeros((h, w), np.uint8)
+                f(w, h, padded.ctypes.data + iy * padded.shape[1] + ix, padded.shape[1], ptr(pred), w, cx, cy)
+                assert out[i * k + c] == O.orc_satd_any_size(w, h, ptr(orig), w, ptr(pred), w), (w, h, i, c)
