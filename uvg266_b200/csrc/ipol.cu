@@ -99,80 +99,116 @@ ipol_kernel(IpolArgs a, size_t n_blocks)
 }
 
 // ---- fused fractional search: interpolate k candidates around the MV and score SATD, 8-bit luma ----
+// Per block: (1) the window covering every candidate (integer offsets -1..+1 around the MV, filter
+// reach 3 / 4) is staged once; (2) the horizontal pass runs once per DISTINCT horizontal position of
+// the candidate set (5 for the 17-point half/quarter-pel pattern, like filter_hpel/qpel_blocks do),
+// 4 outputs per step with dp4a on the window bytes; (3) one thread per (candidate, 8x8 sub-block)
+// runs the vertical pass for its 64 pixels in registers and feeds the packed Hadamard directly.
 struct FracArgs {
   const uint8_t *cur, *ref; int stride, plane_w, plane_h;
-  int w, h;                                              // multiples of 8, <= 64
+  int h;                                                 // multiple of 8, <= 64
   const int32_t *bx, *by, *mvx, *mvy;                    // block origin, base MV in 1/16 samples
-  int k;
-  signed char dx[64], dy[64];                            // candidate offsets in 1/16 samples, -16..15
+  int k, nx;
+  signed char gdx[8];                                    // distinct horizontal offsets (1/16 samples)
+  signed char cg[64], cdy[64];                           // per candidate: index into gdx, vertical offset
   uint32_t *out;                                         // [n][k] satd_any_size(orig, interpolated)
 };
 
+__device__ __forceinline__ int dp4a_us8(uint32_t a, int b, int c)
+{
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+template <int W, int G>      // W: block width; G: blocks per CTA
 __global__ void __launch_bounds__(128)
 frac_search_kernel(FracArgs a, size_t n_blocks)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int w = a.w, h = a.h, ww = w + 9, wh = h + 9;      // window: 1 sample of search margin + 3 / 4 of filter reach
-  uint8_t *win = smem_raw;                                                       // [wh][ww]
-  uint8_t *orig = win + ((ww * wh + 15) & ~15);                                  // [h][w]
-  uint8_t *pred = orig + w * h;                                                  // [h][w]
-  int16_t *hor = reinterpret_cast<int16_t *>(pred + w * h);                      // [h + 7][w]
-  __shared__ unsigned s_sum;
-  const int nsx = w / 8, nsub = nsx * (h / 8);
-  for (size_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
-    const int bx = a.bx[b], by = a.by[b], mvx = a.mvx[b], mvy = a.mvy[b];
+  const int h = a.h, wh = h + 10;
+  constexpr int P = (W + 10 + 3 + 3) & ~3;               // window row pitch (words aligned, 3 spare bytes for the last word)
+  const int win_bytes = (wh * P + 15) & ~15, hor_elems = a.nx * wh * W;
+  const int slot_bytes = win_bytes + W * h + ((hor_elems * 2 + 15) & ~15);
+  const int nsx = W / 8, nsub = nsx * (h / 8);
+  for (size_t b0 = (size_t)blockIdx.x * G; b0 < n_blocks; b0 += (size_t)gridDim.x * G) {
     __syncthreads();
-    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
-      const int r = i / w, c = i - r * w;
-      orig[i] = a.cur[(size_t)min(by + r, a.plane_h - 1) * a.stride + min(bx + c, a.plane_w - 1)];
+    // (1) windows and originals of the CTA's G blocks
+    for (int i = threadIdx.x; i < G * wh * (W + 10); i += blockDim.x) {
+      const int g = i / (wh * (W + 10)), rem = i - g * (wh * (W + 10)), r = rem / (W + 10), c = rem - r * (W + 10);
+      const size_t b = min(b0 + g, n_blocks - 1);
+      const int x0 = a.bx[b] + (a.mvx[b] >> 4) - 4, y0 = a.by[b] + (a.mvy[b] >> 4) - 4;
+      const int yy = min(max(y0 + r, 0), a.plane_h - 1), xx = min(max(x0 + c, 0), a.plane_w - 1);
+      smem_raw[g * slot_bytes + r * P + c] = a.ref[(size_t)yy * a.stride + xx];
     }
-    for (int kk = 0; kk < a.k; ++kk) {
-      const int cx = mvx + a.dx[kk], cy = mvy + a.dy[kk];                        // candidate MV, 1/16 samples
-      const int x0 = bx + (cx >> 4) - 3, y0 = by + (cy >> 4) - 3;
-      int fh[8], fv[8];
-      load_filter<8>(cx & 15, fh); load_filter<8>(cy & 15, fv);
-      __syncthreads();
-      // (re)stage the window for this candidate's integer position: candidates share most of it, the
-      // reads hit L1/L2; only w + 7 columns are needed
-      for (int i = threadIdx.x; i < (h + 7) * (w + 7); i += blockDim.x) {
-        const int r = i / (w + 7), c = i - r * (w + 7);
-        const int yy = min(max(y0 + r, 0), a.plane_h - 1), xx = min(max(x0 + c, 0), a.plane_w - 1);
-        win[r * ww + c] = a.ref[(size_t)yy * a.stride + xx];
-      }
-      if (threadIdx.x == 0) s_sum = 0;
-      __syncthreads();
-      for (int i = threadIdx.x; i < (h + 7) * w; i += blockDim.x) {
-        const int r = i / w, c = i - r * w;
-        int s = 0;
+    for (int i = threadIdx.x; i < G * W * h; i += blockDim.x) {
+      const int g = i / (W * h), rem = i - g * (W * h), r = rem / W, c = rem - r * W;
+      const size_t b = min(b0 + g, n_blocks - 1);
+      smem_raw[g * slot_bytes + win_bytes + rem] =
+          a.cur[(size_t)min(a.by[b] + r, a.plane_h - 1) * a.stride + min(a.bx[b] + c, a.plane_w - 1)];
+    }
+    __syncthreads();
+    // (2) horizontal pass per distinct horizontal position: item = (block, group, row, 4 columns)
+    for (int i = threadIdx.x; i < G * a.nx * wh * (W / 4); i += blockDim.x) {
+      const int g = i / (a.nx * wh * (W / 4)), rem = i - g * (a.nx * wh * (W / 4));
+      const int gx = rem / (wh * (W / 4)), rem2 = rem - gx * (wh * (W / 4)), r = rem2 / (W / 4), c0 = 4 * (rem2 - r * (W / 4));
+      const size_t b = min(b0 + g, n_blocks - 1);
+      const int mvx = a.mvx[b], cx = mvx + a.gdx[gx], relx = (cx >> 4) - (mvx >> 4);
+      int f[8];
+      load_filter<8>(cx & 15, f);
+      const int flo = (f[0] & 255) | ((f[1] & 255) << 8) | ((f[2] & 255) << 16) | ((f[3] & 255) << 24);
+      const int fhi = (f[4] & 255) | ((f[5] & 255) << 8) | ((f[6] & 255) << 16) | ((f[7] & 255) << 24);
+      const unsigned char *row = smem_raw + g * slot_bytes + r * P;
+      const int j0 = 1 + relx + c0, al = j0 & ~3, sh = (j0 & 3) * 8;
+      const uint32_t *wp = reinterpret_cast<const uint32_t *>(row + al);
+      const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+      const uint32_t A0 = __funnelshift_r(w0, w1, sh), A1 = __funnelshift_r(w1, w2, sh), A2 = __funnelshift_r(w2, w3, sh);
+      int16_t *hor = reinterpret_cast<int16_t *>(smem_raw + g * slot_bytes + win_bytes + W * h) + (gx * wh + r) * W + c0;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) s += fh[t] * (int)win[r * ww + c + t];
-        hor[i] = (int16_t)s;                                                     // 8-bit: shift1 = 0
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t lo = e ? __funnelshift_r(A0, A1, 8 * e) : A0, hi = e ? __funnelshift_r(A1, A2, 8 * e) : A1;
+        hor[e] = (int16_t)dp4a_us8(hi, fhi, dp4a_us8(lo, flo, 0));          // 8-bit: shift1 = 0
       }
-      __syncthreads();
-      for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
-        const int r = i / w, c = i - r * w;
-        int s = 0;
+    }
+    __syncthreads();
+    // (3) vertical pass + SATD: item = (block, candidate, 8x8 sub-block)
+    for (int i = threadIdx.x; i < G * a.k * nsub; i += blockDim.x) {
+      const int g = i / (a.k * nsub), rem = i - g * (a.k * nsub), kk = rem / nsub, sb = rem - kk * nsub;
+      const int sy = sb / nsx, sx = sb - sy * nsx;
+      if (b0 + g >= n_blocks) continue;
+      const size_t b = b0 + g;
+      const int mvy = a.mvy[b], cy = mvy + a.cdy[kk], rely = (cy >> 4) - (mvy >> 4);
+      int fv[8];
+      load_filter<8>(cy & 15, fv);
+      const int16_t *hor = reinterpret_cast<const int16_t *>(smem_raw + g * slot_bytes + win_bytes + W * h) +
+                           (a.cg[kk] * wh + 1 + rely + sy * 8) * W + sx * 8;
+      const unsigned char *orig = smem_raw + g * slot_bytes + win_bytes + (sy * 8) * W + sx * 8;
+      uint32_t wo[8][2], wc[8][2];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) s += fv[t] * (int)hor[(r + t) * w + c];
-        pred[i] = (uint8_t)min(max(((s >> 6) + 32) >> 6, 0), 255);
-      }
-      __syncthreads();
-      unsigned part = 0;
-      for (int sb = threadIdx.x; sb < nsub; sb += blockDim.x) {
-        const int sy = sb / nsx, sx = sb - sy * nsx;
-        uint32_t wo[8][2], wc[8][2];
+      for (int y = 0; y < 8; ++y) {
+        int s[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const uint2 o = *reinterpret_cast<const uint2 *>(orig + (sy * 8 + r) * w + sx * 8);
-          const uint2 p = *reinterpret_cast<const uint2 *>(pred + (sy * 8 + r) * w + sx * 8);
-          wo[r][0] = o.x; wo[r][1] = o.y; wc[r][0] = p.x; wc[r][1] = p.y;
+        for (int t = 0; t < 8; ++t) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(hor + (y + t) * W);
+          const int x0 = (int)(short)(v.x & 0xffff), x1 = (int)v.x >> 16, x2 = (int)(short)(v.y & 0xffff), x3 = (int)v.y >> 16;
+          const int x4 = (int)(short)(v.z & 0xffff), x5 = (int)v.z >> 16, x6 = (int)(short)(v.w & 0xffff), x7 = (int)v.w >> 16;
+          s[0] += fv[t] * x0; s[1] += fv[t] * x1; s[2] += fv[t] * x2; s[3] += fv[t] * x3;
+          s[4] += fv[t] * x4; s[5] += fv[t] * x5; s[6] += fv[t] * x6; s[7] += fv[t] * x7;
         }
-        unsigned dummy;
-        part += satd8_words_u8<false>(wo, wc, dummy);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          const uint32_t p = (uint32_t)min(max(((s[x] >> 6) + 32) >> 6, 0), 255);
+          if (x < 4) lo |= p << (8 * x); else hi |= p << (8 * (x - 4));
+        }
+        wc[y][0] = lo; wc[y][1] = hi;
+        const uint2 o = *reinterpret_cast<const uint2 *>(orig + y * W);
+        wo[y][0] = o.x; wo[y][1] = o.y;
       }
-      if (part) atomicAdd(&s_sum, part);
-      __syncthreads();
-      if (threadIdx.x == 0) a.out[b * a.k + kk] = s_sum;
+      unsigned dummy;
+      const unsigned part = satd8_words_u8<false>(wo, wc, dummy);
+      if (nsub == 1) a.out[b * a.k + kk] = part;
+      else atomicAdd(&a.out[b * a.k + kk], part);
     }
   }
 }
@@ -222,24 +258,47 @@ extern "C" int uvg_b200_frac_search_dev(int bitdepth, int w, int h, const void *
 {
   if (ensure_init()) return 1;
   if (bitdepth != 8) { set_error("frac_search: 8-bit only; use ipol_dev + distortion_dev"); return 1; }
-  if (w % 8 || h % 8 || w < 8 || h < 8 || w > 64 || h > 64) { set_error("frac_search: block %dx%d unsupported", w, h); return 1; }
+  if ((w != 8 && w != 16 && w != 32 && w != 64) || h % 8 || h < 8 || h > 64) { set_error("frac_search: block %dx%d unsupported", w, h); return 1; }
   if (k < 1 || k > 64) { set_error("frac_search: 1..64 candidates (got %d)", k); return 1; }
   if (n_blocks == 0) return 0;
   FracArgs a;
   a.cur = static_cast<const uint8_t *>(cur); a.ref = static_cast<const uint8_t *>(ref);
-  a.stride = stride; a.plane_w = plane_w; a.plane_h = plane_h; a.w = w; a.h = h;
-  a.bx = bx; a.by = by; a.mvx = mvx; a.mvy = mvy; a.k = k; a.out = out;
+  a.stride = stride; a.plane_w = plane_w; a.plane_h = plane_h; a.h = h;
+  a.bx = bx; a.by = by; a.mvx = mvx; a.mvy = mvy; a.k = k; a.out = out; a.nx = 0;
   for (int i = 0; i < k; ++i) {
-    a.dx[i] = offsets[2 * i]; a.dy[i] = offsets[2 * i + 1];
-    if (a.dx[i] < -16 || a.dx[i] > 15 || a.dy[i] < -16 || a.dy[i] > 15) { set_error("frac_search: offset out of -16..15"); return 1; }
+    const int dx = offsets[2 * i], dy = offsets[2 * i + 1];
+    if (dx < -16 || dx > 15 || dy < -16 || dy > 15) { set_error("frac_search: offset out of -16..15"); return 1; }
+    int g = 0;
+    while (g < a.nx && a.gdx[g] != dx) ++g;
+    if (g == a.nx) {
+      if (a.nx == 8) { set_error("frac_search: more than 8 distinct horizontal offsets"); return 1; }
+      a.gdx[a.nx++] = (signed char)dx;
+    }
+    a.cg[i] = (signed char)g; a.cdy[i] = (signed char)dy;
   }
-  const size_t smem = (((size_t)(w + 9) * (h + 9) + 15) & ~(size_t)15) + 2 * (size_t)w * h + (size_t)(h + 7) * w * 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nsub = (w / 8) * (h / 8);
+  if (nsub > 1) UVGB_TRY(cudaMemsetAsync(out, 0, n_blocks * (size_t)k * sizeof(uint32_t), st));   // sub-blocks accumulate
+  const int G = w == 8 ? 8 : w == 16 ? 2 : 1;
+  const int P = (w + 10 + 3 + 3) & ~3, wh = h + 10;
+  const size_t slot = (size_t)((wh * P + 15) & ~15) + (size_t)w * h + (size_t)((a.nx * wh * w * 2 + 15) & ~15);
+  const size_t smem = slot * G;
+  if (smem > 200 * 1024) { set_error("frac_search: candidate set needs %zu bytes of shared memory", smem); return 1; }
   static bool attr = false;
-  if (!attr) { UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-  size_t grid = n_blocks;
+  if (!attr) {
+    UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  size_t grid = (n_blocks + G - 1) / G;
   const size_t cap = (size_t)sm_count() * 16;
   if (grid > cap) grid = cap;
-  frac_search_kernel<<<(unsigned)grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(a, n_blocks);
+  if (w == 8) frac_search_kernel<8, 8><<<(unsigned)grid, 128, smem, st>>>(a, n_blocks);
+  else if (w == 16) frac_search_kernel<16, 2><<<(unsigned)grid, 128, smem, st>>>(a, n_blocks);
+  else if (w == 32) frac_search_kernel<32, 1><<<(unsigned)grid, 128, smem, st>>>(a, n_blocks);
+  else frac_search_kernel<64, 1><<<(unsigned)grid, 128, smem, st>>>(a, n_blocks);
   UVGB_LAUNCH_CHECK();
   return 0;
 }
