@@ -388,6 +388,8 @@ def gpu_arm(args):
     if rank == 0:
         extra["kernels"] = kernel_breakdown(torch, U, L, rough, tus, cfg, stream, hbm_peak)
         extra["pairs_64x64"] = pair_bench(torch, U, L, dev, stream, hbm_peak)
+        if world == 1:
+            extra["next_rows"] = next_rows_bench(torch, U, L, dev, stream)
 
     # ---- e2e: the same step through the host-buffer C-ABI entry points (pinned host memory) ----
     e2e = e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, dev)
@@ -460,6 +462,51 @@ def kernel_breakdown(torch, U, L, rough, tus, cfg, stream, hbm_peak):
         out.append({"kernel": "quantize_residual %dx%d" % (x["n"], x["n"]), "ms": ms, "bytes": x["bytes"],
                     "gbps": x["bytes"] / ms / 1e6, "frac": x["bytes"] / ms / 1e6 / hbm_peak,
                     "gmacs": macs / ms / 1e6})
+    return out
+
+
+def next_rows_bench(torch, U, L, dev, stream):
+    """The widened rows 8(f)-2 / 8(f)-1 on one 4K frame (secondary numbers; tools/intra_bench.py and
+    tools/ipol_bench.py are the full versions with the two-step and reference-CPU legs)."""
+    import ctypes as C
+    W, H = FRAME_W, CTU_ROWS * CTU
+    plane = synth_plane_rows([(0, r) for r in range(CTU_ROWS)])
+    cur = synth_plane_rows([(1, r) for r in range(CTU_ROWS)])
+    d_plane, d_cur = torch.from_numpy(plane).to(dev), torch.from_numpy(cur).to(dev)
+    out = {"frame": "%dx%d u8" % (W, H)}
+    # fused intra rough search: every 8x8 (23 modes) and 16x16 (24 modes) block, references = neighbours
+    tot = 0.0
+    for n, modes in ((8, list(range(0, 67, 3))), (16, list(range(0, 67, 3)) + [1])):
+        gp = 2 * n + 4
+        ys, xs = np.meshgrid(np.arange(0, H, n), np.arange(0, W, n), indexing="ij")
+        ys, xs = ys.ravel(), xs.ravel()
+        i = np.arange(gp)
+        top = plane[np.clip(ys - 1, 0, H - 1)[:, None], np.clip(xs[:, None] - 1 + i[None, :], 0, W - 1)]
+        left = plane[np.clip(ys[:, None] - 1 + i[None, :], 0, H - 1), np.clip(xs - 1, 0, W - 1)[:, None]]
+        d_refs = torch.from_numpy(np.ascontiguousarray(np.stack([top, left], axis=1))).to(dev)
+        m8 = np.array(modes, dtype=np.int8)
+        nb, k = ys.size, len(modes)
+        cost = torch.zeros(nb * k, dtype=torch.int32, device=dev)
+        desc = U.Blocks.plane(d_plane.data_ptr(), W, W, n, n)
+        ms = _time(torch, lambda: U.check(L.uvg_b200_intra_rough_dev(8, n, C.byref(desc), d_refs.data_ptr(), m8.ctypes.data, k,
+                                                                     cost.data_ptr(), nb, stream)), iters=5, warm=2)
+        out["intra_rough_%dx%d_k%d_ms" % (n, n, k)] = ms
+        tot += ms
+    out["intra_rough_frame_ms"] = tot
+    # fused fractional search: every 16x16 block, 17 sub-pel candidates around an integer MV
+    offs = [(0, 0)] + [(dx, dy) for dy in (-8, 0, 8) for dx in (-8, 0, 8) if (dx, dy) != (0, 0)] + \
+           [(dx, dy) for dy in (-4, 0, 4) for dx in (-4, 0, 4) if (dx, dy) != (0, 0)]
+    offsets = np.array(offs, dtype=np.int8)
+    rng = np.random.default_rng(7)
+    ys, xs = np.meshgrid(np.arange(0, H, 16), np.arange(0, W, 16), indexing="ij")
+    nb = ys.size
+    arrs = [xs.ravel().astype(np.int32), ys.ravel().astype(np.int32), (rng.integers(-8, 9, nb) * 16).astype(np.int32),
+            (rng.integers(-8, 9, nb) * 16).astype(np.int32)]
+    d = [torch.from_numpy(a).to(dev) for a in arrs]
+    cost = torch.zeros(nb * len(offs), dtype=torch.int32, device=dev)
+    out["frac_search_16x16_k17_ms"] = _time(torch, lambda: U.check(L.uvg_b200_frac_search_dev(
+        8, 16, 16, d_cur.data_ptr(), d_plane.data_ptr(), W, W, H, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+        offsets.ctypes.data, len(offs), cost.data_ptr(), nb, stream)), iters=5, warm=2)
     return out
 
 
