@@ -219,6 +219,19 @@ UVG_B200_API int uvg_b200_frac_search_dev(int bitdepth, int w, int h, const void
                                           const int32_t *mvy, const int8_t *offsets, int k,
                                           uint32_t *out, size_t n_blocks, void *stream);
 
+/* ---- the non-distortion leftovers of the picture table -------------------------------------------
+ * crc32c_4x4 / crc32c_8x8 (strategies-picture.h:157-158, picture-generic.c:1371-1443): the IBC block
+ * hash of n x n blocks addressed by a blocks descriptor (e.g. every block position of a plane).
+ * bipred_average (strategies-picture.h:136-148, picture-generic.c:1133-1247), one plane at a time:
+ * src0 / src1 dense [n_blocks][w*h], each either pixels (is_im 0) or int16 14-bit intermediates
+ * (is_im 1, the output of uvg_b200_ipol_dev with hi = 1); dst through a blocks descriptor. */
+UVG_B200_API int uvg_b200_crc32c_dev(int bitdepth, int n, const uvg_b200_blocks *blocks,
+                                     uint32_t *out, size_t n_blocks, void *stream);
+UVG_B200_API int uvg_b200_bipred_average_dev(int bitdepth, int w, int h,
+                                             const uvg_b200_blocks *dst, const void *src0,
+                                             int src0_is_im, const void *src1, int src1_is_im,
+                                             size_t n_blocks, void *stream);
+
 /* ---------------------------------------------------------------------------------- */
 /* (3) Batched host entry points (H2D + kernels + D2H inside the call, synchronous)    */
 /* ---------------------------------------------------------------------------------- */
@@ -344,6 +357,17 @@ UVG_B200_DECL_INTRA(16, uint16_t)
                                                            int dst_stride, int mvx, int mvy);
 UVG_B200_DECL_IPOL(8, uint8_t)
 UVG_B200_DECL_IPOL(16, uint16_t)
+
+/* crc32c_4x4 / crc32c_8x8 with the reference's signature; bipred_average per plane (the glue splits the
+ * composite's lcu_t / yuv_t arguments into planes exactly like bipred_average_generic does). */
+#define UVG_B200_DECL_MISC(SUF, PIX)                                                            \
+  UVG_B200_API uint32_t uvg_b200_crc32c_4x4_##SUF(const PIX *buf, uint32_t pic_stride);         \
+  UVG_B200_API uint32_t uvg_b200_crc32c_8x8_##SUF(const PIX *buf, uint32_t pic_stride);         \
+  UVG_B200_API void uvg_b200_bipred_average_##SUF(PIX *dst, int dst_stride, const void *src0,   \
+                                                  int src0_is_im, const void *src1,             \
+                                                  int src1_is_im, int w, int h);
+UVG_B200_DECL_MISC(8, uint8_t)
+UVG_B200_DECL_MISC(16, uint16_t)
 
 /* strategies-dct.h:44 dct_func (the typedef's unsigned return is never used; void here) */
 UVG_B200_API void uvg_b200_dct_4x4(int8_t bitdepth, const int16_t *in, int16_t *out);

@@ -301,6 +301,24 @@ void refh_frac_search_batch(int w, int h, const uvg_pixel *cur, int cur_stride, 
   free(pred);
 }
 
+/* crc32c_4x4 / crc32c_8x8 and bipred_average through the strategy pointers (strategies-picture.h:136-162).
+ * bipred: one plane at a time through the luma path of the composite (pu at the LCU origin). */
+uint32_t refh_crc32c(int n, const uvg_pixel *buf, uint32_t stride)
+{
+  return n == 4 ? uvg_crc32c_4x4(buf, stride) : uvg_crc32c_8x8(buf, stride);
+}
+void refh_bipred_average(uvg_pixel *dst /* LCU_WIDTH-strided */, const void *src0, int is_im0, const void *src1, int is_im1,
+                         int w, int h)
+{
+  static __thread lcu_t lcu;
+  yuv_t px0 = { 0 }, px1 = { 0 };
+  yuv_im_t im0 = { 0 }, im1 = { 0 };
+  if (is_im0) im0.y = (uvg_pixel_im *)src0; else px0.y = (uvg_pixel *)src0;
+  if (is_im1) im1.y = (uvg_pixel_im *)src1; else px1.y = (uvg_pixel *)src1;
+  uvg_bipred_average(&lcu, &px0, &px1, &im0, &im1, 0, 0, w, h, is_im0 ? 1 : 0, is_im1 ? 1 : 0, true, false);
+  for (int y = 0; y < h; ++y) memcpy(dst + y * LCU_WIDTH, lcu.rec.y + y * LCU_WIDTH, w * sizeof(uvg_pixel));
+}
+
 /* Rough intra search of a slice of blocks, the way search_intra_rough scores candidates
  * (search_intra.c:1055-1062 + get_cost :149-163): uvg_intra_predict for each of k modes, then
  * min(SATD, 2 * SAD) against the original block. Re-entrant (one call per worker thread).

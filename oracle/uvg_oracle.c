@@ -1082,3 +1082,39 @@ void orc_sample_octpel_chroma_hi(int w, int h, const orc_pixel *src, int src_str
   for (int i = 0; i < 4; ++i) { fh[i] = k_cubic[mvx & 31][i]; fv[i] = k_cubic[mvy & 31][i]; }
   orc_sample(4, w, h, src, src_stride, fh, fv, NULL, dst, dst_stride);
 }
+
+/* =====================================================================================
+ * The two remaining non-distortion entries of the picture strategy table (SURVEY 8(a) "next"):
+ * crc32c_4x4 / crc32c_8x8 (picture-generic.c:1371-1443: CRC-32C, reflected polynomial 0x82F63B78,
+ * over the block's pixel BYTES row by row - little-endian byte pairs for > 8-bit pixels) and
+ * bipred_average (:1133-1247: average of two predictions, each either pixels or 14-bit
+ * intermediates). pixel_var (:1334-1357) accumulates in double in index order and is therefore
+ * not reproducible by a parallel reduction; it stays with the reference.
+ * ===================================================================================== */
+uint32_t orc_crc32c_nxn(int n, const orc_pixel *buf, uint32_t stride)
+{
+  static uint32_t table[256];
+  if (!table[1])
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int b = 0; b < 8; ++b) c = (c >> 1) ^ ((c & 1) ? 0x82F63B78u : 0);
+      table[i] = c;
+    }
+  uint32_t crc = 0xFFFFFFFFu;
+  for (int y = 0; y < n; ++y) {
+    const uint8_t *row = (const uint8_t *)(buf + (size_t)y * stride);
+    for (size_t i = 0; i < (size_t)n * sizeof(orc_pixel); ++i) crc = (crc >> 8) ^ table[(crc ^ row[i]) & 0xFF];
+  }
+  return crc ^ 0xFFFFFFFFu;
+}
+
+void orc_bipred_average(orc_pixel *dst, int dst_stride, const void *src0, int src0_is_im, const void *src1,
+                        int src1_is_im, int w, int h)
+{
+  const int shift = 15 - BD, offset = 1 << (shift - 1);
+  for (int i = 0; i < w * h; ++i) {
+    const int16_t a = src0_is_im ? ((const int16_t *)src0)[i] : (int16_t)(((const orc_pixel *)src0)[i] << (14 - BD));
+    const int16_t b = src1_is_im ? ((const int16_t *)src1)[i] : (int16_t)(((const orc_pixel *)src1)[i] << (14 - BD));
+    dst[(i / w) * dst_stride + (i % w)] = (orc_pixel)clip3(0, PIXEL_MAX, ((int)a + (int)b + offset) >> shift);
+  }
+}

@@ -61,6 +61,8 @@ CASES = [
     ("intra_ultrafast", 8, 128, 128, 2, ["--preset=ultrafast", "-p", "1"]),
     ("intra_ultrafast_signhide_mts", 8, 128, 64, 2, ["--preset=ultrafast", "-p", "1", "--signhide", "--mts=intra", "--rd=2"]),
     ("ldp_ultrafast", 8, 128, 64, 3, ["--preset=ultrafast", "--gop=lp-g4d3t1", "--me=hexbs"]),
+    ("ra_bipred", 8, 64, 64, 4, ["--preset=ultrafast", "--gop=8", "--bipred"]),          # bipred_average
+    ("intra_ibc", 8, 64, 64, 1, ["--preset=ultrafast", "-p", "1", "--ibc=1"]),           # crc32c_4x4 / 8x8 hashes
     ("intra_medium_rdoq", 8, 64, 64, 1, ["--preset=medium", "-p", "1"]),
     ("intra_ultrafast_10bit", 10, 128, 64, 2, ["--preset=ultrafast", "-p", "1"]),
 ]

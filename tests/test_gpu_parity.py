@@ -507,3 +507,55 @@ def test_rough_cost_kernel_variants(mode):
                         "-k", "test_batched_rough_cost or test_full_size_properties"], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("bd", BDS)
+def test_crc32c_and_bipred_average(bd):
+    """The non-distortion leftovers of the picture table: IBC block hash and bi-prediction average,
+    drop-ins and batched entry points."""
+    import torch
+    O = load_oracle(bd)
+    L = U.lib()
+    O.orc_crc32c_nxn.argtypes = [C.c_int, vp, C.c_uint32]; O.orc_crc32c_nxn.restype = C.c_uint32
+    O.orc_bipred_average.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(2600 + bd)
+    hi = (1 << bd) - 1
+    PW, PH = 64, 48
+    plane = rng.integers(0, hi + 1, (PH, PW)).astype(pix_dtype(bd))
+    stream = torch.cuda.current_stream().cuda_stream
+    d_plane = torch.from_numpy(plane.view(np.uint8 if bd == 8 else np.int16)).cuda()
+    for n in (4, 8):
+        f = U.dropin("crc32c_%dx%d" % (n, n), bd)
+        for (y, x) in ((0, 0), (3, 5), (PH - n, PW - n)):
+            p = plane.ctypes.data + (y * PW + x) * plane.itemsize
+            assert f(p, PW) == O.orc_crc32c_nxn(n, p, PW)
+        desc = U.Blocks.plane(d_plane.data_ptr(), PW, PW, n, n)
+        nb = (PW // n) * (PH // n)
+        out = torch.zeros(nb, dtype=torch.int32, device="cuda")
+        U.check(L.uvg_b200_crc32c_dev(bd, n, C.byref(desc), out.data_ptr(), nb, stream))
+        got = out.cpu().numpy().astype(np.uint32)
+        for i in range(nb):
+            y, x = (i // (PW // n)) * n, (i % (PW // n)) * n
+            assert got[i] == O.orc_crc32c_nxn(n, plane.ctypes.data + (y * PW + x) * plane.itemsize, PW)
+    g = U.dropin("bipred_average", bd)
+    for (w, h) in ((4, 4), (8, 16), (32, 32), (64, 64)):
+        for (i0, i1) in ((0, 0), (1, 1), (0, 1), (1, 0)):
+            srcs = [rng.integers(-2000, (hi << (14 - bd)) + 2000, w * h).astype(np.int16) if im else
+                    rng.integers(0, hi + 1, w * h).astype(pix_dtype(bd)) for im in (i0, i1)]
+            d1 = np.zeros((h, 70), pix_dtype(bd)); d2 = np.zeros((h, 70), pix_dtype(bd))
+            O.orc_bipred_average(ptr(d1), 70, ptr(srcs[0]), i0, ptr(srcs[1]), i1, w, h)
+            g(ptr(d2), 70, ptr(srcs[0]), i0, ptr(srcs[1]), i1, w, h)
+            assert (d1 == d2).all(), (bd, w, h, i0, i1)
+    # batched: 10 blocks of 16x16, both sources intermediates
+    w = h = 16; nb = 10
+    a = rng.integers(-500, (hi << (14 - bd)) + 500, nb * w * h).astype(np.int16); b = rng.integers(-500, (hi << (14 - bd)) + 500, nb * w * h).astype(np.int16)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dd = torch.zeros(nb * w * h, dtype=torch.uint8 if bd == 8 else torch.int16, device="cuda")
+    desc = U.Blocks.dense(dd.data_ptr(), w, h)
+    U.check(L.uvg_b200_bipred_average_dev(bd, w, h, C.byref(desc), da.data_ptr(), 1, db.data_ptr(), 1, nb, stream))
+    got = dd.cpu().numpy()
+    got = got.view(np.uint16) if bd != 8 else got
+    for i in range(nb):
+        e = np.zeros(w * h, pix_dtype(bd))
+        O.orc_bipred_average(ptr(e), w, ptr(a[i * w * h:]), 1, ptr(b[i * w * h:]), 1, w, h)
+        assert (got[i * w * h:(i + 1) * w * h] == e).all()

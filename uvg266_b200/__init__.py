@@ -99,6 +99,8 @@ def lib():
     L.uvg_b200_transform_host.argtypes = [i] * 8 + [vp, vp, sz]
     L.uvg_b200_quantize_residual_host.argtypes = [QP, i, i, i, i, i, i, i, BP, sz, BP, sz, BP, sz, vp, vp,
                                                   vp, vp, C.c_uint64, sz]
+    L.uvg_b200_crc32c_dev.argtypes = [i, i, BP, vp, sz, vp]
+    L.uvg_b200_bipred_average_dev.argtypes = [i, i, i, BP, vp, i, vp, i, sz, vp]
     L.uvg_b200_ipol_dev.argtypes = [i, i, i, vp, i, i, i, i, i, vp, vp, vp, vp, vp, sz, vp]
     L.uvg_b200_frac_search_dev.argtypes = [i, i, i, vp, vp, i, i, i, vp, vp, vp, vp, vp, i, vp, sz, vp]
     L.uvg_b200_intra_predict_dev.argtypes = [i, i, vp, vp, i, vp, sz, vp]
@@ -124,6 +126,9 @@ def lib():
         f = getattr(L, "uvg_b200_hor_sad_" + suf); f.argtypes = [vp, vp, i, i] + [C.c_uint32] * 4; f.restype = C.c_uint32
         f = getattr(L, "uvg_b200_generate_residual_" + suf); f.argtypes = [vp, vp, vp, i, i, i, i]; f.restype = None
         f = getattr(L, "uvg_b200_get_optimized_sad_" + suf); f.argtypes = [C.c_int32]; f.restype = vp
+        for nm in ("crc32c_4x4_", "crc32c_8x8_"):
+            f = getattr(L, "uvg_b200_" + nm + suf); f.argtypes = [vp, C.c_uint32]; f.restype = C.c_uint32
+        f = getattr(L, "uvg_b200_bipred_average_" + suf); f.argtypes = [vp, i, vp, i, vp, i, i, i]; f.restype = None
         for nm in ("sample_quarterpel_luma_", "sample_quarterpel_luma_hi_", "sample_octpel_chroma_", "sample_octpel_chroma_hi_"):
             f = getattr(L, "uvg_b200_" + nm + suf); f.argtypes = [vp, i, i, i, vp, i, i, i]; f.restype = None
         f = getattr(L, "uvg_b200_angular_pred_" + suf); f.argtypes = [i, i, i, i, vp, vp, vp, i, i]; f.restype = None

@@ -113,6 +113,31 @@ static void mts_idct_cuda(const int8_t bitdepth, const color_t color, const cu_i
                     tu->type == CU_INTRA ? tu->intra.isp_mode : 0, w, h, in, out, mts_type);
 }
 
+/* bipred_average (picture-generic.c:1195-1247): the composite only chooses, per plane, which of the two
+ * predictions are pixels and which are 14-bit intermediates; the averaging itself is the leaf */
+static void bipred_average_cuda(lcu_t *const lcu, const yuv_t *const px_L0, const yuv_t *const px_L1,
+                                const yuv_im_t *const im_L0, const yuv_im_t *const im_L1, const unsigned pu_x,
+                                const unsigned pu_y, const unsigned pu_w, const unsigned pu_h, const unsigned im_flags_L0,
+                                const unsigned im_flags_L1, const bool predict_luma, const bool predict_chroma)
+{
+  if (predict_luma) {
+    const unsigned off = SUB_SCU(pu_y) * LCU_WIDTH + SUB_SCU(pu_x);
+    const int i0 = im_flags_L0 & 1, i1 = im_flags_L1 & 1;
+    B200(bipred_average)(lcu->rec.y + off, LCU_WIDTH, i0 ? (const void *)im_L0->y : (const void *)px_L0->y, i0,
+                         i1 ? (const void *)im_L1->y : (const void *)px_L1->y, i1, pu_w, pu_h);
+  }
+  if (predict_chroma) {
+    const unsigned off = SUB_SCU(pu_y) / 2 * LCU_WIDTH_C + SUB_SCU(pu_x) / 2;
+    const int i0 = (im_flags_L0 & 2) != 0, i1 = (im_flags_L1 & 2) != 0;
+    B200(bipred_average)(lcu->rec.u + off, LCU_WIDTH_C, i0 ? (const void *)im_L0->u : (const void *)px_L0->u, i0,
+                         i1 ? (const void *)im_L1->u : (const void *)px_L1->u, i1, pu_w / 2, pu_h / 2);
+    B200(bipred_average)(lcu->rec.v + off, LCU_WIDTH_C, i0 ? (const void *)im_L0->v : (const void *)px_L0->v, i0,
+                         i1 ? (const void *)im_L1->v : (const void *)px_L1->v, i1, pu_w / 2, pu_h / 2);
+  }
+}
+static uint32_t crc32c_4x4_cuda(const uvg_pixel *buf, uint32_t pic_stride) { return B200(crc32c_4x4)(buf, pic_stride); }
+static uint32_t crc32c_8x8_cuda(const uvg_pixel *buf, uint32_t pic_stride) { return B200(crc32c_8x8)(buf, pic_stride); }
+
 /* ---- quant ----------------------------------------------------------------------- */
 static void unsupported(const char *what)
 {
@@ -344,6 +369,10 @@ int uvg_strategy_register_picture_cuda(void *opaque, uint8_t bitdepth)
   REG("get_optimized_sad", get_optimized_sad_cuda);
   REG("ver_sad", ver_sad_cuda); REG("hor_sad", hor_sad_cuda);
   REG("generate_residual", generate_residual_cuda);
+  REG("bipred_average", bipred_average_cuda);
+  REG("crc32c_4x4", crc32c_4x4_cuda); REG("crc32c_8x8", crc32c_8x8_cuda);
+  /* pixel_var accumulates in double in index order: not reproducible by a parallel reduction, left to
+   * the reference's implementation */
   return ok;
 }
 
