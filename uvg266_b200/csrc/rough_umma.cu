@@ -182,33 +182,39 @@ rough_umma_kernel(Blocks A, const uint8_t *__restrict__ cand, uint32_t *__restri
     const uint32_t o_sub = r & (NSUB - 1), o_sy = o_sub / NS, o_sx = o_sub - o_sy * NS;
     const uint32_t o_stride = DENSE ? N : A.stride;
     const size_t o_pix = (size_t)(o_sy * 8) * o_stride + o_sx * 8;
+    // per-thread constants of the copies: own row's original chunks 4..7, and candidate chunk r & 3 of
+    // the four rows (r & ~3) | c (lanes 4m..4m+3 copy 64 contiguous bytes of one row)
+    const uint32_t kc = r & 3;
+    uint32_t od[4], cd[4], coff[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      od[c] = r * kRowBytes + (((4 + c) ^ (r & 7)) << 4);
+      const uint32_t row = (r & ~3u) | c, sub = row & (NSUB - 1), sy = sub / NS, sx = sub - sy * NS;
+      cd[c] = row * kRowBytes + ((kc ^ (row & 7)) << 4);
+      coff[c] = (row >> LOG_NSUB) * (N * N) + (sy * 8 + 2 * kc) * N + sx * 8;     // inside the tile's 8 KB of candidates
+    }
+    const uint32_t sA_addr = s32addr(sA);
     auto fetch_orig = [&](uint32_t j) {                 // j = this CTA's tile counter
       const uint32_t st = j % kStages;
       if (j < my_tiles) {
         if (j >= (uint32_t)kStages) bar_wait(&empty_bar[st], ((j / kStages) - 1) & 1);
-        const uint32_t u = (tile0 + j * tstep) * kTileRows + r;
-        if (u < n_units) {
+        const uint32_t tile = tile0 + j * tstep, u = tile * kTileRows + r, dbase = sA_addr + st * kTileBytes;
+        const uint8_t *ctile = cand + (size_t)tile * (kTileRows * 64);            // 128 sub-blocks x 64 bytes
+        const bool full = (tile + 1) * kTileRows <= n_units;                      // every tile but the last
+        if (full || u < n_units) {
           const uint32_t b = fdivk(u >> LOG_NSUB, kd);
           const uint8_t *p = static_cast<const uint8_t *>(A.base) + (DENSE ? (size_t)b * (N * N) : (size_t)A.offset(b)) + o_pix;
-          const uint32_t dst = s32addr(sA + st * kTileBytes) + r * kRowBytes;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint32_t d = dst + (((4 + c) ^ (r & 7)) << 4);
-            if (N == 8 && DENSE) cp_async16(d, p + 16 * c);     // two pixel rows per 16-byte copy
-            else { cp_async8(d, p + (size_t)(2 * c) * o_stride); cp_async8(d + 8, p + (size_t)(2 * c + 1) * o_stride); }
+            if (N == 8 && DENSE) cp_async16(dbase + od[c], p + 16 * c);           // two pixel rows per 16-byte copy
+            else { cp_async8(dbase + od[c], p + (size_t)(2 * c) * o_stride); cp_async8(dbase + od[c] + 8, p + (size_t)(2 * c + 1) * o_stride); }
           }
         }
-        // candidates: lanes 4m..4m+3 copy the four 16-byte chunks of row 4m + c (64 contiguous bytes)
-        const uint32_t kc = r & 3;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint32_t row = (r & ~3u) | c, uc = (tile0 + j * tstep) * kTileRows + row;
-          if (uc < n_units) {
-            const uint32_t sub = row & (NSUB - 1), sy = sub / NS, sx = sub - sy * NS;
-            const uint8_t *p = cand + (size_t)(uc >> LOG_NSUB) * (N * N) + (sy * 8 + 2 * kc) * N + sx * 8;
-            const uint32_t d = s32addr(sA + st * kTileBytes) + row * kRowBytes + ((kc ^ (row & 7)) << 4);
-            if (N == 8) cp_async16(d, p);
-            else { cp_async8(d, p); cp_async8(d + 8, p + N); }
+          if (full || tile * kTileRows + ((r & ~3u) | c) < n_units) {
+            if (N == 8) cp_async16(dbase + cd[c], ctile + coff[c]);
+            else { cp_async8(dbase + cd[c], ctile + coff[c]); cp_async8(dbase + cd[c] + 8, ctile + coff[c] + N); }
           }
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" :: "r"(s32addr(&full_bar[st])) : "memory");
@@ -224,8 +230,8 @@ rough_umma_kernel(Blocks A, const uint8_t *__restrict__ cand, uint32_t *__restri
       unsigned sd[4] = { 0, 0, 0, 0 };
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const uint4 p = *reinterpret_cast<const uint4 *>(tileA + sw128(r, c));
-        const uint4 o = *reinterpret_cast<const uint4 *>(tileA + sw128(r, 4 + c));
+        const uint4 p = *reinterpret_cast<const uint4 *>(tileA + (od[c] ^ 64));       // chunk c = chunk 4 + c with bit 2 of the index flipped
+        const uint4 o = *reinterpret_cast<const uint4 *>(tileA + od[c]);
         sd[0] = __vsadu4(p.x, o.x) + sd[0]; sd[1] = __vsadu4(p.y, o.y) + sd[1];
         sd[2] = __vsadu4(p.z, o.z) + sd[2]; sd[3] = __vsadu4(p.w, o.w) + sd[3];
       }
