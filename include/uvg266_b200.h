@@ -357,6 +357,17 @@ UVG_B200_DECL_INTRA(16, uint16_t)
                                                            int dst_stride, int mvx, int mvy);
 UVG_B200_DECL_IPOL(8, uint8_t)
 UVG_B200_DECL_IPOL(16, uint16_t)
+/* strategies-ipol.h:62-64, :142-145: the four FME block filters filter_hpel_blocks_hor_ver_luma (step
+ * 0), filter_hpel_blocks_diag_luma (1), filter_qpel_blocks_hor_ver_luma (2), filter_qpel_blocks_diag_luma
+ * (3). filtered = the reference's `uvg_pixel filtered[4][LCU_LUMA_SIZE]` (block_pitch = LCU_LUMA_SIZE,
+ * filtered_stride = LCU_WIDTH); off_x / off_y = the best half-pel offset (steps 2, 3). The shared
+ * intermediate buffers of the reference are not used. */
+UVG_B200_API void uvg_b200_fme_filter_8(int step, const uint8_t *src, int src_stride, int w, int h,
+                                        uint8_t *filtered, int filtered_stride, int block_pitch,
+                                        int off_x, int off_y);
+UVG_B200_API void uvg_b200_fme_filter_16(int step, const uint16_t *src, int src_stride, int w, int h,
+                                         uint16_t *filtered, int filtered_stride, int block_pitch,
+                                         int off_x, int off_y);
 
 /* crc32c_4x4 / crc32c_8x8 with the reference's signature; bipred_average per plane (the glue splits the
  * composite's lcu_t / yuv_t arguments into planes exactly like bipred_average_generic does). */

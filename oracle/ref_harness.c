@@ -319,6 +319,26 @@ void refh_bipred_average(uvg_pixel *dst /* LCU_WIDTH-strided */, const void *src
   for (int y = 0; y < h; ++y) memcpy(dst + y * LCU_WIDTH, lcu.rec.y + y * LCU_WIDTH, w * sizeof(uvg_pixel));
 }
 
+/* The FME block filters the way search_frac chains them (search_inter.c:1130-1160): steps 0..step are run
+ * in order on the same intermediate buffers; the four blocks of the LAST step are returned densely
+ * ([4][h][w]). src = top-left of the (w+1) x (h+1) area whose sample (1,1) is the block's integer
+ * position, inside a window with 4 more samples on every side. off_x / off_y: the best half-pel offset
+ * (quarter-pel steps only). */
+void refh_fme_filter(int step, const uvg_pixel *src, int src_stride, int w, int h, int fme_level, int off_x, int off_y,
+                     uvg_pixel *out)
+{
+  static __thread uvg_pixel filtered[4][LCU_LUMA_SIZE];
+  static __thread int16_t intermediate[5][UVG_IPOL_MAX_IM_SIZE_LUMA_SIMD];
+  static __thread int16_t first_cols[5][UVG_EXT_BLOCK_W_LUMA + 1];
+  ipol_blocks_func *steps[4] = { uvg_filter_hpel_blocks_hor_ver_luma, uvg_filter_hpel_blocks_diag_luma,
+                                 uvg_filter_qpel_blocks_hor_ver_luma, uvg_filter_qpel_blocks_diag_luma };
+  for (int st = 0; st <= step; ++st)
+    steps[st](g_state->encoder_control, (uvg_pixel *)src, (int16_t)src_stride, w, h, filtered, intermediate, (int8_t)fme_level,
+              first_cols, (int8_t)(st >= 2 ? off_x : 0), (int8_t)(st >= 2 ? off_y : 0));
+  for (int j = 0; j < 4; ++j)
+    for (int y = 0; y < h; ++y) memcpy(out + ((size_t)j * h + y) * w, &filtered[j][y * LCU_WIDTH], w * sizeof(uvg_pixel));
+}
+
 /* Rough intra search of a slice of blocks, the way search_intra_rough scores candidates
  * (search_intra.c:1055-1062 + get_cost :149-163): uvg_intra_predict for each of k modes, then
  * min(SATD, 2 * SAD) against the original block. Re-entrant (one call per worker thread).

@@ -1118,3 +1118,22 @@ void orc_bipred_average(orc_pixel *dst, int dst_stride, const void *src0, int sr
     dst[(i / w) * dst_stride + (i % w)] = (orc_pixel)clip3(0, PIXEL_MAX, ((int)a + (int)b + offset) >> shift);
   }
 }
+
+/* The four FME block filters (ipol-generic.c:213-680, uvg_filter_hpel_blocks_hor_ver / _diag,
+ * uvg_filter_qpel_blocks_hor_ver / _diag) share buffers of horizontally filtered rows between calls,
+ * but each of their four output blocks is exactly the sample interpolation of the block at one
+ * quarter-pel offset from its integer position (which is sample (1,1) of `src`):
+ *   step 0: (-2,0) (2,0) (0,-2) (0,2)         step 1: (-2,-2) (2,-2) (-2,2) (2,2)
+ *   step 2: c+(-1,0) c+(1,0) c+(0,-1) c+(0,1)  step 3: c+(-1,-1) c+(1,-1) c+(-1,1) c+(1,1),  c = 2*(off_x, off_y)
+ * (established against the reference by tests/test_oracle_ipol_vs_ref.py). out: dense [4][h][w]. */
+void orc_fme_filter(int step, const orc_pixel *src, int src_stride, int w, int h, int off_x, int off_y, orc_pixel *out)
+{
+  static const int8_t d[4][4][2] = { { { -2, 0 }, { 2, 0 }, { 0, -2 }, { 0, 2 } }, { { -2, -2 }, { 2, -2 }, { -2, 2 }, { 2, 2 } },
+                                     { { -1, 0 }, { 1, 0 }, { 0, -1 }, { 0, 1 } }, { { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } } };
+  for (int j = 0; j < 4; ++j) {
+    const int qx = (step >= 2 ? 2 * off_x : 0) + d[step][j][0], qy = (step >= 2 ? 2 * off_y : 0) + d[step][j][1];
+    const int mvx = qx * 4, mvy = qy * 4;               /* 1/16 samples */
+    const orc_pixel *p = src + (1 + (mvy >> 4)) * src_stride + 1 + (mvx >> 4);
+    orc_sample_quarterpel_luma(w, h, p, src_stride, out + (size_t)j * w * h, w, mvx, mvy);
+  }
+}

@@ -130,3 +130,27 @@ def test_fused_frac_search():
                 f(w, h, p0, padded.shape[1], ptr(pred), w, cx, cy)
                 e = O.orc_satd_any_size(w, h, ptr(orig), w, ptr(pred), w)
                 assert got[i, c] == e, (w, h, i, c, dx, dy)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_fme_filter_dropins(bd):
+    """The four FME block filters (filter_hpel/qpel_blocks_*) as drop-ins, output layout of the reference
+    (filtered[4][LCU_LUMA_SIZE], LCU_WIDTH stride), against orc_fme_filter."""
+    O, L = load_oracle(bd), U.lib()
+    O.orc_fme_filter.argtypes = [ci, vp, ci, ci, ci, ci, ci, vp]
+    g = U.dropin("fme_filter", bd)
+    rng = np.random.default_rng(6800 + bd)
+    hi = (1 << bd) - 1
+    LW, LSZ = 64, 64 * 64
+    for (w, h) in ((8, 8), (16, 8), (32, 32), (64, 64), (8, 32)):
+        S = w + 1 + 16
+        win = rng.integers(0, hi + 1, (h + 17, S)).astype(pix_dtype(bd))
+        src = win.ctypes.data + (8 * S + 8) * win.itemsize
+        for step in range(4):
+            for (ox, oy) in ([(0, 0)] if step < 2 else [(-1, -1), (1, 0), (0, 1), (0, 0)]):
+                e = np.zeros((4, h, w), pix_dtype(bd))
+                O.orc_fme_filter(step, src, S, w, h, ox, oy, ptr(e))
+                out = np.zeros((4, LSZ), pix_dtype(bd))
+                g(step, src, S, w, h, ptr(out), LW, LSZ, ox, oy)
+                got = out.reshape(4, 64, 64)[:, :h, :w]
+                assert (got == e).all(), (bd, w, h, step, ox, oy)

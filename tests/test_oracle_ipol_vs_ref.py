@@ -72,3 +72,29 @@ def test_frac_search_batch_matches_oracle():
                 pred = np.zeros((h, w), np.uint8)
                 f(w, h, padded.ctypes.data + iy * padded.shape[1] + ix, padded.shape[1], ptr(pred), w, cx, cy)
                 assert out[i * k + c] == O.orc_satd_any_size(w, h, ptr(orig), w, ptr(pred), w), (w, h, i, c)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_fme_block_filters(bd):
+    """uvg_filter_hpel/qpel_blocks_* chained the way search_frac does (refh_fme_filter) against
+    orc_fme_filter: every output block is the sample interpolation at one quarter-pel offset."""
+    O, R = load_oracle(bd), load_ref(bd)
+    O.orc_fme_filter.argtypes = [ci, vp, ci, ci, ci, ci, ci, vp]
+    R.H.refh_fme_filter.argtypes = [ci, vp, ci, ci, ci, ci, ci, ci, vp]
+    rng = np.random.default_rng(6700 + bd)
+    hi = (1 << bd) - 1
+    n = 0
+    for (w, h) in ((8, 8), (16, 8), (8, 16), (32, 32), (64, 64), (16, 64)):
+        S = w + 1 + 16
+        for ex in (False, True):
+            win = (rng.choice([0, hi], (h + 17, S)) if ex else rng.integers(0, hi + 1, (h + 17, S))).astype(pix_dtype(bd))
+            src = win.ctypes.data + (8 * S + 8) * win.itemsize
+            for fme_level in (1, 2, 3, 4):
+                step = fme_level - 1
+                for (ox, oy) in ([(0, 0)] if step < 2 else [(-1, -1), (0, -1), (1, 0), (-1, 1), (0, 0), (1, 1)]):
+                    d1 = np.zeros((4, h, w), pix_dtype(bd)); d2 = np.zeros((4, h, w), pix_dtype(bd))
+                    O.orc_fme_filter(step, src, S, w, h, ox, oy, ptr(d1))
+                    R.H.refh_fme_filter(step, src, S, w, h, fme_level, ox, oy, ptr(d2))
+                    assert (d1 == d2).all(), (bd, w, h, fme_level, ox, oy)
+                    n += 1
+    assert n > 100

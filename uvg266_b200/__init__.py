@@ -126,6 +126,7 @@ def lib():
         f = getattr(L, "uvg_b200_hor_sad_" + suf); f.argtypes = [vp, vp, i, i] + [C.c_uint32] * 4; f.restype = C.c_uint32
         f = getattr(L, "uvg_b200_generate_residual_" + suf); f.argtypes = [vp, vp, vp, i, i, i, i]; f.restype = None
         f = getattr(L, "uvg_b200_get_optimized_sad_" + suf); f.argtypes = [C.c_int32]; f.restype = vp
+        f = getattr(L, "uvg_b200_fme_filter_" + suf); f.argtypes = [i, vp, i, i, i, vp, i, i, i, i]; f.restype = None
         for nm in ("crc32c_4x4_", "crc32c_8x8_"):
             f = getattr(L, "uvg_b200_" + nm + suf); f.argtypes = [vp, C.c_uint32]; f.restype = C.c_uint32
         f = getattr(L, "uvg_b200_bipred_average_" + suf); f.argtypes = [vp, i, vp, i, vp, i, i, i]; f.restype = None

@@ -339,6 +339,50 @@ void sample_leaf(int chroma, int hi, const Pix *src, int src_stride, int w, int 
 }
 }  // namespace
 
+// The four FME block filters (strategies-ipol.h:142-145, ipol-generic.c:213-680): each of their four output
+// blocks is the sample interpolation of the block at one quarter-pel offset from its integer position
+// (sample (1,1) of src) - established against the reference by tests/test_oracle_ipol_vs_ref.py:
+//   step 0: (-2,0) (2,0) (0,-2) (0,2)          step 1: (-2,-2) (2,-2) (-2,2) (2,2)
+//   step 2: c+(-1,0) c+(1,0) c+(0,-1) c+(0,1)   step 3: c+(-1,-1) c+(1,-1) c+(-1,1) c+(1,1),  c = 2 * (off_x, off_y)
+// so one launch of ipol_kernel with four jobs over the same window serves a call; the reference's
+// intermediate buffers are not needed (and not written: install the four filters together).
+namespace {
+template <typename Pix>
+void fme_leaf(int step, const Pix *src, int src_stride, int w, int h, Pix *filtered, int filtered_stride, int block_pitch,
+              int off_x, int off_y)
+{
+  static const signed char d[4][4][2] = { { { -2, 0 }, { 2, 0 }, { 0, -2 }, { 0, 2 } }, { { -2, -2 }, { 2, -2 }, { -2, 2 }, { 2, 2 } },
+                                          { { -1, 0 }, { 1, 0 }, { 0, -1 }, { 0, 1 } }, { { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } } };
+  if (ensure_init()) { fprintf(stderr, "uvg266_b200: %s\n", uvg_b200_last_error()); abort(); }
+  if (step < 0 || step > 3 || w < 1 || h < 1 || w > 64 || h > 64) { fprintf(stderr, "uvg266_b200: fme filter: bad step / block %dx%d\n", w, h); abort(); }
+  const int ww = w + 8, wh = h + 8;                        // samples -3 .. w+4 around the (w+1) x (h+1) area
+  Staging &s = tls_staging();
+  const size_t win_bytes = align_up((size_t)ww * wh * sizeof(Pix), 256), out_bytes = align_up((size_t)4 * w * h * sizeof(Pix), 256);
+  if (s.ensure(win_bytes + out_bytes + 64, win_bytes + out_bytes + 256)) { fprintf(stderr, "uvg266_b200: %s\n", uvg_b200_last_error()); abort(); }
+  Pix *hw = reinterpret_cast<Pix *>(s.h_pin);
+  for (int r = 0; r < wh; ++r) memcpy(hw + (size_t)r * ww, src + (ptrdiff_t)(r - 3) * src_stride - 3, (size_t)ww * sizeof(Pix));
+  int32_t *h_job = reinterpret_cast<int32_t *>(s.h_pin + win_bytes + out_bytes);
+  for (int j = 0; j < 4; ++j) {
+    const int qx = (step >= 2 ? 2 * off_x : 0) + d[step][j][0], qy = (step >= 2 ? 2 * off_y : 0) + d[step][j][1];
+    h_job[j] = 4; h_job[4 + j] = 4;                       // the integer position (1,1) of src inside the window
+    h_job[8 + j] = qx * 4; h_job[12 + j] = qy * 4;        // quarter-pel -> 1/16 samples
+  }
+  UVGB_MUST(cudaMemcpyAsync(s.d_buf, hw, (size_t)ww * wh * sizeof(Pix), cudaMemcpyHostToDevice, s.stream));
+  int32_t *d_job = reinterpret_cast<int32_t *>(s.d_buf + win_bytes + out_bytes);
+  UVGB_MUST(cudaMemcpyAsync(d_job, h_job, 16 * sizeof(int32_t), cudaMemcpyHostToDevice, s.stream));
+  if (ipol_launch(dropin_bitdepth(sizeof(Pix)), 0, 0, s.d_buf, ww, ww, wh, w, h, d_job, d_job + 4, d_job + 8, d_job + 12,
+                  s.d_buf + win_bytes, 4, s.stream)) {
+    fprintf(stderr, "uvg266_b200: %s\n", uvg_b200_last_error()); abort();
+  }
+  Pix *ho = reinterpret_cast<Pix *>(s.h_pin + win_bytes);
+  UVGB_MUST(cudaMemcpyAsync(ho, s.d_buf + win_bytes, (size_t)4 * w * h * sizeof(Pix), cudaMemcpyDeviceToHost, s.stream));
+  UVGB_MUST(cudaStreamSynchronize(s.stream));
+  for (int j = 0; j < 4; ++j)
+    for (int r = 0; r < h; ++r)
+      memcpy(filtered + (size_t)j * block_pitch + (size_t)r * filtered_stride, ho + ((size_t)j * h + r) * w, (size_t)w * sizeof(Pix));
+}
+}  // namespace
+
 #define UVGB_IPOL_LEAVES(SUF, PIX)                                                                                   \
   extern "C" void uvg_b200_sample_quarterpel_luma_##SUF(const PIX *src, int src_stride, int w, int h, PIX *dst,       \
                                                         int dst_stride, int mvx, int mvy)                           \
@@ -354,3 +398,10 @@ void sample_leaf(int chroma, int hi, const Pix *src, int src_stride, int w, int 
   { sample_leaf<PIX>(1, 1, src, src_stride, w, h, dst, dst_stride, mvx, mvy); }
 UVGB_IPOL_LEAVES(8, uint8_t)
 UVGB_IPOL_LEAVES(16, uint16_t)
+
+extern "C" void uvg_b200_fme_filter_8(int step, const uint8_t *src, int src_stride, int w, int h, uint8_t *filtered,
+                                      int filtered_stride, int block_pitch, int off_x, int off_y)
+{ fme_leaf<uint8_t>(step, src, src_stride, w, h, filtered, filtered_stride, block_pitch, off_x, off_y); }
+extern "C" void uvg_b200_fme_filter_16(int step, const uint16_t *src, int src_stride, int w, int h, uint16_t *filtered,
+                                       int filtered_stride, int block_pitch, int off_x, int off_y)
+{ fme_leaf<uint16_t>(step, src, src_stride, w, h, filtered, filtered_stride, block_pitch, off_x, off_y); }

@@ -311,8 +311,7 @@ static void pdpc_planar_dc_cuda(const int mode, const cu_loc_t *const cu_loc, co
   B200(pdpc_planar_dc)(mode, w, h, used_ref->top, used_ref->left, dst);
 }
 
-/* ---- ipol (row 8(f)-1): strategies-ipol.h:105-108, the MC sample-interpolation leaves. The FME block
- * filters (filter_*pel_blocks_*) and get_extended_block stay with the reference. ---------------------- */
+/* ---- ipol (row 8(f)-1): strategies-ipol.h:105-108, the MC sample-interpolation leaves ---------------- */
 static void sample_quarterpel_luma_cuda(const encoder_control_t *const encoder, uvg_pixel *src, int16_t src_stride, int width,
                                         int height, uvg_pixel *dst, int16_t dst_stride, int8_t hor_flag, int8_t ver_flag,
                                         const mv_t mv[2])
@@ -329,6 +328,22 @@ static void sample_octpel_chroma_hi_cuda(const encoder_control_t *const encoder,
                                          int height, int16_t *dst, int16_t dst_stride, int8_t hor_flag, int8_t ver_flag,
                                          const mv_t mv[2])
 { (void)encoder; (void)hor_flag; (void)ver_flag; B200(sample_octpel_chroma_hi)(src, src_stride, width, height, dst, dst_stride, mv[0], mv[1]); }
+
+/* The four FME block filters (ipol_blocks_func, strategies-ipol.h:62-64): the outputs are plain sample
+ * interpolations at fixed quarter-pel offsets, so the shared intermediate buffers are ignored. They are
+ * always installed together. */
+#define FME_STEP(name, step)                                                                                       \
+  static void name(const encoder_control_t *encoder, uvg_pixel *src, int16_t src_stride, int width, int height,    \
+                   uvg_pixel filtered[4][LCU_LUMA_SIZE], int16_t hor_intermediate[5][UVG_IPOL_MAX_IM_SIZE_LUMA_SIMD], \
+                   int8_t fme_level, int16_t hor_first_cols[5][UVG_EXT_BLOCK_W_LUMA + 1], int8_t off_x, int8_t off_y) \
+  {                                                                                                                \
+    (void)encoder; (void)hor_intermediate; (void)fme_level; (void)hor_first_cols;                                  \
+    B200(fme_filter)(step, src, src_stride, width, height, &filtered[0][0], LCU_WIDTH, LCU_LUMA_SIZE, off_x, off_y); \
+  }
+FME_STEP(filter_hpel_blocks_hor_ver_luma_cuda, 0)
+FME_STEP(filter_hpel_blocks_diag_luma_cuda, 1)
+FME_STEP(filter_qpel_blocks_hor_ver_luma_cuda, 2)
+FME_STEP(filter_qpel_blocks_diag_luma_cuda, 3)
 
 /* ---- registration ---------------------------------------------------------------- */
 static int device_ready(uint8_t bitdepth)
@@ -405,6 +420,11 @@ int uvg_strategy_register_ipol_cuda(void *opaque, uint8_t bitdepth)
   int ok = 1;
   REG("sample_quarterpel_luma", sample_quarterpel_luma_cuda); REG("sample_quarterpel_luma_hi", sample_quarterpel_luma_hi_cuda);
   REG("sample_octpel_chroma", sample_octpel_chroma_cuda); REG("sample_octpel_chroma_hi", sample_octpel_chroma_hi_cuda);
+  REG("filter_hpel_blocks_hor_ver_luma", filter_hpel_blocks_hor_ver_luma_cuda);
+  REG("filter_hpel_blocks_diag_luma", filter_hpel_blocks_diag_luma_cuda);
+  REG("filter_qpel_blocks_hor_ver_luma", filter_qpel_blocks_hor_ver_luma_cuda);
+  REG("filter_qpel_blocks_diag_luma", filter_qpel_blocks_diag_luma_cuda);
+  /* get_extended_block(_wraparound): pure memcpy / border replication on the host side, left alone */
   return ok;
 }
 
