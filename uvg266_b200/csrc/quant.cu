@@ -298,6 +298,35 @@ quant_kernel(const int16_t *__restrict__ coef, int16_t *__restrict__ qcoef, size
   }
 }
 
+// Without sign hiding and LFNST, quant (:86-121) and dequant (:660-668) are element-wise: 8 coefficients
+// (one 16-byte vector) per thread and step, no shared memory. `total` is a multiple of 8 (area >= 16 / 8).
+template <bool DEQUANT>
+__global__ void __launch_bounds__(256)
+quant_flat_kernel(const int16_t *__restrict__ in, int16_t *__restrict__ out, size_t total8, QParams q)
+{
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total8; t += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(in) + t);
+    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int o[2];
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const int c = hlf ? (int)w[i] >> 16 : (int)(short)(w[i] & 0xffff);
+        if (DEQUANT) {
+          o[hlf] = clip3(-32768, 32767, (c * q.dq_scale + q.dq_add) >> q.dq_shift);
+        } else {
+          const int level = quant_level(c, q.coeff_default, q);
+          o[hlf] = clip3(-32768, 32767, c < 0 ? -level : level);
+        }
+      }
+      r[i] = ((uint32_t)o[0] & 0xffff) | ((uint32_t)o[1] << 16);
+    }
+    reinterpret_cast<uint4 *>(out)[t] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 dequant_kernel(const int16_t *__restrict__ qcoef, int16_t *__restrict__ coef, size_t total, QParams q)
 {
@@ -460,6 +489,17 @@ extern "C" int uvg_b200_quant_dev(const uvg_b200_quant_cfg *cfg, const int16_t *
   if (n_tus == 0) return 0;
   QParams q;
   if (make_qparams(q, cfg, w, h, color, transform_skip, lfnst_idx)) return 1;
+  {
+    const size_t total = n_tus * (size_t)q.area;
+    if (!q.signhide && !q.lfnst_idx && total % 8 == 0 && ((reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(q_coef)) & 15) == 0) {
+      size_t grid = (total / 8 + 255) / 256;
+      const size_t cap = (size_t)sm_count() * 16;
+      if (grid > cap) grid = cap;
+      quant_flat_kernel<false><<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(coef, q_coef, total / 8, q);
+      UVGB_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const int slots = slots_for(q.area);
   const size_t smem = (size_t)slots * 2 * q.area * sizeof(int16_t) + slots * sizeof(unsigned) + slots * 64;
   size_t grid = (n_tus + slots - 1) / slots;
@@ -480,6 +520,14 @@ extern "C" int uvg_b200_dequant_dev(const uvg_b200_quant_cfg *cfg, const int16_t
   uvg_b200_quant_cfg c = *cfg; c.signhide = 0;
   if (make_qparams(q, &c, w, h, color, transform_skip, 0)) return 1;
   const size_t total = n_tus * (size_t)q.area;
+  if (total % 8 == 0 && ((reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(q_coef)) & 15) == 0) {
+    size_t grid8 = (total / 8 + 255) / 256;
+    const size_t cap8 = (size_t)sm_count() * 16;
+    if (grid8 > cap8) grid8 = cap8;
+    quant_flat_kernel<true><<<(unsigned)grid8, 256, 0, static_cast<cudaStream_t>(stream)>>>(q_coef, coef, total / 8, q);
+    UVGB_LAUNCH_CHECK();
+    return 0;
+  }
   size_t grid = (total + 255) / 256;
   const size_t cap = (size_t)sm_count() * 16;
   if (grid > cap) grid = cap;

@@ -30,6 +30,31 @@ __device__ __forceinline__ void fwd_pass(const int16_t *__restrict__ src, int16_
                                          int reduced, int cutoff, int shift, int tid, int nthreads)
 {
   const int add = shift > 0 ? 1 << (shift - 1) : 0;
+  if (n >= 16) {             // (n % 4 == 0 and enough outputs per TU to keep every thread busy)
+    // four consecutive outputs per thread: one 32-bit word of the transposed matrix (4 int8) and one
+    // data sample per contraction step feed 4 MACs (the matrix rows are 4-byte aligned for n % 4 == 0)
+    const int nq = n >> 2, total4 = nq * line;
+    for (int o = tid; o < total4; o += nthreads) {
+      const int j = o / nq, k0 = (o - j * nq) << 2;
+      int sum[4] = { 0, 0, 0, 0 };
+      if (j < reduced && k0 < cutoff) {
+        const int16_t *s = src + j * n;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+          const int sv = s[i];
+          const uint32_t w = *reinterpret_cast<const uint32_t *>(Tt + i * n + k0);
+          sum[0] += sv * (int)(signed char)(w & 0xff); sum[1] += sv * (int)(signed char)((w >> 8) & 0xff);
+          sum[2] += sv * (int)(signed char)((w >> 16) & 0xff); sum[3] += sv * ((int)w >> 24);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = k0 + c;
+        dst[k * line + j] = (j < reduced && k < cutoff) ? (int16_t)(short)((sum[c] + add) >> shift) : (int16_t)0;
+      }
+    }
+    return;
+  }
   const int total = n * line;
   for (int o = tid; o < total; o += nthreads) {
     const int j = o / n, k = o - j * n;      // k fastest: conflict-free reads of Tt
@@ -54,6 +79,26 @@ __device__ __forceinline__ void inv_pass(const int16_t *__restrict__ src, int16_
                                          int reduced, int cutoff, int shift, int tid, int nthreads)
 {
   const int add = shift > 0 ? 1 << (shift - 1) : 0;
+  if (n >= 16) {             // (n % 4 == 0 and enough outputs per TU to keep every thread busy)
+    const int nq = n >> 2, total4 = nq * line;
+    for (int o = tid; o < total4; o += nthreads) {
+      const int j = o / nq, i0 = (o - j * nq) << 2;
+      int sum[4] = { 0, 0, 0, 0 };
+      if (j < reduced) {
+#pragma unroll 4
+        for (int k = 0; k < cutoff; ++k) {
+          const int sv = src[k * line + j];
+          const uint32_t w = *reinterpret_cast<const uint32_t *>(T + k * n + i0);
+          sum[0] += sv * (int)(signed char)(w & 0xff); sum[1] += sv * (int)(signed char)((w >> 8) & 0xff);
+          sum[2] += sv * (int)(signed char)((w >> 16) & 0xff); sum[3] += sv * ((int)w >> 24);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        dst[j * n + i0 + c] = j < reduced ? (int16_t)clip3(-32768, 32767, (sum[c] + add) >> shift) : (int16_t)0;
+    }
+    return;
+  }
   const int total = n * line;
   for (int o = tid; o < total; o += nthreads) {
     const int j = o / n, i = o - j * n;
