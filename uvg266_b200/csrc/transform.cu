@@ -227,10 +227,136 @@ transform_kernel(const int16_t *__restrict__ in, int16_t *__restrict__ out, size
   }
 }
 
+// ---- fast 2-D path: every dimension a multiple of 4 ---------------------------------------------------
+// Both passes read their contraction index contiguously: data rows as pairs of int16 (one 32-bit word),
+// matrix rows as 4 int8 per word, so one IDP.2A (dp2a) does two MACs; a thread owns a 4 x 4 tile of
+// outputs (4 matrix words + 4 x 2 data words feed 32 dp2a per step of 4 contraction indices).
+// Forward: load natural, pass 1 and pass 2 both write transposed (fastForward* contract).
+// Inverse: the coefficient block is transposed on the way into shared memory, pass 1 writes
+// transposed, pass 2 natural; the matrices are stored transposed (M[i][k] = T[k][i]).
+struct FastPass { int n, contr, out_limit, line, reduced, shift, clip, transposed_out; };
+
+__device__ __forceinline__ void fast_pass(const int16_t *__restrict__ src, int16_t *__restrict__ dst,
+                                          const int8_t *__restrict__ M, const FastPass f, int tid, int nthreads)
+{
+  const int add = f.shift > 0 ? 1 << (f.shift - 1) : 0;
+  const int nq = f.n >> 2, lq = f.line >> 2;
+  // rows are padded by 4 elements (data) / 4 bytes (matrix): tiles 4 rows apart land in different banks
+  const int sp = f.n + 4, mp = f.n + 4, dp = f.transposed_out ? f.line + 4 : f.n + 4;
+  for (int o = tid; o < nq * lq; o += nthreads) {
+    const int jq = o / nq, k0 = (o - jq * nq) << 2, j0 = jq << 2;
+    int acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+    if (j0 < f.reduced && k0 < f.out_limit) {
+      for (int i = 0; i < f.contr; i += 4) {
+        uint32_t m[4];
+        uint2 d[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) m[a] = *reinterpret_cast<const uint32_t *>(M + (k0 + a) * mp + i);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) d[b] = *reinterpret_cast<const uint2 *>(src + (j0 + b) * sp + i);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = __dp2a_hi((int)d[b].y, (int)m[a], __dp2a_lo((int)d[b].x, (int)m[a], acc[a][b]));
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int k = k0 + a, j = j0 + b;
+        int v = 0;
+        if (j < f.reduced && k < f.out_limit) {
+          v = (acc[a][b] + add) >> f.shift;
+          v = f.clip ? clip3(-32768, 32767, v) : (int)(short)v;
+        }
+        if (f.transposed_out) dst[k * dp + j] = (int16_t)v; else dst[j * dp + k] = (int16_t)v;
+      }
+  }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(256)
+transform_fast_kernel(const int16_t *__restrict__ in, int16_t *__restrict__ out, size_t n_tus, TrPlan p, int slots,
+                      FastPass f1, FastPass f2)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int area = p.w * p.h;
+  const int mx = p.w > p.h ? p.w : p.h, bsz = (mx + 4) * mx;          // one padded buffer (int16 elements)
+  int8_t *sM1 = reinterpret_cast<int8_t *>(smem_raw);
+  int8_t *sM2 = sM1 + p.n1 * (p.n1 + 4);
+  int16_t *sbuf = reinterpret_cast<int16_t *>(smem_raw + ((p.n1 * (p.n1 + 4) + p.n2 * (p.n2 + 4) + 15) & ~15));
+  for (int t = threadIdx.x; t < p.n1 * p.n1; t += blockDim.x) {
+    const int k = t / p.n1, i = t - k * p.n1;
+    if (INV) sM1[i * (p.n1 + 4) + k] = p.t1[t]; else sM1[k * (p.n1 + 4) + i] = p.t1[t];
+  }
+  for (int t = threadIdx.x; t < p.n2 * p.n2; t += blockDim.x) {
+    const int k = t / p.n2, i = t - k * p.n2;
+    if (INV) sM2[i * (p.n2 + 4) + k] = p.t2[t]; else sM2[k * (p.n2 + 4) + i] = p.t2[t];
+  }
+  const int tps = blockDim.x / slots, slot = threadIdx.x / tps, tid = threadIdx.x - slot * tps;
+  int16_t *bufA = sbuf + (size_t)slot * 2 * bsz, *bufB = bufA + bsz;
+  const int ip = f1.n + 4;                          // pitch of the pass-1 input rows
+  const int op = (INV ? f2.n : f2.line) + 4;        // pitch of the final rows (forward: transposed write)
+  const int ow = INV ? f2.n : f2.line;              // = p.w: both directions end row-major [h][w]
+  for (size_t base = (size_t)blockIdx.x * slots; base < n_tus; base += (size_t)gridDim.x * slots) {
+    const size_t tu = base + slot;
+    const bool active = tu < n_tus;
+    __syncthreads();
+    if (active) {
+      if (INV) {                                   // in[k][j] -> bufA[j][k]: the contraction index becomes contiguous
+        for (int t = tid; t < area; t += tps) { const int k = t / f1.line, j = t - k * f1.line; bufA[j * ip + k] = in[tu * area + t]; }
+      } else {
+        const int vpr = f1.n >> 2;                 // 8-byte vectors per input row
+        for (int t = tid; t < area / 4; t += tps) {
+          const int r = t / vpr, c = t - r * vpr;
+          *reinterpret_cast<uint2 *>(bufA + r * ip + 4 * c) = __ldg(reinterpret_cast<const uint2 *>(in + tu * area) + t);
+        }
+      }
+    }
+    __syncthreads();
+    if (active) fast_pass(bufA, bufB, sM1, f1, tid, tps);
+    __syncthreads();
+    if (active) fast_pass(bufB, bufA, sM2, f2, tid, tps);
+    __syncthreads();
+    if (active) {
+      const int vpr = ow >> 2;
+      for (int t = tid; t < area / 4; t += tps) {
+        const int r = t / vpr, c = t - r * vpr;
+        reinterpret_cast<uint2 *>(out + tu * area)[t] = *reinterpret_cast<const uint2 *>(bufA + r * op + 4 * c);
+      }
+    }
+  }
+}
+
 int launch_transform(bool inverse, const TrPlan &p, const int16_t *in, int16_t *out, size_t n_tus,
                      cudaStream_t st)
 {
   const int area = p.w * p.h;
+  const int cl1 = inverse ? p.cutoff1 : p.n1, cl2 = inverse ? p.cutoff2 : p.n2;     // contraction lengths
+  if (p.n2 && !(p.n1 & 3) && !(p.n2 & 3) && !(cl1 & 3) && !(cl2 & 3) && area >= 64 &&
+      !(reinterpret_cast<uintptr_t>(in) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15)) {
+    // forward: output cutoff, full contraction; inverse: full output, contraction stops at the cutoff
+    const FastPass f1{ p.n1, cl1, inverse ? p.n1 : p.cutoff1, p.line1, p.reduced1, p.shift1, inverse ? 1 : 0, 1 };
+    const FastPass f2{ p.n2, cl2, inverse ? p.n2 : p.cutoff2, p.line2, p.reduced2, p.shift2, inverse ? 1 : 0, inverse ? 0 : 1 };
+    const int items = (p.n1 / 4) * (p.line1 / 4);     // 4 x 4 output tiles per TU and pass (same for both passes)
+    int slots = 256 / items;
+    if (slots < 1) slots = 1;
+    const int mx = p.w > p.h ? p.w : p.h, bsz = (mx + 4) * mx;
+    while ((size_t)slots * 2 * bsz * sizeof(int16_t) > 40 * 1024) slots >>= 1;
+    const size_t smem = ((p.n1 * (p.n1 + 4) + p.n2 * (p.n2 + 4) + 15) & ~15) + (size_t)slots * 2 * bsz * sizeof(int16_t);
+    size_t grid = (n_tus + slots - 1) / slots;
+    const size_t cap = (size_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    if (inverse) transform_fast_kernel<true><<<(unsigned)grid, 256, smem, st>>>(in, out, n_tus, p, slots, f1, f2);
+    else transform_fast_kernel<false><<<(unsigned)grid, 256, smem, st>>>(in, out, n_tus, p, slots, f1, f2);
+    UVGB_LAUNCH_CHECK();
+    return 0;
+  }
   int slots = 256 / (area < 16 ? 16 : area);
   if (slots < 1) slots = 1;
   if (slots > 16) slots = 16;
