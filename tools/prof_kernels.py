@@ -54,3 +54,43 @@ for metric in (U.SAD_NXN, U.SATD):
         U.check(L.uvg_b200_distortion_dev(metric, 8, n, n, C.byref(A), C.byref(B), out.data_ptr(), N, 1, stream))
 torch.cuda.synchronize()
 print("ok")
+
+# ---- widened rows and standalone steps (one launch each, bench-sized) --------------------------------
+import numpy as np
+W, H = bench.FRAME_W, bench.CTU_ROWS * 64
+cur_h = bench.synth_plane_rows([(1, r) for r in range(bench.CTU_ROWS)])
+d_plane, d_cur = torch.from_numpy(plane_h).to(dev), torch.from_numpy(cur_h).to(dev)
+for n, modes in ((8, list(range(0, 67, 3))), (16, list(range(0, 67, 3)) + [1])):
+    gp = 2 * n + 4
+    ys, xs = np.meshgrid(np.arange(0, H, n), np.arange(0, W, n), indexing="ij")
+    ys, xs = ys.ravel(), xs.ravel()
+    i = np.arange(gp)
+    top = plane_h[np.clip(ys - 1, 0, H - 1)[:, None], np.clip(xs[:, None] - 1 + i[None, :], 0, W - 1)]
+    left = plane_h[np.clip(ys[:, None] - 1 + i[None, :], 0, H - 1), np.clip(xs - 1, 0, W - 1)[:, None]]
+    d_refs = torch.from_numpy(np.ascontiguousarray(np.stack([top, left], axis=1))).to(dev)
+    m8 = np.array(modes, dtype=np.int8)
+    cost = torch.zeros(ys.size * len(modes), dtype=torch.int32, device=dev)
+    desc = U.Blocks.plane(d_plane.data_ptr(), W, W, n, n)
+    U.check(L.uvg_b200_intra_rough_dev(8, n, C.byref(desc), d_refs.data_ptr(), m8.ctypes.data, len(modes), cost.data_ptr(), ys.size, stream))
+offs = [(0, 0)] + [(dx, dy) for dy in (-8, 0, 8) for dx in (-8, 0, 8) if (dx, dy) != (0, 0)] + \
+       [(dx, dy) for dy in (-4, 0, 4) for dx in (-4, 0, 4) if (dx, dy) != (0, 0)]
+offsets = np.array(offs, dtype=np.int8)
+ys, xs = np.meshgrid(np.arange(0, H, 16), np.arange(0, W, 16), indexing="ij")
+rng = np.random.default_rng(7)
+arrs = [xs.ravel().astype(np.int32), ys.ravel().astype(np.int32), (rng.integers(-8, 9, ys.size) * 16).astype(np.int32),
+        (rng.integers(-8, 9, ys.size) * 16).astype(np.int32)]
+dj = [torch.from_numpy(a_).to(dev) for a_ in arrs]
+cost = torch.zeros(ys.size * len(offs), dtype=torch.int32, device=dev)
+U.check(L.uvg_b200_frac_search_dev(8, 16, 16, d_cur.data_ptr(), d_plane.data_ptr(), W, W, H, dj[0].data_ptr(), dj[1].data_ptr(),
+                                   dj[2].data_ptr(), dj[3].data_ptr(), offsets.ctypes.data, len(offs), cost.data_ptr(), ys.size, stream))
+pred = torch.empty(ys.size * 256, dtype=torch.uint8, device=dev)
+U.check(L.uvg_b200_ipol_dev(8, 0, 0, d_plane.data_ptr(), W, W, H, 16, 16, dj[0].data_ptr(), dj[1].data_ptr(), dj[2].data_ptr(),
+                            dj[3].data_ptr(), pred.data_ptr(), ys.size, stream))
+NT = 1 << 18
+src = torch.randint(-255, 256, (NT * 1024,), dtype=torch.int16, device=dev)
+dst = torch.zeros_like(src)
+U.check(L.uvg_b200_transform_dev(0, 8, 32, 32, 0, 0, 0, 0, src.data_ptr(), dst.data_ptr(), NT, stream))
+U.check(L.uvg_b200_transform_dev(1, 8, 32, 32, 0, 0, 0, 0, dst.data_ptr(), src.data_ptr(), NT, stream))
+U.check(L.uvg_b200_quant_dev(C.byref(cfg), src.data_ptr(), dst.data_ptr(), 32, 32, 0, 0, 0, NT, stream))
+torch.cuda.synchronize()
+print("ok (widened rows)")
