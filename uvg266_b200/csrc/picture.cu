@@ -502,10 +502,16 @@ static int launch_sad_ssd(const Blocks &A, const Blocks &B, uint32_t *out, size_
     UVGB_LAUNCH_CHECK();
     return 0;
   }
+  // Small dense blocks (4x4, 8-bit 8x8: the whole block is <= 64 contiguous bytes): treat the block as one
+  // row of w*h pixels and give every lane ONE 16-byte chunk, so that a warp's loads are fully coalesced
+  // (as rows, an 8x8 u8 block is sixteen 4-byte chunks per operand: 41 % of the HBM roofline).
+  const size_t blk_bytes = (size_t)w * h * sizeof(Pix);
+  const bool linear = A.stride == (uint32_t)w && B.stride == (uint32_t)w && blk_bytes <= 64 && blk_bytes % 16 == 0 && h > 1;
+  if (linear) { w *= h; h = 1; }
   const bool wide = (w % (4 * PW)) == 0;
   const int chunks = wide ? (w / (4 * PW)) * h : (w / PW) * h;
   // aim for >= 4 chunks per lane so several loads are in flight per thread
-  int G = pick_group((chunks + 3) / 4);
+  int G = linear ? pick_group(chunks) : pick_group((chunks + 3) / 4);
   const int block = 256;
 #define UVGB_SAD_CASE(GG)                                                                      \
   case GG:                                                                                     \
