@@ -390,6 +390,15 @@ def gpu_arm(args):
         extra["pairs_64x64"] = pair_bench(torch, U, L, dev, stream, hbm_peak)
         if world == 1:
             extra["next_rows"] = next_rows_bench(torch, U, L, dev, stream)
+            if not args.no_cpu_baseline:
+                # the same hot path with the rough-search predictions generated on the device, both arms
+                # (secondary: the headline e2e below keeps the step that takes predictions as inputs)
+                try:
+                    sys.path.insert(0, os.path.join(ROOT, "tools"))
+                    import e2e_predict_on_device as pod
+                    extra["e2e_predict_on_device"] = pod.run(steps=max(3, min(args.e2e_steps, 6)), threads=args.e2e_threads)
+                except Exception as exc:  # reported, never silently replaced
+                    extra["e2e_predict_on_device"] = {"unavailable": str(exc)}
 
     # ---- e2e: the same step through the host-buffer C-ABI entry points (pinned host memory) ----
     e2e = e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, dev)
