@@ -8,7 +8,12 @@
 // only way up is fewer instructions per byte. The 2-D Hadamard of an 8x8 block is one product
 // with the 64x64 +-1 matrix H8 (x) H8 (entry (k,n) = (-1)^popcount(k & n)), and by linearity
 // H(O - P)H^T = H O H^T - H P H^T, so the 8-bit pixels themselves are the u8 operand:
-//   mma.sync.m16n8k32.u8.s8: 16 blocks (rows) x 64 pixels (K) x 64 coefficients (N) = 16 IMMAs,
+//   mma.sync.m16n8k32.u8.s8: 16 blocks (rows) x 64 pixels (K) x 64 coefficients (N). K is split
+//   into even / odd pixel rows (the lane's two 16-byte vectors): S0, S1 for the four even
+//   coefficient columns are 8 IMMAs, and the odd columns differ only in the sign of the odd pixel
+//   rows, so coefficient 2j = S0 + S1 and 2j+1 = S0 - S1 (one accumulator butterfly instead of
+//   8 more IMMAs). 13 -> 8 IMMAs per tile left the kernel time unchanged (0.0906 / 0.0720 ms):
+//   the kernel is issue / latency bound (55 % issue, L1 56 %), not tensor-pipe bound;
 //   row 0 of every tile = the original block, rows 1..15 = 15 candidates of that block;
 //   epilogue per lane: 32 x VABSDIFF-accumulate |Z - T_O| (T_O broadcast from row 0 by shuffle),
 //   8 x VABSDIFF4 for the SAD on the same fragment registers, one packed quad reduction.
@@ -55,18 +60,17 @@ rough_mma_kernel(Blocks A, const uint8_t *__restrict__ cand, uint32_t *__restric
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   // B operand = column n = 8j + g of H8 (x) H8 at rows m = 16t + 8s + 4h + i: sign = parity of
   // popcount(m & n) = (i & g & 3) ^ (h & g>>2) ^ (s & j) ^ (t & j>>1): byte pattern and the (h, j>>1)
-  // dependent flips are per-lane registers, the (s & j & 1) flip picks the negated copy at compile time.
+  // dependent flips are per-lane registers; the (s & j & 1) flip is a butterfly on the accumulators.
   uint32_t pat = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) pat |= ((__popc(i & g & 3) & 1) ? 0xffu : 0x01u) << (8 * i);
-  uint32_t wp[2][4], wn[2][4];
+  uint32_t wp[2][4];
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int flip = ((h & (g >> 2)) ^ __popc(t & jj)) & 1;
       wp[h][jj] = flip ? pat ^ 0xfefefefeu : pat;
-      wn[h][jj] = wp[h][jj] ^ 0xfefefefeu;
     }
   const int tiles = (k + kRowsPerTile - 1) / kRowsPerTile;
   const uint32_t warp_global = blockIdx.x * 4 + (threadIdx.x >> 5), n_warps = gridDim.x * 4;
@@ -132,16 +136,19 @@ rough_mma_kernel(Blocks A, const uint8_t *__restrict__ cand, uint32_t *__restric
     for (int p = 0; p < PAIR; ++p) {
       uint32_t a[2][4];
       frag(cur, p, a);
+      // k-step s holds the pixel rows of parity s, so column tile j (vertical frequency v = j) sees
+      // (-1)^(s & j): the even rows contribute the same to tiles 2jj and 2jj+1, the odd rows with
+      // opposite sign. Eight IMMAs give S0 (even rows) and S1 (odd rows) of the four even tiles; one
+      // butterfly on the accumulators gives all eight tiles: Z[2jj] = S0 + S1, Z[2jj+1] = S0 - S1.
       int acc[8][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0; }
+      for (int jj = 0; jj < 4; ++jj) {
+        int s0[4] = { 0, 0, 0, 0 }, s1[4] = { 0, 0, 0, 0 };
+        imma32(s0, a[0], wp[0][jj], wp[1][jj]);
+        imma32(s1, a[1], wp[0][jj], wp[1][jj]);
 #pragma unroll
-      for (int s = 0; s < 2; ++s)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool neg = s & j & 1;
-          imma32(acc[j], a[s], neg ? wn[0][j >> 1] : wp[0][j >> 1], neg ? wn[1][j >> 1] : wp[1][j >> 1]);
-        }
+        for (int c = 0; c < 4; ++c) { acc[2 * jj][c] = s0[c] + s1[c]; acc[2 * jj + 1][c] = s0[c] - s1[c]; }
+      }
       unsigned sl = 0, sh = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {

@@ -5,8 +5,9 @@
 // (picture-generic.c:256-348 8x8 Hadamard incl. the |dc|>>2 rule, :371-410, :1091-1113).
 //
 // The packed-ALU Hadamard (rough.cu) needs ~860 issue slots per 8x8 candidate and saturates the
-// issue ports at 40-43 % of the HBM roofline; mma.sync IMMA (rough_mma.cu) runs ~32 cycles per
-// m16n8k32 on this part and ends up no faster. tcgen05 does the same product at full rate:
+// issue ports at 40-43 % of the HBM roofline; mma.sync IMMA (rough_mma.cu) keeps the accumulators
+// in registers and pays ~390 instructions of epilogue per tile, ending up no faster. tcgen05 does
+// the same product with the accumulators in TMEM:
 //   the 2-D Hadamard of an 8x8 block is one product with the 64x64 +-1 matrix H8 (x) H8
 //   (entry (k, n) = (-1)^popcount(k & n)); H(O - P)H^T = H O H^T - H P H^T, so the u8 pixels are
 //   the A operand as they are, and the original block is just one more row of the same tile.
