@@ -292,6 +292,8 @@ UVG_B200_API void uvg_b200_set_dropin_bitdepth(int bitdepth);
   UVG_B200_API void uvg_b200_sad_8x8_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);   \
   UVG_B200_API void uvg_b200_sad_16x16_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out); \
   UVG_B200_API void uvg_b200_sad_32x32_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out); \
+  UVG_B200_API void uvg_b200_sad_64x64_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out); \
+  UVG_B200_API void uvg_b200_satd_64x64_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);\
   UVG_B200_API void uvg_b200_satd_4x4_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);  \
   UVG_B200_API void uvg_b200_satd_8x8_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);  \
   UVG_B200_API void uvg_b200_satd_16x16_dual_##SUF(const PIX *preds, const PIX *orig, unsigned n, unsigned *out);\

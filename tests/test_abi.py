@@ -24,7 +24,7 @@ def test_every_reference_strategy_type_has_a_dropin():
     picture = (["reg_sad", "satd_any_size", "satd_any_size_vtm", "satd_any_size_quad", "pixels_calc_ssd",
                 "get_optimized_sad", "ver_sad", "hor_sad", "generate_residual"] +
                ["%s_%dx%d" % (m, n, n) for m in ("sad", "satd") for n in (4, 8, 16, 32, 64)] +
-               ["%s_%dx%d_dual" % (m, n, n) for m in ("sad", "satd") for n in (4, 8, 16, 32)])
+               ["%s_%dx%d_dual" % (m, n, n) for m in ("sad", "satd") for n in (4, 8, 16, 32, 64)])
     for suf in ("8", "16"):
         for t in picture:
             assert hasattr(L, "uvg_b200_%s_%s" % (t, suf)), t

@@ -104,8 +104,8 @@ def test_dropin_picture_nxn(bd):
             a = rnd_pix(rng, bd, n * n, extreme=(it == 0)); b = rnd_pix(rng, bd, n * n, extreme=(it == 0))
             assert sad(ptr(a), ptr(b)) == O.orc_sad_nxn(n, ptr(a), ptr(b))
             assert satd(ptr(a), ptr(b)) == O.orc_satd_nxn(n, ptr(a), ptr(b))
-            if n <= 32:
-                preds = rnd_pix(rng, bd, 2048)
+            if True:
+                preds = rnd_pix(rng, bd, 1024 + max(1024, n * n))    # 64x64 dual: overlapping 4096-pixel reads
                 c1 = np.zeros(2, np.uint32); c2 = np.zeros(2, np.uint32)
                 U.dropin("sad_%dx%d_dual" % (n, n), bd)(ptr(preds), ptr(a), 2, ptr(c1))
                 O.orc_sad_nxn_dual(n, ptr(preds), ptr(a), ptr(c2)); assert (c1 == c2).all()

@@ -38,8 +38,10 @@ def test_picture_pair_functions(bd):
             b = rnd_pix(rng, bd, n * n, extreme=(it == 0))
             assert O.orc_sad_nxn(n, ptr(a), ptr(b)) == sad(ptr(a), ptr(b))
             assert O.orc_satd_nxn(n, ptr(a), ptr(b)) == satd(ptr(a), ptr(b))
-            if n <= 32:
-                preds = rnd_pix(rng, bd, 2 * 1024)
+            if True:
+                # pred_buffer slots are 1024 pixels apart for every n; the (unreachable) 64x64 dual reads
+                # 4096 pixels from each slot, i.e. overlapping ranges
+                preds = rnd_pix(rng, bd, 1024 + max(1024, n * n))
                 c1 = np.zeros(2, np.uint32); c2 = np.zeros(2, np.uint32)
                 O.orc_sad_nxn_dual(n, ptr(preds), ptr(a), ptr(c1)); sad2(ptr(preds), ptr(a), 2, ptr(c2))
                 assert (c1 == c2).all()

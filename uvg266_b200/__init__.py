@@ -113,9 +113,8 @@ def lib():
             for m in ("sad", "satd"):
                 f = getattr(L, "uvg_b200_%s_%dx%d_%s" % (m, n, n, suf))
                 f.argtypes = [vp, vp]; f.restype = C.c_uint
-                if n <= 32:
-                    g = getattr(L, "uvg_b200_%s_%dx%d_dual_%s" % (m, n, n, suf))
-                    g.argtypes = [vp, vp, C.c_uint, vp]; g.restype = None
+                g = getattr(L, "uvg_b200_%s_%dx%d_dual_%s" % (m, n, n, suf))
+                g.argtypes = [vp, vp, C.c_uint, vp]; g.restype = None
         f = getattr(L, "uvg_b200_reg_sad_" + suf); f.argtypes = [vp, vp, i, i, C.c_uint, C.c_uint]; f.restype = C.c_uint
         for nm in ("satd_any_size_", "satd_any_size_vtm_"):
             f = getattr(L, "uvg_b200_" + nm + suf); f.argtypes = [i, i, vp, i, vp, i]; f.restype = C.c_uint

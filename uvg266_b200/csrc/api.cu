@@ -490,6 +490,8 @@ extern "C" int uvg_b200_quantize_residual_host(const uvg_b200_quant_cfg *cfg, in
   extern "C" void uvg_b200_sad_8x8_dual_##SUF(const PIX *p, const PIX *o, unsigned n, unsigned *out) { (void)n; dropin_dual<PIX>(UVG_B200_SAD_NXN, 8, p, o, out); }     \
   extern "C" void uvg_b200_sad_16x16_dual_##SUF(const PIX *p, const PIX *o, unsigned n, unsigned *out) { (void)n; dropin_dual<PIX>(UVG_B200_SAD_NXN, 16, p, o, out); }  \
   extern "C" void uvg_b200_sad_32x32_dual_##SUF(const PIX *p, const PIX *o, unsigned n, unsigned *out) { (void)n; dropin_dual<PIX>(UVG_B200_SAD_NXN, 32, p, o, out); }  \
+  extern "C" void uvg_b200_sad_64x64_dual_##SUF(const PIX *p, const PIX *o, unsigned n, unsigned *out) { (void)n; dropin_dual<PIX>(UVG_B200_SAD_NXN, 64, p, o, out); }  \
+  extern "C" void uvg_b200_satd_64x64_dual_##SUF(const PIX *p, const PIX *o, unsigned n, unsigned *out) { (void)n; dropin_dual<PIX>(UVG_B200_SATD, 64, p, o, out); }    \
   extern "C" void uvg_b200_satd_4x4_dual_##SUF(const PIX *p, const PIX *o, unsigned n, unsigned *out) { (void)n; dropin_dual<PIX>(UVG_B200_SATD_4X4, 4, p, o, out); }   \
   extern "C" void uvg_b200_satd_8x8_dual_##SUF(const PIX *p, const PIX *o, unsigned n, unsigned *out) { (void)n; dropin_dual<PIX>(UVG_B200_SATD, 8, p, o, out); }       \
   extern "C" void uvg_b200_satd_16x16_dual_##SUF(const PIX *p, const PIX *o, unsigned n, unsigned *out) { (void)n; dropin_dual<PIX>(UVG_B200_SATD, 16, p, o, out); }    \

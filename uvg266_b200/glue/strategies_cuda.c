@@ -66,7 +66,7 @@ NXN(4) NXN(8) NXN(16) NXN(32) NXN(64)
   static void satd_##n##_dual_cuda(const pred_buffer preds, const uvg_pixel *const orig,         \
                                    unsigned num_modes, unsigned *costs_out)                      \
   { B200(satd_##n##x##n##_dual)(&preds[0][0], orig, num_modes, costs_out); }
-DUAL(4) DUAL(8) DUAL(16) DUAL(32)
+DUAL(4) DUAL(8) DUAL(16) DUAL(32) DUAL(64)
 
 static unsigned satd_any_size_cuda(int w, int h, const uvg_pixel *b1, int s1, const uvg_pixel *b2, int s2)
 { return B200(satd_any_size)(w, h, b1, s1, b2, s2); }
@@ -377,8 +377,9 @@ int uvg_strategy_register_picture_cuda(void *opaque, uint8_t bitdepth)
   REG("sad_16x16_dual", sad_16_dual_cuda); REG("sad_32x32_dual", sad_32_dual_cuda);
   REG("satd_4x4_dual", satd_4_dual_cuda); REG("satd_8x8_dual", satd_8_dual_cuda);
   REG("satd_16x16_dual", satd_16_dual_cuda); REG("satd_32x32_dual", satd_32_dual_cuda);
-  /* sad/satd_64x64_dual exist in the table but are unreachable (search_intra.c:1000): left to
-   * the implementations the reference registers */
+  /* unreachable from the encoder (search_intra.c:1000) but in the table: pred_buffer semantics kept
+   * literally - candidate 1 starts 1024 pixels after candidate 0 and both read 4096 pixels */
+  REG("sad_64x64_dual", sad_64_dual_cuda); REG("satd_64x64_dual", satd_64_dual_cuda);
   REG("satd_any_size_quad", satd_any_size_quad_cuda);
   REG("pixels_calc_ssd", pixels_calc_ssd_cuda);
   REG("get_optimized_sad", get_optimized_sad_cuda);
