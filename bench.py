@@ -301,7 +301,7 @@ def gpu_arm(args):
     step_bytes = sum(x["bytes"] for x in rough) + sum(x["bytes"] for x in tus)
 
     names = ["rough_cost 8x8 k=23 (rough_staged_kernel<8>)", "rough_cost 16x16 k=24 (rough_mma_kernel<16>)",
-             "quantize_residual 4x4 (fused_small_kernel<4>)", "quantize_residual 8x8 (fused_imma_kernel<8>)",
+             "quantize_residual 4x4 (fused_small_kernel<4>)", "quantize_residual 8x8 (fused_imma8_kernel)",
              "quantize_residual 16x16 (fused_imma_kernel<16>)", "quantize_residual 32x32 (fused_imma_kernel<32>)"]
     kbytes = [x["bytes"] for x in rough] + [x["bytes"] for x in tus]
 

@@ -24,6 +24,8 @@
 // 8x8 TUs: two TUs per warp, stacked in the M dimension with block-diagonal constant operands
 // (rows g <-> TU A, rows g+8 <-> TU B), so fragments are fully used.
 #include "quant.cuh"
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -454,6 +456,211 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 8x8 specialisation (the kernel of the path with the lowest bytes/s: 120 TUs per CTU).
+// Same four products and the same two-TUs-per-warp stacking as fused_imma_kernel<8>, with the
+// instruction stream cut to what an 8-bit 8x8 TU needs:
+//   * a lane loads the two pixels (2t, 2t+1) of row g of BOTH TUs (four 16-bit loads); the F1
+//     contraction slots are permuted to match (slot 4t+e <-> TU e>>1, pixel 2t+(e&1)), so the
+//     inverse transform hands every lane back exactly the pixels it loaded: no shuffles;
+//   * the eight constant fragment words live in registers for the whole grid-stride loop (no
+//     shared memory, no barrier);
+//   * the rounding offsets enter as the C operand of the first mma of each stage;
+//   * shifts are literals (8-bit video: 2 / 9 / 7 / 12), there is no zero-out for 8-point
+//     transforms (skip_w/h only exist for 32-point, dct-generic.c:2582-2583), and the level
+//     clip is dropped: q_bits >= 18 here (14 + qp/6 + transform_shift 4, quant-generic.c:62-77),
+//     so |level| <= (32768 * 26214 + add) >> 18 < 3300;
+//   * fast_coeff_cost weights are picked with one PRMT from the packed Q8.8 table instead of a
+//     4-way branch; 32-bit block indexing.
+template <bool AU, bool BU>
+__device__ __forceinline__ void imma_c(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0, int c)
+{
+  if (AU && !BU)
+    asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};\n"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(b0), "r"(c));
+  else if (!AU && BU)
+    asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};\n"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(b0), "r"(c));
+  else
+    asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};\n"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(b0), "r"(c));
+}
+
+// byte offset of block i (i, pitches < 2^32: checked on the host)
+__device__ __forceinline__ uint64_t block_off32(const Blocks &b, uint32_t i)
+{
+  if (b.bpr == 1) return (uint64_t)i * (uint32_t)b.row_pitch;
+  const uint32_t r = i / b.bpr, c = i - r * b.bpr;
+  return (uint64_t)r * (uint32_t)b.row_pitch + (uint64_t)c * (uint32_t)b.col_pitch;
+}
+
+// fragment words of lane (g, t), [word][lane]: AH0 AH1 ANH0 ANH1 AVT0 AVT1 BV BH
+static void build_tables8(const int8_t *th, const int8_t *tv, std::vector<uint32_t> &out)
+{
+  out.assign(8 * 32, 0);
+  for (int ln = 0; ln < 32; ++ln) {
+    const int g = ln >> 2, t = ln & 3;
+    for (int r = 0; r < 2; ++r) {
+      int bh[4], bv[4];
+      for (int e = 0; e < 4; ++e) {
+        bh[e] = ((e >> 1) == r) ? th[g * 8 + 2 * t + (e & 1)] : 0;      // F1: slot e -> TU e>>1, pixel 2t+(e&1)
+        bv[e] = ((e >> 1) == r) ? tv[(2 * t + (e & 1)) * 8 + g] : 0;    // I1: slot e -> TU e>>1, kv 2t+(e&1)
+      }
+      out[(0 + r) * 32 + ln] = pack4(bh[0], bh[1], bh[2], bh[3]);
+      out[(2 + r) * 32 + ln] = pack4(-bh[0], -bh[1], -bh[2], -bh[3]);
+      out[(4 + r) * 32 + ln] = pack4(bv[0], bv[1], bv[2], bv[3]);
+    }
+    out[6 * 32 + ln] = pack4(tv[g * 8 + 2 * t], tv[g * 8 + 2 * t + 1], 0, 0);             // F2 B: slots e>=2 are padding
+    out[7 * 32 + ln] = pack4(th[(2 * t) * 8 + g], th[(2 * t + 1) * 8 + g], 0, 0);         // I2 B
+  }
+}
+
+static const uint32_t *cached_tables8(int th, int tv)
+{
+  static std::mutex mu;
+  static const uint32_t *cache[3][3] = {};
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache[th][tv]) return cache[th][tv];
+  std::vector<uint32_t> h;
+  build_tables8(tr_matrix_host(th, 8), tr_matrix_host(tv, 8), h);
+  uint32_t *d = nullptr;
+  if (cudaMalloc(&d, h.size() * 4) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  cache[th][tv] = d;
+  return d;
+}
+
+__global__ void __launch_bounds__(128)
+fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__restrict__ tab)
+{
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const uint32_t ah0 = tab[lane], ah1 = tab[32 + lane], anh0 = tab[64 + lane], anh1 = tab[96 + lane];
+  const uint32_t avt0 = tab[128 + lane], avt1 = tab[160 + lane], bv = tab[192 + lane], bh = tab[224 + lane];
+  const uint32_t wlo = a.w0 | (a.w1 << 16), whi = a.w2 | (a.w3 << 16);
+  const uint32_t n_units = (n_tus + 1) >> 1;
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  const uint8_t *ref_b = static_cast<const uint8_t *>(a.ref.base), *pred_b = static_cast<const uint8_t *>(a.pred.base);
+  uint8_t *rec_b = const_cast<uint8_t *>(static_cast<const uint8_t *>(a.rec.base));
+  const uint32_t ref_ln = g * a.ref.stride + 2 * t, pred_ln = g * a.pred.stride + 2 * t, rec_ln = g * a.rec.stride + 2 * t;
+  const bool do_recon = !a.early_skip;
+
+  for (uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < n_units; unit += warps_total) {
+    const uint32_t tuA = 2 * unit;
+    const bool validB = tuA + 1 < n_tus;
+    const uint32_t tuB = validB ? tuA + 1 : tuA;
+    // ---- pixels (2t, 2t+1) of row g of both TUs -----------------------------------------------
+    const uint32_t rA = __ldg(reinterpret_cast<const uint16_t *>(ref_b + block_off32(a.ref, tuA) + ref_ln));
+    const uint32_t rB = __ldg(reinterpret_cast<const uint16_t *>(ref_b + block_off32(a.ref, tuB) + ref_ln));
+    const uint32_t pA = __ldg(reinterpret_cast<const uint16_t *>(pred_b + block_off32(a.pred, tuA) + pred_ln));
+    uint32_t pB = __ldg(reinterpret_cast<const uint16_t *>(pred_b + block_off32(a.pred, tuB) + pred_ln));
+    if (!validB) pB = rB;                                  // odd tail: the phantom TU has zero residual
+    const uint32_t refw = rA | (rB << 16), predw = pA | (pB << 16);
+
+    // ---- F1: D' = Th X^T (rows kh of TU A | TU B, columns = pixel rows 2t, 2t+1) ----------------
+    int v[4];
+    {
+      int d[4];
+      imma_c<false, true>(d, ah0, ah1, refw, 2);
+      imma<false, true>(d, anh0, anh1, predw);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = (int)(short)(d[c] >> 2);
+    }
+    // ---- F2: Y^T = D' Tv^T (rows kh, columns kv = 2t, 2t+1); bytes 2,3 of the A words meet zeros --
+    {
+      int accL[4], accH[4];
+      imma_c<true, false>(accL, __byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), bv, 256);
+      imma_c<false, false>(accH, __byte_perm(v[0], v[1], 0x0051), __byte_perm(v[2], v[3], 0x0051), bv, 0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = (int)(short)((accH[c] * 256 + accL[c]) >> 9);
+    }
+    // ---- quant, cost, dequant: c0,c1 = TU A (kh g, kv 2t, 2t+1), c2,c3 = TU B --------------------
+    unsigned ul[4], wg[4];
+    int lv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      ul[c] = ((unsigned)abs(v[c]) * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits;
+      lv[c] = v[c] < 0 ? -(int)ul[c] : (int)ul[c];
+      wg[c] = __byte_perm(wlo, whi, min(ul[c], 3u) * 0x22u + 0x10u) & 0xffffu;
+      v[c] = clip3(-32768, 32767, (lv[c] * q.dq_scale + q.dq_add) >> q.dq_shift);
+    }
+    {
+      int16_t *co = a.coeff_out + (size_t)tuA * 64 + 16 * t + g;           // [kv][kh]
+      co[0] = (int16_t)lv[0]; co[8] = (int16_t)lv[1];
+      if (validB) { co[64] = (int16_t)lv[2]; co[72] = (int16_t)lv[3]; }
+    }
+    const bool hasA = __any_sync(0xffffffffu, (ul[0] | ul[1]) != 0);
+    const bool hasB = __any_sync(0xffffffffu, (ul[2] | ul[3]) != 0);
+    if (a.cost) {
+      const unsigned costA = __reduce_add_sync(0xffffffffu, wg[0] + wg[1]);
+      const unsigned costB = __reduce_add_sync(0xffffffffu, wg[2] + wg[3]);
+      if (lane == 0) {
+        a.cost[tuA] = (costA + 128u) >> 8;
+        if (validB) a.cost[tuA + 1] = (costB + 128u) >> 8;
+      }
+    }
+    if (lane == 0) {
+      a.has_coeffs[tuA] = hasA ? 1 : 0;
+      if (validB) a.has_coeffs[tuA + 1] = hasB ? 1 : 0;
+    }
+    const bool reconA = hasA && do_recon, reconB = hasB && do_recon;
+
+    // ---- I1, I2, reconstruction (skipped when neither TU has coefficients) ---------------------
+    uint32_t outw = predw;
+    if (reconA || reconB) {
+      uint32_t lo, hi;
+      split4(v[0], v[1], v[2], v[3], lo, hi);
+      int accL[4], accH[4], u[4];
+      imma_c<false, true>(accL, avt0, avt1, lo, 64);
+      imma_c<false, false>(accH, avt0, avt1, hi, 0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) u[c] = clip3(-32768, 32767, (accH[c] * 256 + accL[c]) >> 7);
+      imma_c<true, false>(accL, __byte_perm(u[0], u[1], 0x0040), __byte_perm(u[2], u[3], 0x0040), bh, 2048);
+      imma_c<false, false>(accH, __byte_perm(u[0], u[1], 0x0051), __byte_perm(u[2], u[3], 0x0051), bh, 0);
+      int px[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int r = clip3(-32768, 32767, (accH[c] * 256 + accL[c]) >> 12);
+        px[c] = clip3(0, q.pixel_max, (int)(short)(r + (int)((predw >> (8 * c)) & 0xffu)));
+      }
+      const uint32_t w = pack4(px[0], px[1], px[2], px[3]);
+      outw = (reconA ? (w & 0xffffu) : (predw & 0xffffu)) | (reconB ? (w & 0xffff0000u) : (predw & 0xffff0000u));
+    }
+    if (reconA || !a.rec_is_pred)
+      *reinterpret_cast<uint16_t *>(rec_b + block_off32(a.rec, tuA) + rec_ln) = (uint16_t)outw;
+    if (validB && (reconB || !a.rec_is_pred))
+      *reinterpret_cast<uint16_t *>(rec_b + block_off32(a.rec, tuB) + rec_ln) = (uint16_t)(outw >> 16);
+    if (a.ssd) {
+      const uint32_t d4 = __vabsdiffu4(refw, outw);
+      const unsigned ssdA = __reduce_add_sync(0xffffffffu, __dp4a(d4 & 0xffffu, d4, 0u));
+      const unsigned ssdB = __reduce_add_sync(0xffffffffu, __dp4a(d4 & 0xffff0000u, d4, 0u));
+      if (lane == 0) {
+        a.ssd[tuA] = (uint32_t)((int32_t)ssdA >> q.ssd_shift);
+        if (validB) a.ssd[tuA + 1] = (uint32_t)((int32_t)ssdB >> q.ssd_shift);
+      }
+    }
+  }
+}
+
+static bool fits32(const Blocks &b) { return b.row_pitch < (1ull << 32) && b.col_pitch < (1ull << 32); }
+
+// -1 = not covered (the general fused_imma_kernel<8> takes it)
+static int launch_imma8(const FusedArgs &a, size_t n_tus, const QParams &q, int th, int tv, cudaStream_t st)
+{
+  static const char *force = getenv("UVG266_B200_FUSED8");
+  if (force && !strcmp(force, "general")) return -1;
+  if (n_tus >= (1ull << 31) || q.q_bits < 16 || q.q_bits > 31 || !fits32(a.ref) || !fits32(a.pred) || !fits32(a.rec)) return -1;
+  const uint32_t *tab = cached_tables8(th, tv);
+  if (!tab) { set_error("fused_imma8: fragment table allocation failed"); return 1; }
+  const int warps_per_block = 4;
+  const size_t n_units = (n_tus + 1) / 2;
+  size_t grid = (n_units + warps_per_block - 1) / warps_per_block;
+  const size_t cap = (size_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  fused_imma8_kernel<<<(unsigned)grid, warps_per_block * 32, 0, st>>>(a, (uint32_t)n_tus, q, tab);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int N>
 static int launch_imma(const FusedArgs &a, size_t n_tus, const QParams &q, const ImmaParams &p, cudaStream_t st)
 {
@@ -489,7 +696,10 @@ int launch_fused_imma(const FusedArgs &a, size_t n_tus, const QParams &q, int bi
   p.cut1 = (th == UVG_B200_DCT2 || N < 8) ? N : N - skip_w;
   p.cut2 = (tv == UVG_B200_DCT2 || N < 8) ? N : N - skip_h;
   switch (N) {
-    case 8: return launch_imma<8>(a, n_tus, q, p, st);
+    case 8: {
+      const int rc = launch_imma8(a, n_tus, q, th, tv, st);
+      return rc >= 0 ? rc : launch_imma<8>(a, n_tus, q, p, st);
+    }
     case 16: return launch_imma<16>(a, n_tus, q, p, st);
     default: return launch_imma<32>(a, n_tus, q, p, st);
   }
