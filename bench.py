@@ -584,14 +584,23 @@ def e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, d
                 x["ssd"].data_ptr() + lo * 4, x["cost"].data_ptr() + lo * 4, hi - lo)
     plans = [([rough_slice(x, w) for x in hr], [tu_slice(x, w) for x in ht]) for w in range(T)]
 
-    def work(w):
-        rs, ts = plans[w]
-        for x, (A, ab, B, bb, out, nb) in zip(hr, rs):
+    def do_rough(w):
+        for x, (A, ab, B, bb, out, nb) in zip(hr, plans[w][0]):
             U.check(L.uvg_b200_rough_cost_host(8, x["n"], C.byref(A), ab, C.byref(B), bb, out, nb, x["k"]))
-        for x, (R, P, O, nbytes, coeff, has, ssd, cost, nt) in zip(ht, ts):
+
+    def do_tus(w):
+        for x, (R, P, O, nbytes, coeff, has, ssd, cost, nt) in zip(ht, plans[w][1]):
             U.check(L.uvg_b200_quantize_residual_host(C.byref(cfg), 1, 0, x["n"], x["n"], 0, 0, 0, C.byref(R), nbytes,
                                                       C.byref(P), nbytes, C.byref(O), nbytes, coeff, has, ssd, cost,
                                                       COST_WEIGHTS, nt))
+
+    def work(w):
+        # the rough-cost calls are upload-heavy (425 MB in, 12 MB out per step), the TU calls download-heavy
+        # (77 MB in, 150 MB out): odd threads take their TU slice first so both PCIe directions stay busy
+        if args.e2e_order == "interleaved" and (w & 1):
+            do_tus(w); do_rough(w)
+        else:
+            do_rough(w); do_tus(w)
     import concurrent.futures
     pool = concurrent.futures.ThreadPoolExecutor(T)
 
@@ -610,9 +619,24 @@ def e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, d
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     secs = float(t.item())
-    return {"value": n_ctu * world * k / secs, "unit": "CTU/s", "h2d_bytes_per_step": int(h2d),
+    # what the link itself does on this box (one 256 MiB pinned copy per direction, best of 3): the ceiling for e2e
+    probe = {}
+    try:
+        hb = torch.empty(1 << 28, dtype=torch.uint8, pin_memory=True); db = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+        for name, (dst, src) in (("h2d_gbs", (db, hb)), ("d2h_gbs", (hb, db))):
+            best = 0.0
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); dst.copy_(src, non_blocking=True); b.record(); torch.cuda.synchronize()
+                best = max(best, (1 << 28) / (a.elapsed_time(b) * 1e-3) / 1e9)
+            probe[name] = round(best, 1)
+        del hb, db
+    except RuntimeError:
+        pass
+    return {"value": n_ctu * world * k / secs, "unit": "CTU/s", "h2d_bytes_per_step": int(h2d), "pcie_probe": probe,
+            "h2d_gbs_in_e2e": round(h2d / (secs / k) / 1e9, 1),
             "d2h_bytes_per_step": int(d2h), "steps": k, "ms_per_step": 1e3 * secs / k,
-            "host_threads": T,
+            "host_threads": T, "call_order": args.e2e_order,
             "api": "uvg_b200_rough_cost_host + uvg_b200_quantize_residual_host (pinned host buffers)"}
 
 
@@ -626,6 +650,8 @@ def main():
     ap.add_argument("--cpu-ctus", type=int, default=2040, help="CTUs of the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the *_host calls")
+    ap.add_argument("--e2e-order", default="interleaved", choices=["interleaved", "sequential"],
+                    help="order of the independent *_host calls inside a host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -283,6 +283,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
     // ---- quant, coefficients out, cost, dequant ------------------------------------------
     // N >= 16: one TU; N == 8: c0,c1 belong to TU A (rows g), c2,c3 to TU B (rows g+8)
     unsigned nzA = 0, nzB = 0, costA = 0, costB = 0;
+    const uint32_t wlo = a.w0 | (a.w1 << 16), whi = a.w2 | (a.w3 << 16);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -290,21 +291,21 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int cf = v[mt][nt][c];
-          const unsigned av = (unsigned)abs(cf);
-          int level = (int)((av * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits);
-          level = cf < 0 ? -level : level;
-          level = clip3(-32768, 32767, level);
+          // no int16 clip of the level: 8-bit video has q_bits >= 16 (checked by the launcher), so
+          // |level| <= (32768 * 26214 + add) >> 16 < 13200
+          const unsigned ulevel = ((unsigned)abs(cf) * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits;
+          const int level = cf < 0 ? -(int)ulevel : (int)ulevel;
           const int kv = nt * 8 + 2 * t + (c & 1);
-          const unsigned al = min((unsigned)abs(level), 3u);
-          const unsigned wgt = al == 0 ? a.w0 : al == 1 ? a.w1 : al == 2 ? a.w2 : a.w3;
+          // fast_coeff_cost weight of min(|level|, 3): one PRMT on the packed Q8.8 table, no branch
+          const unsigned wgt = __byte_perm(wlo, whi, min(ulevel, 3u) * 0x22u + 0x10u) & 0xffffu;
           if (N >= 16) {
             const int kh = mt * 16 + g + 8 * (c >> 1);
             a.coeff_out[tu0 * (size_t)(N * N) + kv * N + kh] = (int16_t)level;
-            nzA |= (unsigned)(level != 0); costA += wgt;
+            nzA |= ulevel; costA += wgt;
           } else {
             const size_t tuc = tu0 + (c >> 1);
             if (tuc < n_tus) a.coeff_out[tuc * (size_t)(N * N) + kv * N + g] = (int16_t)level;
-            if (c >> 1) { nzB |= (unsigned)(level != 0); costB += wgt; } else { nzA |= (unsigned)(level != 0); costA += wgt; }
+            if (c >> 1) { nzB |= ulevel; costB += wgt; } else { nzA |= ulevel; costA += wgt; }
           }
           v[mt][nt][c] = clip3(-32768, 32767, (level * q.dq_scale + q.dq_add) >> q.dq_shift);   // dequant
         }
@@ -667,7 +668,8 @@ static int launch_imma(const FusedArgs &a, size_t n_tus, const QParams &q, const
   const int warps_per_block = 4;
   const size_t n_units = (n_tus + ImmaShape<N>::TUS - 1) / ImmaShape<N>::TUS;
   size_t grid = (n_units + warps_per_block - 1) / warps_per_block;
-  const size_t cap = (size_t)sm_count() * 16;
+  static const int cap_mult = getenv("UVG266_B200_IMMA_CAP") ? atoi(getenv("UVG266_B200_IMMA_CAP")) : 16;
+  const size_t cap = (size_t)sm_count() * (size_t)(cap_mult > 0 ? cap_mult : 16);
   if (grid > cap) grid = cap;
   fused_imma_kernel<N><<<(unsigned)grid, warps_per_block * 32, 0, st>>>(a, n_tus, q, p);
   UVGB_LAUNCH_CHECK();
@@ -687,6 +689,7 @@ int launch_fused_imma(const FusedArgs &a, size_t n_tus, const QParams &q, int bi
 {
   if (bitdepth != 8 || q.w != q.h || (q.w != 8 && q.w != 16 && q.w != 32)) return -1;
   if (q.signhide || q.lfnst_idx || a.use_trskip) return -1;
+  if (q.q_bits < 16 || q.q_bits > 31) return -1;       // the kernels drop the level clip (see the quant step)
   if (!word_aligned(a.ref, q.w) || !word_aligned(a.pred, q.w) || !word_aligned(a.rec, q.w)) return -1;
   const int N = q.w, l2 = ilog2_host(N);
   ImmaParams p;
