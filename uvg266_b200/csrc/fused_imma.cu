@@ -153,7 +153,7 @@ static const uint32_t *cached_tables(int N, int th, int tv)
 }
 
 template <int N>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, N == 32 ? 4 : 1)
 fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 {
   using S = ImmaShape<N>;

@@ -144,16 +144,14 @@ fused_small_kernel(FusedArgs a, size_t n_tus, QParams q, SmallTr<N> tr)
   // quant (uvg_quant_generic level loop, no sign hiding on this path), coefficient cost
   int qc[N * N];
   unsigned nz = 0, cost = 0;
+  const uint32_t wlo = a.w0 | (a.w1 << 16), whi = a.w2 | (a.w3 << 16);
 #pragma unroll
   for (int i = 0; i < N * N; ++i) {
-    const unsigned av = (unsigned)abs(c[i]);
-    int level = (int)((av * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits);
-    level = c[i] < 0 ? -level : level;
-    level = clip3(-32768, 32767, level);
-    qc[i] = level;
-    nz |= (unsigned)(level != 0);
-    const unsigned al = min((unsigned)abs(level), 3u);
-    cost += al == 0 ? a.w0 : al == 1 ? a.w1 : al == 2 ? a.w2 : a.w3;
+    // no int16 clip of the level: the launcher admits q_bits >= 15 only, so |level| <= (32768 * 26214 + add) >> 15 < 32767
+    const unsigned ul = ((unsigned)abs(c[i]) * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits;
+    qc[i] = c[i] < 0 ? -(int)ul : (int)ul;
+    nz |= ul;
+    cost += __byte_perm(wlo, whi, min(ul, 3u) * 0x22u + 0x10u) & 0xffffu;   // weight of min(|level|, 3), packed Q8.8 table
   }
   // coefficients out: N*N int16 contiguous per TU
   {
@@ -248,6 +246,7 @@ int launch_fused_small(const FusedArgs &a, size_t n_tus, const QParams &q, int b
                        cudaStream_t st)
 {
   if (q.w != q.h || (q.w != 4 && q.w != 8) || q.signhide || q.lfnst_idx) return -1;
+  if (q.q_bits < 15 || q.q_bits > 31) return -1;           // the kernel drops the level clip (see the quant loop)
   if (bitdepth == 8) {
     return q.w == 4 ? launch_small<uint8_t, 4>(a, n_tus, q, bitdepth, th, tv, st)
                     : launch_small<uint8_t, 8>(a, n_tus, q, bitdepth, th, tv, st);

@@ -23,6 +23,7 @@
 // sum|c| <= 64 * ||D||_2 <= 130560 < 2^17, which is what lets SATD and SAD share one register
 // through the reduction.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace uvgb {
 
@@ -200,7 +201,8 @@ int launch_rough_mma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_i
   const size_t n_blocks = n_items / (size_t)k;
   if (n_blocks * (size_t)k != n_items || n_blocks >= (1ull << 31)) return -1;
   size_t grid = (n_blocks + 3) / 4;
-  const size_t cap = (size_t)sm_count() * 8;
+  static const int cap_mult = getenv("UVG266_B200_MMA_CAP") ? atoi(getenv("UVG266_B200_MMA_CAP")) : 24;
+  const size_t cap = (size_t)sm_count() * (size_t)(cap_mult > 0 ? cap_mult : 24);
   if (grid > cap) grid = cap;
   const uint8_t *cb = static_cast<const uint8_t *>(B.base);
   if (n == 8) rough_mma_kernel<8><<<(unsigned)grid, 128, 0, st>>>(A, cb, out, (uint32_t)n_blocks, k);
