@@ -210,6 +210,7 @@ fused_mma_kernel(FusedArgs a, size_t n_tus, QParams q, MmaParams p)
     // ---- quant, coefficients out, has_coeffs, cost, dequant --------------------------------
     unsigned nz = 0, cost = 0;
     int16_t *cout = a.coeff_out + tu * (size_t)(N * N);
+    const uint32_t wlo = a.w0 | (a.w1 << 16), whi = a.w2 | (a.w3 << 16);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -217,15 +218,13 @@ fused_mma_kernel(FusedArgs a, size_t n_tus, QParams q, MmaParams p)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int cf = v[mt][nt][c];
-          const unsigned av = (unsigned)abs(cf);
-          int level = (int)((av * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits);
-          level = cf < 0 ? -level : level;
-          level = clip3(-32768, 32767, level);
+          // no int16 clip of the level: the launcher admits q_bits >= 15 only (|level| <= 26214 + 1)
+          const unsigned ul = ((unsigned)abs(cf) * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits;
+          const int level = cf < 0 ? -(int)ul : (int)ul;
           const int kh = mt * 16 + g + 8 * (c >> 1), kv = nt * 8 + 2 * t + (c & 1);
           cout[kv * N + kh] = (int16_t)level;
-          nz |= (unsigned)(level != 0);
-          const unsigned al = min((unsigned)abs(level), 3u);
-          cost += al == 0 ? a.w0 : al == 1 ? a.w1 : al == 2 ? a.w2 : a.w3;
+          nz |= ul;
+          cost += __byte_perm(wlo, whi, min(ul, 3u) * 0x22u + 0x10u) & 0xffffu;   // fast_coeff_cost weight, packed Q8.8 table
           v[mt][nt][c] = clip3(-32768, 32767, (level * q.dq_scale + q.dq_add) >> q.dq_shift);   // dequant
         }
     const bool has = __any_sync(0xffffffffu, nz != 0);
@@ -358,6 +357,7 @@ int launch_fused_mma(const FusedArgs &a, size_t n_tus, const QParams &q, int bit
 {
   if (q.w != q.h || (q.w != 16 && q.w != 32) || q.signhide || q.lfnst_idx || a.use_trskip) return -1;
   if (bitdepth > 10) return -1;          // |residual| must stay below 2048 for exact f16 operands
+  if (q.q_bits < 15 || q.q_bits > 31) return -1;   // the kernel drops the level clip
   const int N = q.w, l2 = ilog2_host(N);
   MmaParams p;
   p.th = tr_matrix_dev(th, N); p.tv = tr_matrix_dev(tv, N);
