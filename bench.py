@@ -240,7 +240,7 @@ def reference_arm(args):
         "e2e": {"value": v, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -436,7 +436,7 @@ def gpu_arm(args):
             "clocks": clocks, "step_gbps": step_bytes * args.steps / (ms_max * 1e-3) / 1e9,
         }
         line.update(extra)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -656,9 +656,27 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly one JSON line: anything libraries write to fd 1 on the way (NCCL prints its version
+    # banner there) is routed to stderr until the line is printed
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return reference_arm(args)
     return gpu_arm(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
 
 
 if __name__ == "__main__":
