@@ -171,6 +171,25 @@ UVG_B200_API int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, i
                                                 uint64_t cost_weights, size_t n_tus,
                                                 void *stream);
 
+/* Joint Cb-Cr residual coding (quant_cbcr_residual, strategies-quant.h:62-80;
+ * uvg_quant_cbcr_residual_generic, quant-generic.c:241-442) for the plain chain (no LFNST / RDOQ /
+ * dep-quant), n_tus TUs per launch: the two chroma residuals are mixed into one
+ * ((4cb +- 2cr)/5, (cb +- cr)/2, (4cr +- 2cb)/5 by joint_cb_cr = 2, 3, 1 and jccr_sign; C division),
+ * transformed / quantised / dequantised / inverse transformed as plane V (joint_cb_cr == 1) or U,
+ * split back (:388-429) and both planes reconstructed; without coefficients (or early_skip) both
+ * reconstructions are the predictions. has_coeffs[i] = 0 / 1 (the strategy returns joint_cb_cr or 0). */
+UVG_B200_API int uvg_b200_quant_cbcr_residual_dev(const uvg_b200_quant_cfg *cfg, int cu_type,
+                                                  int tr_idx, int w, int h, int joint_cb_cr,
+                                                  int jccr_sign, int early_skip,
+                                                  const uvg_b200_blocks *u_ref,
+                                                  const uvg_b200_blocks *v_ref,
+                                                  const uvg_b200_blocks *u_pred,
+                                                  const uvg_b200_blocks *v_pred,
+                                                  const uvg_b200_blocks *u_rec,
+                                                  const uvg_b200_blocks *v_rec,
+                                                  int16_t *coeff_out, uint8_t *has_coeffs,
+                                                  size_t n_tus, void *stream);
+
 /* coeff_abs_sum / fast_coeff_cost over n_tus dense blocks of `len` coefficients. */
 UVG_B200_API int uvg_b200_coeff_abs_sum_dev(const int16_t *coeffs, size_t len, uint32_t *out,
                                             size_t n_tus, void *stream);
@@ -426,6 +445,22 @@ UVG_B200_API int uvg_b200_quantize_residual_16(const uvg_b200_quant_cfg *cfg, in
                                                const uint16_t *ref_in, const uint16_t *pred_in,
                                                uint16_t *rec_out, int16_t *coeff_out,
                                                int early_skip);
+/* quant_cbcr_residual (strategies-quant.h:62-80): cur_cu->joint_cb_cr and state->frame->jccr_sign
+ * travel as plain ints; returns joint_cb_cr when coefficients survive, else 0. */
+UVG_B200_API int uvg_b200_quant_cbcr_residual_8(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx,
+                                                int w, int h, int joint_cb_cr, int jccr_sign,
+                                                int in_stride, int out_stride,
+                                                const uint8_t *u_ref, const uint8_t *v_ref,
+                                                const uint8_t *u_pred, const uint8_t *v_pred,
+                                                uint8_t *u_rec, uint8_t *v_rec, int16_t *coeff_out,
+                                                int early_skip);
+UVG_B200_API int uvg_b200_quant_cbcr_residual_16(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx,
+                                                 int w, int h, int joint_cb_cr, int jccr_sign,
+                                                 int in_stride, int out_stride,
+                                                 const uint16_t *u_ref, const uint16_t *v_ref,
+                                                 const uint16_t *u_pred, const uint16_t *v_pred,
+                                                 uint16_t *u_rec, uint16_t *v_rec, int16_t *coeff_out,
+                                                 int early_skip);
 UVG_B200_API uint32_t uvg_b200_coeff_abs_sum(const int16_t *coeffs, size_t length);
 UVG_B200_API uint32_t uvg_b200_fast_coeff_cost(const int16_t *coeff, int32_t w, int32_t h,
                                                uint64_t weights);

@@ -185,6 +185,22 @@ int refh_quantize_residual(const char *strategy, int cu_type, int tr_idx, int lf
                 UVG_BOTH_T);
 }
 
+/* quant_cbcr_residual (JCCR) of the named strategy; returns joint_cb_cr / 0, or -1. */
+int refh_quant_cbcr_residual(const char *strategy, int cu_type, int tr_idx, int joint_cb_cr, int jccr_sign,
+                             int w, int h, int in_stride, int out_stride, const uvg_pixel *u_ref,
+                             const uvg_pixel *v_ref, const uvg_pixel *u_pred, const uvg_pixel *v_pred,
+                             uvg_pixel *u_rec, uvg_pixel *v_rec, int16_t *coeff_out, int early_skip)
+{
+  quant_cbcr_func *f = refh_get("quant_cbcr_residual", strategy);
+  if (!f) return -1;
+  cu_info_t cu;
+  fill_cu(&cu, cu_type, tr_idx, 0, 0, 0);
+  cu.joint_cb_cr = (uint8_t)joint_cb_cr;
+  g_state->frame->jccr_sign = jccr_sign != 0;
+  return (int)f(g_state, &cu, w, h, SCAN_DIAG, in_stride, out_stride, u_ref, v_ref, u_pred, v_pred, u_rec, v_rec,
+                coeff_out, early_skip != 0, 0, UVG_BOTH_T);
+}
+
 /* uvg_image_calc_sad on a small picture pair (frame-edge semantics, image.c:438). */
 unsigned refh_image_calc_sad(const uvg_pixel *pic_y, const uvg_pixel *ref_y, int pic_w,
                              int pic_h, int pic_x, int pic_y0, int ref_x, int ref_y0,

@@ -751,6 +751,69 @@ int orc_quantize_residual(const orc_quant_params *p, int cu_type, int tr_idx, in
   return has_coeffs;
 }
 
+/* uvg_quant_cbcr_residual_generic, quant-generic.c:241-442, plain path (no LFNST, quant = uvg_quant,
+ * no LMCS). cbf_mask = joint_cb_cr * (jccr_sign ? -1 : 1) (:273); the coded plane is V for joint_cb_cr == 1,
+ * else U (:311, :337). Both reconstructions are always written (:415-441). Returns joint_cb_cr or 0 (:444). */
+int orc_quant_cbcr_residual(const orc_quant_params *p, int cu_type, int tr_idx, int w, int h, int joint_cb_cr,
+                            int jccr_sign, int in_stride, int out_stride, const orc_pixel *u_ref,
+                            const orc_pixel *v_ref, const orc_pixel *u_pred, const orc_pixel *v_pred,
+                            orc_pixel *u_rec, orc_pixel *v_rec, int16_t *coeff_out, int early_skip)
+{
+  int16_t u_res[32 * 32], v_res[32 * 32], comb[32 * 32], coeff[32 * 32];
+  orc_generate_residual(u_ref, u_pred, u_res, w, h, in_stride, in_stride);
+  orc_generate_residual(v_ref, v_pred, v_res, w, h, in_stride, in_stride);
+  const int mask = joint_cb_cr * (jccr_sign ? -1 : 1);
+  for (int i = 0; i < w * h; ++i) {
+    const int cb = u_res[i], cr = v_res[i];
+    int v;
+    switch (mask) {                                   /* :275-309, C division truncates toward zero */
+      case 2: v = (4 * cb + 2 * cr) / 5; break;
+      case -2: v = (4 * cb - 2 * cr) / 5; break;
+      case 3: v = (cb + cr) / 2; break;
+      case -3: v = (cb - cr) / 2; break;
+      case 1: v = (4 * cr + 2 * cb) / 5; break;
+      default: v = (4 * cr - 2 * cb) / 5; break;
+    }
+    comb[i] = (int16_t)v;
+  }
+  const int color = joint_cb_cr == 1 ? 2 : 1;
+  if (p->mts || w != h) orc_mts_dct(p->bitdepth, color, cu_type, tr_idx, 0, 0, 0, w, h, comb, coeff, p->mts);
+  else orc_dct_nxn(w, p->bitdepth, comb, coeff);
+  orc_quant(p, coeff, coeff_out, w, h, color, cu_type, 0, 0);
+  int has_coeffs = 0;
+  for (int i = 0; i < w * h; ++i) if (coeff_out[i] != 0) { has_coeffs = 1; break; }
+  if (has_coeffs && !early_skip) {
+    orc_dequant(p, coeff_out, coeff, w, h, color, cu_type, 0);
+    if (p->mts || w != h) orc_mts_idct(p->bitdepth, color, cu_type, tr_idx, 0, 0, 0, w, h, coeff, comb, p->mts);
+    else orc_idct_nxn(w, p->bitdepth, coeff, comb);
+    for (int i = 0; i < w * h; ++i) {                 /* :388-414 */
+      const int c = comb[i];
+      switch (mask) {
+        case 2: u_res[i] = (int16_t)c; v_res[i] = (int16_t)(c >> 1); break;
+        case -2: u_res[i] = (int16_t)c; v_res[i] = (int16_t)(-c >> 1); break;
+        case 3: u_res[i] = (int16_t)c; v_res[i] = (int16_t)c; break;
+        case -3: u_res[i] = (int16_t)c; v_res[i] = (int16_t)(-c); break;
+        case 1: u_res[i] = (int16_t)(c >> 1); v_res[i] = (int16_t)c; break;
+        default: u_res[i] = (int16_t)(-c >> 1); v_res[i] = (int16_t)c; break;
+      }
+    }
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        const int16_t uv = (int16_t)(u_res[x + y * w] + u_pred[x + y * in_stride]);
+        const int16_t vv = (int16_t)(v_res[x + y * w] + v_pred[x + y * in_stride]);
+        u_rec[x + y * out_stride] = (orc_pixel)clip3(0, PIXEL_MAX, uv);
+        v_rec[x + y * out_stride] = (orc_pixel)clip3(0, PIXEL_MAX, vv);
+      }
+  } else {
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        u_rec[x + y * out_stride] = u_pred[x + y * in_stride];
+        v_rec[x + y * out_stride] = v_pred[x + y * in_stride];
+      }
+  }
+  return has_coeffs ? joint_cb_cr : 0;
+}
+
 /* coeff_abs_sum_generic :671-678 */
 uint32_t orc_coeff_abs_sum(const int16_t *coeffs, size_t length)
 {

@@ -109,6 +109,10 @@ int orc_quantize_residual(const orc_quant_params *p, int cu_type, int tr_idx, in
                           int color, int use_trskip, int in_stride, int out_stride,
                           const orc_pixel *ref_in, const orc_pixel *pred_in,
                           orc_pixel *rec_out, int16_t *coeff_out, int early_skip);
+int orc_quant_cbcr_residual(const orc_quant_params *p, int cu_type, int tr_idx, int w, int h, int joint_cb_cr,
+                            int jccr_sign, int in_stride, int out_stride, const orc_pixel *u_ref,
+                            const orc_pixel *v_ref, const orc_pixel *u_pred, const orc_pixel *v_pred,
+                            orc_pixel *u_rec, orc_pixel *v_rec, int16_t *coeff_out, int early_skip);
 uint32_t orc_coeff_abs_sum(const int16_t *coeffs, size_t length);
 uint32_t orc_fast_coeff_cost(const int16_t *coeff, int w, int h, uint64_t weights);
 

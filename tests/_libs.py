@@ -71,6 +71,8 @@ def load_oracle(bd=8):
     L.orc_dequant.argtypes = [vp, vp, vp, i, i, i, i, i]
     L.orc_quantize_residual.argtypes = [vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, i]
     L.orc_quantize_residual.restype = i
+    L.orc_quant_cbcr_residual.argtypes = [vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, i]
+    L.orc_quant_cbcr_residual.restype = i
     L.orc_coeff_abs_sum.argtypes = [vp, C.c_size_t]; L.orc_coeff_abs_sum.restype = C.c_uint32
     L.orc_fast_coeff_cost.argtypes = [vp, i, i, C.c_uint64]; L.orc_fast_coeff_cost.restype = C.c_uint32
     _oracles[bd] = L
@@ -103,6 +105,8 @@ class Ref:
         H.refh_quant.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p] + [C.c_int] * 7
         H.refh_dequant.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5
         H.refh_quantize_residual.argtypes = [C.c_char_p] + [C.c_int] * 9 + [C.c_void_p] * 4 + [C.c_int]
+        H.refh_quant_cbcr_residual.argtypes = [C.c_char_p] + [C.c_int] * 8 + [C.c_void_p] * 7 + [C.c_int]
+        H.refh_quant_cbcr_residual.restype = C.c_int
         H.refh_ctu_pass.restype = C.c_double
         H.refh_pair_batch.restype = C.c_double
         self.opts = None

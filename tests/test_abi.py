@@ -34,6 +34,7 @@ def test_every_reference_strategy_type_has_a_dropin():
     for t in dct + quant:
         assert hasattr(L, "uvg_b200_" + t), t
     assert hasattr(L, "uvg_b200_quantize_residual_8") and hasattr(L, "uvg_b200_quantize_residual_16")
+    assert hasattr(L, "uvg_b200_quant_cbcr_residual_8") and hasattr(L, "uvg_b200_quant_cbcr_residual_16")   # 6 of 6 quant types
 
 
 def test_only_uvg_prefixed_symbols_are_exported():

@@ -65,7 +65,10 @@ CASES = [
     ("intra_ibc", 8, 64, 64, 1, ["--preset=ultrafast", "-p", "1", "--ibc=1"]),           # crc32c_4x4 / 8x8 hashes
     ("intra_medium_rdoq", 8, 64, 64, 1, ["--preset=medium", "-p", "1"]),
     ("intra_ultrafast_10bit", 10, 128, 64, 2, ["--preset=ultrafast", "-p", "1"]),
-    # JCCR: the reference's quant_cbcr_residual (not overridden) runs on the cuda transform / quant / dequant leaves
+    # JCCR: quant_cbcr_residual as one fused cuda kernel (plain chain) ...
+    ("intra_jccr", 8, 128, 64, 2, ["--preset=ultrafast", "-p", "1", "--rd=2", "--jccr"]),
+    ("intra_jccr_10bit_signhide", 10, 64, 64, 1, ["--preset=ultrafast", "-p", "1", "--rd=2", "--jccr", "--signhide"]),
+    # ... and forwarded to the reference's composite (which runs on the cuda leaves) when LFNST is in play
     ("intra_jccr_lfnst_mts", 8, 128, 64, 2, ["--preset=ultrafast", "-p", "1", "--rd=2", "--jccr", "--lfnst", "--mts=intra"]),
     # the tool set of BASELINE config 4 (10-bit, MTS + LFNST)
     ("intra_mts_lfnst_10bit", 10, 128, 64, 2, ["--preset=ultrafast", "-p", "1", "--rd=2", "--mts=intra", "--lfnst"]),

@@ -282,6 +282,79 @@ def test_dropin_quantize_residual(bd, mts_val):
     assert n_cases >= 256
 
 
+@pytest.mark.parametrize("bd", BDS)
+def test_quant_cbcr_residual_dropin_and_batched(bd):
+    """JCCR (quant_cbcr_residual, quant-generic.c:241-442): the drop-in on strided planes and the batched
+    device entry point on dense TUs, all six joint modes, against the oracle."""
+    import torch
+    O = load_oracle(bd)
+    L = U.lib()
+    rng = np.random.default_rng(1450 + bd)
+    qptr, qlist = chroma_map(bd)
+    f = getattr(L, "uvg_b200_quant_cbcr_residual_%s" % U.suffix(bd))
+    hi = 1 << bd
+    dt = pix_dtype(bd)
+    n_cases = 0
+    for (w, h) in ((4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 16), (16, 8)):
+        for qp in (17, 32):
+            for joint in (1, 2, 3):
+                for sign in (0, 1):
+                    sh = n_cases & 1
+                    early = (n_cases >> 1) & 1 if qp == 32 else 0
+                    p = OrcQuantParams(qp, bd, 1, sh, 0, qptr)
+                    cfg = U.QuantCfg.make(qp, bd, 1, sh, 0, qlist)
+                    stride = 32
+                    noise = int(rng.choice([2, 12, 60, hi]))
+                    pl = []
+                    for _ in range(2):
+                        ref = rng.integers(0, hi, stride * h).astype(dt)
+                        pl.append((ref, np.clip(ref.astype(int) + rng.integers(-noise, noise + 1, stride * h), 0, hi - 1).astype(dt)))
+                    (ur, up), (vr, vq) = pl
+                    rec = [np.full(stride * h, 7, dt) for _ in range(4)]
+                    co1 = np.zeros(w * h, np.int16); co2 = np.zeros(w * h, np.int16)
+                    r1 = f(C.byref(cfg), 1, 0, w, h, joint, sign, stride, stride, ptr(ur), ptr(vr), ptr(up), ptr(vq),
+                           ptr(rec[0]), ptr(rec[1]), ptr(co1), early)
+                    r2 = O.orc_quant_cbcr_residual(C.byref(p), 1, 0, w, h, joint, sign, stride, stride, ptr(ur), ptr(vr),
+                                                   ptr(up), ptr(vq), ptr(rec[2]), ptr(rec[3]), ptr(co2), early)
+                    assert r1 == r2, (w, h, qp, joint, sign, early)
+                    assert (co1 == co2).all(), (w, h, qp, joint, sign)
+                    assert (rec[0] == rec[2]).all() and (rec[1] == rec[3]).all(), (w, h, qp, joint, sign, early)
+                    n_cases += 1
+    # batched: 300 dense 8x8 TUs per mode, one launch each
+    dev = torch.device("cuda", 0)
+    n, nt = 8, 300
+    cfg = U.QuantCfg.make(27, bd, 1, 0, 0, qlist)
+    p = OrcQuantParams(27, bd, 1, 0, 0, qptr)
+    tdt = torch.uint8 if bd == 8 else torch.int16
+    for joint in (1, 2, 3):
+        for sign in (0, 1):
+            host = []
+            for _ in range(2):
+                ref = rng.integers(0, hi, nt * n * n).astype(dt)
+                pred = np.clip(ref.astype(int) + rng.integers(-20, 21, ref.size), 0, hi - 1).astype(dt)
+                pred[: 3 * n * n] = ref[: 3 * n * n]
+                host += [ref, pred]
+            ur, up, vr, vq = host
+            d = [torch.from_numpy(a.view(np.int16) if bd != 8 else a).to(dev) for a in (ur, vr, up, vq)]
+            urec = torch.zeros(nt * n * n, dtype=tdt, device=dev); vrec = torch.zeros_like(urec)
+            coeff = torch.zeros(nt * n * n, dtype=torch.int16, device=dev)
+            has = torch.zeros(nt, dtype=torch.uint8, device=dev)
+            B = [U.Blocks.dense(t.data_ptr(), n, n) for t in d + [urec, vrec]]
+            U.check(L.uvg_b200_quant_cbcr_residual_dev(C.byref(cfg), 1, 0, n, n, joint, sign, 0, *[C.byref(b) for b in B],
+                                                       coeff.data_ptr(), has.data_ptr(), nt, 0))
+            torch.cuda.synchronize()
+            g_u, g_v = urec.cpu().numpy().view(dt), vrec.cpu().numpy().view(dt)
+            g_c, g_h = coeff.cpu().numpy(), has.cpu().numpy()
+            for i in range(nt):
+                sl = slice(i * n * n, (i + 1) * n * n)
+                ru = np.zeros(n * n, dt); rv = np.zeros(n * n, dt); co = np.zeros(n * n, np.int16)
+                r = O.orc_quant_cbcr_residual(C.byref(p), 1, 0, n, n, joint, sign, n, n, ptr(ur[sl].copy()), ptr(vr[sl].copy()),
+                                              ptr(up[sl].copy()), ptr(vq[sl].copy()), ptr(ru), ptr(rv), ptr(co), 0)
+                assert (1 if r else 0) == int(g_h[i]), (joint, sign, i)
+                assert (co == g_c[sl]).all() and (ru == g_u[sl]).all() and (rv == g_v[sl]).all(), (joint, sign, i)
+    assert n_cases >= 80
+
+
 def test_dropin_coeff_costs():
     O = load_oracle(8)
     L = U.lib()

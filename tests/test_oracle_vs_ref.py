@@ -269,6 +269,44 @@ def test_quantize_residual(bd, mts):
     assert n_cases >= 128
 
 
+@pytest.mark.parametrize("bd", BDS)
+@pytest.mark.parametrize("signhide", [0, 1])
+def test_quant_cbcr_residual(bd, signhide):
+    """JCCR (quant-generic.c:241-442): all six joint modes, square and non-square chroma TUs, early skip."""
+    O = load_oracle(bd)
+    R = load_ref(bd, "preset=ultrafast,signhide=%d,rdoq=0,jccr=1" % signhide)
+    rng = np.random.default_rng(900 + bd + signhide)
+    qmap = R.H.refh_chroma_qp_map()
+    n_cases = 0
+    for (w, h) in ((4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 16), (16, 8)):
+        for qp in (17, 27, 37):
+            for joint in (1, 2, 3):
+                for sign in (0, 1):
+                    for early in (0, 1):
+                        R.H.refh_set_state(qp, 1)
+                        p = OrcQuantParams(qp, bd, 1, signhide, 0, qmap)
+                        stride = 32
+                        hi = 1 << bd
+                        noise = int(rng.choice([2, 12, 60, hi]))
+                        planes = []
+                        for _ in range(2):
+                            ref = rng.integers(0, hi, stride * h).astype(pix_dtype(bd))
+                            pred = np.clip(ref.astype(int) + rng.integers(-noise, noise + 1, stride * h), 0, hi - 1).astype(pix_dtype(bd))
+                            planes.append((ref, pred))
+                        (ur, up), (vr, vp_) = planes
+                        rec = [np.full(stride * h, 7, pix_dtype(bd)) for _ in range(4)]
+                        co1 = np.zeros(w * h, np.int16); co2 = np.zeros(w * h, np.int16)
+                        r1 = O.orc_quant_cbcr_residual(C.byref(p), 1, 0, w, h, joint, sign, stride, stride, ptr(ur), ptr(vr),
+                                                       ptr(up), ptr(vp_), ptr(rec[0]), ptr(rec[1]), ptr(co1), early)
+                        r2 = R.H.refh_quant_cbcr_residual(b"generic", 1, 0, joint, sign, w, h, stride, stride, ptr(ur), ptr(vr),
+                                                          ptr(up), ptr(vp_), ptr(rec[2]), ptr(rec[3]), ptr(co2), early)
+                        assert r1 == r2, (w, h, qp, joint, sign, early)
+                        assert (co1 == co2).all(), (w, h, qp, joint, sign)
+                        assert (rec[0] == rec[2]).all() and (rec[1] == rec[3]).all(), (w, h, qp, joint, sign, early)
+                        n_cases += 1
+    assert n_cases >= 250
+
+
 def test_coeff_costs():
     O, R = load_oracle(8), load_ref(8)
     rng = np.random.default_rng(800)

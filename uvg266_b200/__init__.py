@@ -92,6 +92,7 @@ def lib():
     L.uvg_b200_dequant_dev.argtypes = [QP, vp, vp, i, i, i, i, sz, vp]
     L.uvg_b200_quantize_residual_dev.argtypes = [QP, i, i, i, i, i, i, i, BP, BP, BP, vp, vp, vp, vp,
                                                  C.c_uint64, sz, vp]
+    L.uvg_b200_quant_cbcr_residual_dev.argtypes = [QP, i, i, i, i, i, i, i, BP, BP, BP, BP, BP, BP, vp, vp, sz, vp]
     L.uvg_b200_coeff_abs_sum_dev.argtypes = [vp, sz, vp, sz, vp]
     L.uvg_b200_fast_coeff_cost_dev.argtypes = [vp, i, i, C.c_uint64, vp, sz, vp]
     L.uvg_b200_distortion_host.argtypes = [i, i, i, i, BP, sz, BP, sz, vp, sz, i]
@@ -136,6 +137,8 @@ def lib():
         f = getattr(L, "uvg_b200_pdpc_planar_dc_" + suf); f.argtypes = [i, i, i, vp, vp, vp]; f.restype = None
         f = getattr(L, "uvg_b200_quantize_residual_" + suf)
         f.argtypes = [QP, i, i, i, i, i, i, i, i, vp, vp, vp, vp, i]; f.restype = i
+        f = getattr(L, "uvg_b200_quant_cbcr_residual_" + suf)
+        f.argtypes = [QP, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, i]; f.restype = i
     for n in (4, 8, 16, 32):
         for m in ("dct", "idct"):
             f = getattr(L, "uvg_b200_%s_%dx%d" % (m, n, n)); f.argtypes = [C.c_int8, vp, vp]; f.restype = None

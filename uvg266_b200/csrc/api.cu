@@ -293,6 +293,44 @@ static int dropin_quantize_residual(const uvg_b200_quant_cfg *cfg, int cu_type, 
   return has;
 }
 
+// uvg_quant_cbcr_residual_generic (quant-generic.c:241-442), plain chain. Returns joint_cb_cr when
+// coefficients survive, else 0 (:444).
+template <typename Pix>
+static int dropin_quant_cbcr_residual(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx, int w, int h,
+                                      int joint_cb_cr, int jccr_sign, int in_stride, int out_stride,
+                                      const Pix *u_ref, const Pix *v_ref, const Pix *u_pred, const Pix *v_pred,
+                                      Pix *u_rec, Pix *v_rec, int16_t *coeff_out, int early_skip)
+{
+  if (ensure_init()) { fprintf(stderr, "uvg266_b200: %s\n", t_err); abort(); }
+  Staging &s = tls_staging();
+  const size_t blk = align_up((size_t)w * h * sizeof(Pix), 16);
+  const size_t cbytes = align_up((size_t)w * h * sizeof(int16_t), 16);
+  // device: [u_ref | v_ref | u_pred | v_pred | u_rec | v_rec | coeff | has(16)]
+  const size_t total = 6 * blk + cbytes + 16;
+  if (s.ensure(total, total)) { fprintf(stderr, "uvg266_b200: %s\n", t_err); abort(); }
+  const Pix *in[4] = { u_ref, v_ref, u_pred, v_pred };
+  for (int i = 0; i < 4; ++i) pack_rows(reinterpret_cast<Pix *>(s.h_pin + i * blk), in[i], w, h, (size_t)in_stride);
+  UVGB_MUST(cudaMemcpyAsync(s.d_buf, s.h_pin, 4 * blk, cudaMemcpyHostToDevice, s.stream));
+  uvg_b200_blocks B[6];
+  for (int i = 0; i < 6; ++i) B[i] = dense_blocks(s.d_buf + i * blk, w, h);
+  int16_t *d_coeff = reinterpret_cast<int16_t *>(s.d_buf + 6 * blk);
+  uint8_t *d_has = s.d_buf + 6 * blk + cbytes;
+  if (uvg_b200_quant_cbcr_residual_dev(cfg, cu_type, tr_idx, w, h, joint_cb_cr, jccr_sign, early_skip, &B[0], &B[1],
+                                       &B[2], &B[3], &B[4], &B[5], d_coeff, d_has, 1, s.stream)) {
+    fprintf(stderr, "uvg266_b200: %s\n", t_err); abort();
+  }
+  UVGB_MUST(cudaMemcpyAsync(s.h_pin + 4 * blk, s.d_buf + 4 * blk, 2 * blk + cbytes + 16, cudaMemcpyDeviceToHost, s.stream));
+  UVGB_MUST(cudaStreamSynchronize(s.stream));
+  const int has = s.h_pin[6 * blk + cbytes];
+  memcpy(coeff_out, s.h_pin + 6 * blk, (size_t)w * h * sizeof(int16_t));
+  const Pix *su = reinterpret_cast<const Pix *>(s.h_pin + 4 * blk), *sv = reinterpret_cast<const Pix *>(s.h_pin + 5 * blk);
+  for (int y = 0; y < h; ++y) {                     // both planes are always written (:415-441)
+    memcpy(u_rec + (size_t)y * out_stride, su + (size_t)y * w, (size_t)w * sizeof(Pix));
+    memcpy(v_rec + (size_t)y * out_stride, sv + (size_t)y * w, (size_t)w * sizeof(Pix));
+  }
+  return has ? joint_cb_cr : 0;
+}
+
 }  // namespace uvgb
 
 using namespace uvgb;
@@ -599,6 +637,20 @@ extern "C" int uvg_b200_quantize_residual_16(const uvg_b200_quant_cfg *cfg, int 
                                              const uint16_t *ref_in, const uint16_t *pred_in, uint16_t *rec_out,
                                              int16_t *coeff_out, int early_skip)
 { return dropin_quantize_residual<uint16_t>(cfg, cu_type, tr_idx, w, h, color, use_trskip, in_stride, out_stride, ref_in, pred_in, rec_out, coeff_out, early_skip); }
+
+extern "C" int uvg_b200_quant_cbcr_residual_8(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx, int w, int h,
+                                              int joint_cb_cr, int jccr_sign, int in_stride, int out_stride,
+                                              const uint8_t *u_ref, const uint8_t *v_ref, const uint8_t *u_pred,
+                                              const uint8_t *v_pred, uint8_t *u_rec, uint8_t *v_rec,
+                                              int16_t *coeff_out, int early_skip)
+{ return dropin_quant_cbcr_residual<uint8_t>(cfg, cu_type, tr_idx, w, h, joint_cb_cr, jccr_sign, in_stride, out_stride, u_ref, v_ref, u_pred, v_pred, u_rec, v_rec, coeff_out, early_skip); }
+
+extern "C" int uvg_b200_quant_cbcr_residual_16(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx, int w, int h,
+                                               int joint_cb_cr, int jccr_sign, int in_stride, int out_stride,
+                                               const uint16_t *u_ref, const uint16_t *v_ref, const uint16_t *u_pred,
+                                               const uint16_t *v_pred, uint16_t *u_rec, uint16_t *v_rec,
+                                               int16_t *coeff_out, int early_skip)
+{ return dropin_quant_cbcr_residual<uint16_t>(cfg, cu_type, tr_idx, w, h, joint_cb_cr, jccr_sign, in_stride, out_stride, u_ref, v_ref, u_pred, v_pred, u_rec, v_rec, coeff_out, early_skip); }
 
 static uint32_t dropin_coeff_sum(const int16_t *coeffs, size_t len, int mode, int w, int h, uint64_t weights)
 {

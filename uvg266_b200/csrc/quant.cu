@@ -377,10 +377,29 @@ quantize_residual_kernel(FusedArgs a, size_t n_tus, QParams q, TrPlan fp, TrPlan
     __syncthreads();
     if (tid < 3) s_red[slot * 3 + tid] = 0;
     // 1. residual (generate_residual :480)
+    const Pix *pref2 = nullptr, *ppred2 = nullptr; Pix *prec2 = nullptr;
+    if (active && a.jccr) {
+      pref2 = static_cast<const Pix *>(a.ref2.base) + a.ref2.offset(tu);
+      ppred2 = static_cast<const Pix *>(a.pred2.base) + a.pred2.offset(tu);
+      prec2 = const_cast<Pix *>(static_cast<const Pix *>(a.rec2.base)) + a.rec2.offset(tu);
+    }
     if (active)
       for (int t = tid; t < area; t += tps) {
         const int y = t / w, x = t - y * w;
-        bufA[t] = (int16_t)((int)pref[(size_t)y * a.ref.stride + x] - (int)ppred[(size_t)y * a.pred.stride + x]);
+        const int cb = (int)pref[(size_t)y * a.ref.stride + x] - (int)ppred[(size_t)y * a.pred.stride + x];
+        if (!a.jccr) { bufA[t] = (int16_t)cb; continue; }
+        // joint residual, quant-generic.c:275-309 (C division: truncation toward zero)
+        const int cr = (int)pref2[(size_t)y * a.ref2.stride + x] - (int)ppred2[(size_t)y * a.pred2.stride + x];
+        int v;
+        switch (a.jccr) {
+          case 2: v = (4 * cb + 2 * cr) / 5; break;
+          case -2: v = (4 * cb - 2 * cr) / 5; break;
+          case 3: v = (cb + cr) / 2; break;
+          case -3: v = (cb - cr) / 2; break;
+          case 1: v = (4 * cr + 2 * cb) / 5; break;
+          default: v = (4 * cr - 2 * cb) / 5; break;      // -1
+        }
+        bufA[t] = (int16_t)v;
       }
     __syncthreads();
     // 2. forward transform (:495-501) -> coefficients in bufA
@@ -425,7 +444,31 @@ quantize_residual_kernel(FusedArgs a, size_t n_tus, QParams q, TrPlan fp, TrPlan
       }
     }
     // 6. reconstruction (:591-611) + SSD against the source
-    if (active) {
+    if (active && a.jccr) {
+      // split the joint residual back (quant-generic.c:388-429), both planes; without coefficients both
+      // reconstructions are copies of the predictions (:431-441)
+      for (int t = tid; t < area; t += tps) {
+        const int y = t / w, x = t - y * w;
+        const int pu = (int)ppred[(size_t)y * a.pred.stride + x], pv2 = (int)ppred2[(size_t)y * a.pred2.stride + x];
+        int ru = pu, rv2 = pv2;
+        if (recon) {
+          const int c = bufA[t];
+          int16_t ur, vr;
+          switch (a.jccr) {
+            case 2: ur = (int16_t)c; vr = (int16_t)(c >> 1); break;
+            case -2: ur = (int16_t)c; vr = (int16_t)(-c >> 1); break;
+            case 3: ur = (int16_t)c; vr = (int16_t)c; break;
+            case -3: ur = (int16_t)c; vr = (int16_t)(-c); break;
+            case 1: ur = (int16_t)(c >> 1); vr = (int16_t)c; break;
+            default: ur = (int16_t)(-c >> 1); vr = (int16_t)c; break;   // -1
+          }
+          ru = clip3(0, q.pixel_max, (int)(int16_t)(ur + pu));
+          rv2 = clip3(0, q.pixel_max, (int)(int16_t)(vr + pv2));
+        }
+        prec[(size_t)y * a.rec.stride + x] = (Pix)ru;
+        prec2[(size_t)y * a.rec2.stride + x] = (Pix)rv2;
+      }
+    } else if (active) {
       unsigned ssd = 0;
       for (int t = tid; t < area; t += tps) {
         const int y = t / w, x = t - y * w;
@@ -536,16 +579,15 @@ extern "C" int uvg_b200_dequant_dev(const uvg_b200_quant_cfg *cfg, const int16_t
   return 0;
 }
 
-extern "C" int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx,
-                                              int w, int h, int color, int use_trskip, int early_skip,
-                                              const uvg_b200_blocks *ref, const uvg_b200_blocks *pred,
-                                              const uvg_b200_blocks *rec, int16_t *coeff_out,
-                                              uint8_t *has_coeffs, uint32_t *ssd, uint32_t *cost,
-                                              uint64_t cost_weights, size_t n_tus, void *stream)
+// Shared by quantize_residual and quant_cbcr_residual: plans, parameters, kernel choice.
+// cr_* == nullptr: single plane. Otherwise the joint Cb-Cr mode of the general kernel (jccr != 0).
+static int run_quantize_residual(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx, int w, int h, int color,
+                                 int use_trskip, int early_skip, const uvg_b200_blocks *ref,
+                                 const uvg_b200_blocks *pred, const uvg_b200_blocks *rec,
+                                 const uvg_b200_blocks *cr_ref, const uvg_b200_blocks *cr_pred,
+                                 const uvg_b200_blocks *cr_rec, int jccr, int16_t *coeff_out, uint8_t *has_coeffs,
+                                 uint32_t *ssd, uint32_t *cost, uint64_t cost_weights, size_t n_tus, void *stream)
 {
-  if (ensure_init()) return 1;
-  if (n_tus == 0) return 0;
-  if (!cfg || !ref || !pred || !rec || !coeff_out || !has_coeffs) { set_error("quantize_residual: NULL argument"); return 1; }
   QParams q;
   // quant is called with transform_skip = (tr_idx == MTS_SKIP && luma), quant-generic.c:538
   const int ts_flag = (tr_idx == 1 && color == 0) ? 1 : 0;
@@ -568,9 +610,12 @@ extern "C" int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, int
   a.rec_is_pred = (rec->base == pred->base && rec->stride == pred->stride &&
                    rec->col_pitch == pred->col_pitch && rec->row_pitch == pred->row_pitch &&
                    rec->blocks_per_row == pred->blocks_per_row);
+  a.jccr = jccr;
+  if (jccr) { a.ref2 = to_blocks(cr_ref); a.pred2 = to_blocks(cr_pred); a.rec2 = to_blocks(cr_rec); }
+  else { a.ref2 = a.ref; a.pred2 = a.pred; a.rec2 = a.rec; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // shape-specialised kernels first: registers-only for 4x4/8x8, tensor cores for 16x16/32x32
-  {
+  if (!jccr) {
     // UVG266_B200_FUSED = imma | small | hmma | generic restricts the choice (A/B measurements)
     static const char *force = getenv("UVG266_B200_FUSED");
     int rc = -1;
@@ -591,6 +636,42 @@ extern "C" int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, int
   else quantize_residual_kernel<uint16_t><<<(unsigned)grid, 256, smem, st>>>(a, n_tus, q, fp, ip, slots);
   UVGB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int uvg_b200_quantize_residual_dev(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx,
+                                              int w, int h, int color, int use_trskip, int early_skip,
+                                              const uvg_b200_blocks *ref, const uvg_b200_blocks *pred,
+                                              const uvg_b200_blocks *rec, int16_t *coeff_out,
+                                              uint8_t *has_coeffs, uint32_t *ssd, uint32_t *cost,
+                                              uint64_t cost_weights, size_t n_tus, void *stream)
+{
+  if (ensure_init()) return 1;
+  if (n_tus == 0) return 0;
+  if (!cfg || !ref || !pred || !rec || !coeff_out || !has_coeffs) { set_error("quantize_residual: NULL argument"); return 1; }
+  return run_quantize_residual(cfg, cu_type, tr_idx, w, h, color, use_trskip, early_skip, ref, pred, rec, nullptr,
+                               nullptr, nullptr, 0, coeff_out, has_coeffs, ssd, cost, cost_weights, n_tus, stream);
+}
+
+// uvg_quant_cbcr_residual_generic (quant-generic.c:241-442) for the plain chain (no LFNST / RDOQ / dep-quant):
+// joint residual of the two chroma planes -> transform -> quant -> has_coeffs -> dequant -> inverse transform ->
+// split -> both reconstructions. The coded plane is V when joint_cb_cr == 1, else U (:311, :337).
+extern "C" int uvg_b200_quant_cbcr_residual_dev(const uvg_b200_quant_cfg *cfg, int cu_type, int tr_idx, int w, int h,
+                                                int joint_cb_cr, int jccr_sign, int early_skip,
+                                                const uvg_b200_blocks *u_ref, const uvg_b200_blocks *v_ref,
+                                                const uvg_b200_blocks *u_pred, const uvg_b200_blocks *v_pred,
+                                                const uvg_b200_blocks *u_rec, const uvg_b200_blocks *v_rec,
+                                                int16_t *coeff_out, uint8_t *has_coeffs, size_t n_tus, void *stream)
+{
+  if (ensure_init()) return 1;
+  if (n_tus == 0) return 0;
+  if (!cfg || !u_ref || !v_ref || !u_pred || !v_pred || !u_rec || !v_rec || !coeff_out || !has_coeffs) {
+    set_error("quant_cbcr_residual: NULL argument"); return 1;
+  }
+  if (joint_cb_cr < 1 || joint_cb_cr > 3) { set_error("quant_cbcr_residual: joint_cb_cr = %d", joint_cb_cr); return 1; }
+  const int color = joint_cb_cr == 1 ? 2 : 1;                 // COLOR_V : COLOR_U
+  return run_quantize_residual(cfg, cu_type, tr_idx, w, h, color, 0, early_skip, u_ref, u_pred, u_rec, v_ref, v_pred,
+                               v_rec, joint_cb_cr * (jccr_sign ? -1 : 1), coeff_out, has_coeffs, nullptr, nullptr, 0,
+                               n_tus, stream);
 }
 
 extern "C" int uvg_b200_coeff_abs_sum_dev(const int16_t *coeffs, size_t len, uint32_t *out, size_t n_tus,

@@ -25,6 +25,10 @@ struct FusedArgs {
   uint32_t *cost;
   unsigned w0, w1, w2, w3;   // fast_coeff_cost weights (Q8.8), rdo.c:440
   int use_trskip, early_skip, rec_is_pred;
+  // joint Cb-Cr mode (uvg_quant_cbcr_residual_generic, quant-generic.c:241-442), general kernel only:
+  // ref/pred/rec = the Cb plane, ref2/pred2/rec2 = the Cr plane, jccr = joint_cb_cr * (jccr_sign ? -1 : 1)
+  Blocks ref2, pred2, rec2;
+  int jccr;
 };
 
 

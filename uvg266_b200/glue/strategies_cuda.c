@@ -429,13 +429,54 @@ int uvg_strategy_register_ipol_cuda(void *opaque, uint8_t bitdepth)
   return ok;
 }
 
+/* quant_cbcr_residual (JCCR, strategies-quant.h:62-80): the plain chain is one fused kernel over both chroma
+ * planes. With LFNST, RDOQ or dep-quant in play (tools of the encoder proper) the call is
+ * forwarded to the implementation the reference registered for this type - its composite then runs transform /
+ * quant / dequant through the strategy table, i.e. on the cuda leaves. */
+static quant_cbcr_func *ref_quant_cbcr_residual;
+
+static unsigned quant_cbcr_residual_cuda(encoder_state_t *const state, const cu_info_t *const cur_cu, const int width,
+                                         const int height, const coeff_scan_order_t scan_order, const int in_stride,
+                                         const int out_stride, const uvg_pixel *const u_ref_in,
+                                         const uvg_pixel *const v_ref_in, const uvg_pixel *const u_pred_in,
+                                         const uvg_pixel *const v_pred_in, uvg_pixel *u_rec_out, uvg_pixel *v_rec_out,
+                                         coeff_t *coeff_out, bool early_skip, int lmcs_chroma_adj,
+                                         enum uvg_tree_type tree_type)
+{
+  const encoder_control_t *const enc = state->encoder_control;
+  const uint8_t lfnst_idx = tree_type == UVG_CHROMA_T ? cur_cu->cr_lfnst_idx : cur_cu->lfnst_idx;
+  const bool rdoq = enc->cfg.rdoq_enable && (width > 4 || !enc->cfg.rdoq_skip);
+  if (lfnst_idx || rdoq || enc->cfg.dep_quant) {
+    if (!ref_quant_cbcr_residual) unsupported("quant_cbcr_residual with LFNST / RDOQ / dep-quant");
+    return ref_quant_cbcr_residual(state, cur_cu, width, height, scan_order, in_stride, out_stride, u_ref_in, v_ref_in,
+                                   u_pred_in, v_pred_in, u_rec_out, v_rec_out, coeff_out, early_skip, lmcs_chroma_adj,
+                                   tree_type);
+  }
+  uvg_b200_quant_cfg c;
+  fill_cfg(state, &c);
+  return (unsigned)B200(quant_cbcr_residual)(&c, cur_cu->type, cur_cu->tr_idx, width, height, cur_cu->joint_cb_cr,
+                                             state->frame->jccr_sign ? 1 : 0, in_stride, out_stride, u_ref_in, v_ref_in,
+                                             u_pred_in, v_pred_in, u_rec_out, v_rec_out, coeff_out, early_skip);
+}
+
 int uvg_strategy_register_quant_cuda(void *opaque, uint8_t bitdepth)
 {
   if (!device_ready(bitdepth)) return 0;
   int ok = 1;
+  /* the reference's own quant_cbcr_residual (highest priority registered so far) for the forwarded cases */
+  const strategy_list_t *const list = (const strategy_list_t *)opaque;
+  unsigned best = 0;
+  for (unsigned i = 0; i < list->count; ++i) {
+    const strategy_t *const st = &list->strategies[i];
+    if (!strcmp(st->type, "quant_cbcr_residual") && strcmp(st->strategy_name, STRATEGY_NAME) &&
+        (!ref_quant_cbcr_residual || st->priority >= best)) {
+      ref_quant_cbcr_residual = (quant_cbcr_func *)st->fptr;
+      best = st->priority;
+    }
+  }
   REG("quant", quant_cuda); REG("dequant", dequant_cuda);
   REG("quantize_residual", quantize_residual_cuda);
+  REG("quant_cbcr_residual", quant_cbcr_residual_cuda);
   REG("coeff_abs_sum", coeff_abs_sum_cuda); REG("fast_coeff_cost", fast_coeff_cost_cuda);
-  /* quant_cbcr_residual (JCCR) stays with the reference's implementation: SURVEY.md 8(f)-4 */
   return ok;
 }
