@@ -270,12 +270,14 @@ def test_quantize_residual(bd, mts):
 
 
 @pytest.mark.parametrize("bd", BDS)
-@pytest.mark.parametrize("signhide", [0, 1])
-def test_quant_cbcr_residual(bd, signhide):
-    """JCCR (quant-generic.c:241-442): all six joint modes, square and non-square chroma TUs, early skip."""
+@pytest.mark.parametrize("signhide,mts", [(0, "off"), (1, "off"), (0, "both"), (1, "implicit")])
+def test_quant_cbcr_residual(bd, signhide, mts):
+    """JCCR (quant-generic.c:241-442): all six joint modes, square and non-square chroma TUs, early skip;
+    with MTS enabled the chroma transform stays DCT-2 but goes through mts_dct (transform.c:256-292)."""
     O = load_oracle(bd)
-    R = load_ref(bd, "preset=ultrafast,signhide=%d,rdoq=0,jccr=1" % signhide)
-    rng = np.random.default_rng(900 + bd + signhide)
+    R = load_ref(bd, "preset=ultrafast,signhide=%d,rdoq=0,jccr=1,mts=%s" % (signhide, mts))
+    mts_val = {"off": 0, "both": 3, "implicit": 4}[mts]
+    rng = np.random.default_rng(900 + bd + signhide + mts_val)
     qmap = R.H.refh_chroma_qp_map()
     n_cases = 0
     for (w, h) in ((4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 16), (16, 8)):
@@ -284,7 +286,7 @@ def test_quant_cbcr_residual(bd, signhide):
                 for sign in (0, 1):
                     for early in (0, 1):
                         R.H.refh_set_state(qp, 1)
-                        p = OrcQuantParams(qp, bd, 1, signhide, 0, qmap)
+                        p = OrcQuantParams(qp, bd, 1, signhide, mts_val, qmap)
                         stride = 32
                         hi = 1 << bd
                         noise = int(rng.choice([2, 12, 60, hi]))
