@@ -201,6 +201,46 @@ int refh_quant_cbcr_residual(const char *strategy, int cu_type, int tr_idx, int 
                 coeff_out, early_skip != 0, 0, UVG_BOTH_T);
 }
 
+/* LFNST: the reference's kernels (exported data, lfnst_tables.h:56/:211) for the oracle's setter; the two
+ * entry points themselves; quantize_residual with the LFNST fields of cu_info_t filled in. */
+extern const int8_t uvg_lfnst_8x8[4][2][16][48];
+extern const int8_t uvg_lfnst_4x4[4][2][16][16];
+const int8_t *refh_lfnst_table(int eight) { return eight ? &uvg_lfnst_8x8[0][0][0][0] : &uvg_lfnst_4x4[0][0][0][0]; }
+
+static void fill_cu_lfnst(cu_info_t *cu, int cu_type, int tr_idx, int lfnst_idx, int cr_lfnst_idx, int intra_mode,
+                          int mode_chroma, int cu_log2_w, int cu_log2_h)
+{
+  fill_cu(cu, cu_type, tr_idx, lfnst_idx, cr_lfnst_idx, 0);
+  cu->intra.mode = (int8_t)intra_mode;
+  cu->intra.mode_chroma = (int8_t)mode_chroma;
+  cu->log2_width = (uint8_t)cu_log2_w;
+  cu->log2_height = (uint8_t)cu_log2_h;
+}
+
+void refh_lfnst(int inverse, int w, int h, int color, int lfnst_idx, int tr_idx, int intra_mode, int mode_chroma,
+                int cu_log2_w, int cu_log2_h, int tree_type, int luma_mode, int16_t *coeffs)
+{
+  cu_info_t cu;
+  fill_cu_lfnst(&cu, CU_INTRA, tr_idx, lfnst_idx, lfnst_idx, intra_mode, mode_chroma, cu_log2_w, cu_log2_h);
+  if (inverse) uvg_inv_lfnst(&cu, w, h, (color_t)color, (uint16_t)lfnst_idx, coeffs, (enum uvg_tree_type)tree_type, (int8_t)luma_mode);
+  else uvg_fwd_lfnst(&cu, w, h, (color_t)color, (uint16_t)lfnst_idx, coeffs, (enum uvg_tree_type)tree_type, (int8_t)luma_mode);
+}
+
+int refh_quantize_residual_lfnst(const char *strategy, int cu_type, int tr_idx, int lfnst_idx, int cr_lfnst_idx,
+                                 int intra_mode, int mode_chroma, int cu_log2_w, int cu_log2_h, int tree_type,
+                                 int luma_mode, int w, int h, int color, int in_stride, int out_stride,
+                                 const uvg_pixel *ref_in, const uvg_pixel *pred_in, uvg_pixel *rec_out,
+                                 int16_t *coeff_out, int early_skip)
+{
+  quant_residual_func *f = refh_get("quantize_residual", strategy);
+  if (!f) return -1;
+  cu_info_t cu;
+  fill_cu_lfnst(&cu, cu_type, tr_idx, lfnst_idx, cr_lfnst_idx, intra_mode, mode_chroma, cu_log2_w, cu_log2_h);
+  g_state->collocated_luma_mode = (int8_t)luma_mode;
+  return (int)f(g_state, &cu, w, h, (color_t)color, SCAN_DIAG, 0, in_stride, out_stride, ref_in, pred_in, rec_out,
+                coeff_out, early_skip != 0, 0, (enum uvg_tree_type)tree_type);
+}
+
 /* uvg_image_calc_sad on a small picture pair (frame-edge semantics, image.c:438). */
 unsigned refh_image_calc_sad(const uvg_pixel *pic_y, const uvg_pixel *ref_y, int pic_w,
                              int pic_h, int pic_x, int pic_y0, int ref_x, int ref_y0,

@@ -814,6 +814,167 @@ int orc_quant_cbcr_residual(const orc_quant_params *p, int cu_type, int tr_idx, 
   return has_coeffs ? joint_cb_cr : 0;
 }
 
+/* ===================================================================================
+ * LFNST (first piece): uvg_fwd_lfnst / uvg_inv_lfnst, transform.c:878-1200.
+ * The two trained kernels are NOT part of this repository: the test harness takes their
+ * addresses from the compiled reference (exported read-only symbols uvg_lfnst_8x8 /
+ * uvg_lfnst_4x4, lfnst_tables.h:56/:211) and hands them in through orc_set_lfnst_tables.
+ * Everything else (set selection, transposition, scan positions) follows from the code cited.
+ * ================================================================================= */
+static const int8_t *g_lfnst8;   /* [4][2][16][48] */
+static const int8_t *g_lfnst4;   /* [4][2][16][16] */
+void orc_set_lfnst_tables(const int8_t *t8x8, const int8_t *t4x4) { g_lfnst8 = t8x8; g_lfnst4 = t4x4; }
+
+/* uvg_lfnst_lut (lfnst_tables.h:51-54) as intervals of the extended mode index 0..94 */
+static int lfnst_set(int m) { return m < 2 ? 0 : m <= 12 ? 1 : m <= 23 ? 2 : m <= 44 ? 3 : m <= 55 ? 2 : 1; }
+
+/* uvg_wide_angle_correction, intra.c:637-658 */
+static int wide_angle(int mode, int l2w, int l2h, int account_for_dc_planar)
+{
+  static const int shift[6] = { 0, 6, 10, 12, 14, 15 };
+  if (l2w != l2h && mode > 1 && mode <= 66) {
+    const int d = l2w > l2h ? l2w - l2h : l2h - l2w;
+    if (l2w > l2h && mode < 2 + shift[d]) return mode + 65;
+    if (l2h > l2w && mode > 66 - shift[d]) return mode - 65 - (account_for_dc_planar ? 2 : 0);
+  }
+  return mode;
+}
+
+/* Position of LFNST scan entry j in a block of width w: up-right diagonal order inside a 4x4
+ * group and over the 2x2 groups of the top-left 8x8 (uvg_coef_top_left_diag_scan_8x8,
+ * lfnst_tables.h:366; first group of uvg_g_sig_last_scan[SCAN_DIAG] for narrower blocks). */
+static int lfnst_scan_pos(int j, int w, int whge3)
+{
+  static const uint8_t dx[16] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 1, 2, 3, 2, 3, 3 };
+  static const uint8_t dy[16] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 3, 2, 1, 3, 2, 3 };
+  static const uint8_t gx[4] = { 0, 0, 1, 1 }, gy[4] = { 0, 1, 0, 1 };
+  const int g = whge3 ? j >> 4 : 0, i = j & 15;
+  return (gy[g] * 4 + dy[i]) * w + gx[g] * 4 + dx[i];
+}
+
+typedef struct { int mode, transpose, sb, zero_out, whge3; } lfnst_ctx;
+
+/* the part uvg_fwd_lfnst and uvg_inv_lfnst share (:986-1018, :1128-1157). intra_mode: the block's
+ * mode after the CCLM / MIP substitutions; wa_log2_*: cur_cu->log2_* for luma, the block's for chroma */
+static lfnst_ctx lfnst_setup(int w, int h, int intra_mode, int wa_log2_w, int wa_log2_h)
+{
+  lfnst_ctx c;
+  int m = wide_angle(intra_mode, wa_log2_w, wa_log2_h, 1);
+  m = m < 0 ? m + 14 + 67 : m >= 67 ? m + 14 : m;                 /* get_lfnst_intra_mode :932-950 */
+  c.mode = m;
+  c.transpose = (m >= 67 && m >= 81) || (m < 67 && m > 34);       /* get_transpose_flag :952-956 */
+  c.whge3 = w >= 8 && h >= 8;
+  c.sb = c.whge3 ? 8 : 4;
+  c.zero_out = ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 8 : 16;
+  return c;
+}
+
+void orc_fwd_lfnst(int w, int h, int lfnst_idx, int intra_mode, int wa_log2_w, int wa_log2_h, int16_t *coeffs)
+{
+  const lfnst_ctx c = lfnst_setup(w, h, intra_mode, wa_log2_w, wa_log2_h);
+  int16_t in[48], out[48];
+  /* gather the top-left region, row-major or transposed (:1030-1066): 8x8 blocks use the L-shaped 48 */
+  int n = 0;
+  if (!c.transpose) {
+    for (int y = 0; y < c.sb; ++y) {
+      const int len = y < 4 ? c.sb : 4;
+      for (int x = 0; x < len; ++x) in[n++] = coeffs[y * w + x];
+    }
+  } else if (c.sb == 4) {
+    for (int y = 0; y < 4; ++y) for (int x = 0; x < 4; ++x) in[4 * x + y] = coeffs[y * w + x];
+  } else {
+    for (int y = 0; y < 8; ++y) {
+      for (int x = 0; x < 4; ++x) in[8 * x + y] = coeffs[y * w + x];
+      if (y < 4) for (int x = 4; x < 8; ++x) in[32 + 4 * (x - 4) + y] = coeffs[y * w + x];
+    }
+  }
+  /* uvg_fwd_lfnst_NxN :878-915 */
+  const int tr_size = c.sb > 4 ? 48 : 16;
+  const int8_t *mat = c.sb > 4 ? g_lfnst8 + ((size_t)(lfnst_set(c.mode) * 2 + lfnst_idx - 1) * 16) * 48
+                               : g_lfnst4 + ((size_t)(lfnst_set(c.mode) * 2 + lfnst_idx - 1) * 16) * 16;
+  for (int j = 0; j < tr_size; ++j) {
+    int acc = 0;
+    if (j < c.zero_out) {
+      for (int i = 0; i < tr_size; ++i) acc += in[i] * mat[j * tr_size + i];
+      out[j] = (int16_t)((acc + 64) >> 7);
+    } else {
+      out[j] = 0;
+    }
+  }
+  for (int j = 0; j < tr_size; ++j) coeffs[lfnst_scan_pos(j, w, c.whge3)] = out[j];    /* :1071-1081 */
+}
+
+void orc_inv_lfnst(int w, int h, int lfnst_idx, int intra_mode, int wa_log2_w, int wa_log2_h, int16_t *coeffs)
+{
+  const lfnst_ctx c = lfnst_setup(w, h, intra_mode, wa_log2_w, wa_log2_h);
+  int16_t in[16], out[48];
+  for (int j = 0; j < 16; ++j) in[j] = coeffs[lfnst_scan_pos(j, w, c.whge3)];          /* :1165-1169 */
+  /* uvg_inv_lfnst_NxN :1086-1108: the cast to coeff_t comes before the clip, which is then a no-op */
+  const int tr_size = c.sb > 4 ? 48 : 16;
+  const int8_t *mat = c.sb > 4 ? g_lfnst8 + ((size_t)(lfnst_set(c.mode) * 2 + lfnst_idx - 1) * 16) * 48
+                               : g_lfnst4 + ((size_t)(lfnst_set(c.mode) * 2 + lfnst_idx - 1) * 16) * 16;
+  for (int j = 0; j < tr_size; ++j) {
+    int acc = 0;
+    for (int i = 0; i < c.zero_out; ++i) acc += in[i] * mat[i * tr_size + j];
+    out[j] = (int16_t)((acc + 64) >> 7);
+  }
+  int n = 0;
+  if (!c.transpose) {                                                                   /* :1175-1198 */
+    for (int y = 0; y < c.sb; ++y) {
+      const int len = y < 4 ? c.sb : 4;
+      for (int x = 0; x < len; ++x) coeffs[y * w + x] = out[n++];
+    }
+  } else if (c.sb == 4) {
+    for (int y = 0; y < 4; ++y) for (int x = 0; x < 4; ++x) coeffs[y * w + x] = out[4 * x + y];
+  } else {
+    for (int y = 0; y < 8; ++y) {
+      for (int x = 0; x < 4; ++x) coeffs[y * w + x] = out[8 * x + y];
+      if (y < 4) for (int x = 4; x < 8; ++x) coeffs[y * w + x] = out[32 + 4 * (x - 4) + y];
+    }
+  }
+}
+
+/* uvg_quantize_residual_generic with cfg.lfnst (quant-generic.c:497-566), plain quant path.
+ * li: what the composite reads from cu_info_t / the state for LFNST. */
+int orc_quantize_residual_lfnst(const orc_quant_params *p, const orc_lfnst_info *li, int cu_type, int tr_idx,
+                                int w, int h, int color, int in_stride, int out_stride,
+                                const orc_pixel *ref_in, const orc_pixel *pred_in, orc_pixel *rec_out,
+                                int16_t *coeff_out, int early_skip)
+{
+  int16_t residual[32 * 32], coeff[32 * 32];
+  orc_generate_residual(ref_in, pred_in, residual, w, h, in_stride, in_stride);
+  if (p->mts || w != h) orc_mts_dct(p->bitdepth, color, cu_type, tr_idx, li->lfnst_idx, li->cr_lfnst_idx, 0, w, h, residual, coeff, p->mts);
+  else orc_dct_nxn(w, p->bitdepth, residual, coeff);
+  const int lfnst_index = (li->tree_type != 2 || color == 0) ? li->lfnst_idx : li->cr_lfnst_idx;   /* :509 */
+  const int ts_flag = (tr_idx == 1 && color == 0);
+  /* uvg_fwd_lfnst's own gate (:983-990) */
+  const int sep_tree = li->cu_log2_w + li->cu_log2_h < 6 || li->tree_type != 0;
+  int mode = color == 0 ? li->intra_mode : li->mode_chroma;
+  if (mode >= 81 && mode <= 83) mode = li->luma_mode;
+  const int l2w = ilog2(w), l2h = ilog2(h);
+  const int wl2w = color == 0 ? li->cu_log2_w : l2w, wl2h = color == 0 ? li->cu_log2_h : l2h;
+  const int do_lfnst = cu_type == 1 && lfnst_index && !ts_flag && (color == 0 || sep_tree);
+  if (do_lfnst) orc_fwd_lfnst(w, h, lfnst_index, mode, wl2w, wl2h, coeff);
+  orc_quant(p, coeff, coeff_out, w, h, color, cu_type, ts_flag, lfnst_index);
+  int has_coeffs = 0;
+  for (int i = 0; i < w * h; ++i) if (coeff_out[i] != 0) { has_coeffs = 1; break; }
+  if (has_coeffs && !early_skip) {
+    orc_dequant(p, coeff_out, coeff, w, h, color, cu_type, ts_flag);
+    if (do_lfnst) orc_inv_lfnst(w, h, lfnst_index, mode, wl2w, wl2h, coeff);
+    if (p->mts || w != h) orc_mts_idct(p->bitdepth, color, cu_type, tr_idx, li->lfnst_idx, li->cr_lfnst_idx, 0, w, h, coeff, residual, p->mts);
+    else orc_idct_nxn(w, p->bitdepth, coeff, residual);
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        int16_t val = (int16_t)(residual[x + y * w] + pred_in[x + y * in_stride]);
+        rec_out[x + y * out_stride] = (orc_pixel)clip3(0, PIXEL_MAX, val);
+      }
+  } else if (rec_out != pred_in) {
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) rec_out[x + y * out_stride] = pred_in[x + y * in_stride];
+  }
+  return has_coeffs;
+}
+
 /* coeff_abs_sum_generic :671-678 */
 uint32_t orc_coeff_abs_sum(const int16_t *coeffs, size_t length)
 {

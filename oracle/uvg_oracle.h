@@ -109,6 +109,21 @@ int orc_quantize_residual(const orc_quant_params *p, int cu_type, int tr_idx, in
                           int color, int use_trskip, int in_stride, int out_stride,
                           const orc_pixel *ref_in, const orc_pixel *pred_in,
                           orc_pixel *rec_out, int16_t *coeff_out, int early_skip);
+/* LFNST (transform.c:878-1200). The trained kernels come from the compiled reference at run time. */
+typedef struct {
+  int lfnst_idx, cr_lfnst_idx;      /* cu_info_t.lfnst_idx / cr_lfnst_idx */
+  int intra_mode, mode_chroma;      /* cu_info_t.intra.mode / mode_chroma */
+  int cu_log2_w, cu_log2_h;         /* cu_info_t.log2_width / log2_height */
+  int tree_type;                    /* 0 both, 1 luma, 2 chroma (cu.h:91-93) */
+  int luma_mode;                    /* state->collocated_luma_mode (CCLM substitution) */
+} orc_lfnst_info;
+void orc_set_lfnst_tables(const int8_t *t8x8, const int8_t *t4x4);
+void orc_fwd_lfnst(int w, int h, int lfnst_idx, int intra_mode, int wa_log2_w, int wa_log2_h, int16_t *coeffs);
+void orc_inv_lfnst(int w, int h, int lfnst_idx, int intra_mode, int wa_log2_w, int wa_log2_h, int16_t *coeffs);
+int orc_quantize_residual_lfnst(const orc_quant_params *p, const orc_lfnst_info *li, int cu_type, int tr_idx,
+                                int w, int h, int color, int in_stride, int out_stride,
+                                const orc_pixel *ref_in, const orc_pixel *pred_in, orc_pixel *rec_out,
+                                int16_t *coeff_out, int early_skip);
 int orc_quant_cbcr_residual(const orc_quant_params *p, int cu_type, int tr_idx, int w, int h, int joint_cb_cr,
                             int jccr_sign, int in_stride, int out_stride, const orc_pixel *u_ref,
                             const orc_pixel *v_ref, const orc_pixel *u_pred, const orc_pixel *v_pred,
