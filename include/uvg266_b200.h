@@ -138,7 +138,8 @@ typedef struct uvg_b200_quant_cfg {
   int32_t slice_intra;   /* state->frame->slicetype == UVG_SLICE_I                     */
   int32_t signhide;      /* cfg.signhide_enable                                        */
   int32_t mts;           /* cfg.mts (enum uvg_mts): selects mts_dct in uvg_transform2d */
-  int32_t reserved;
+  int32_t isp_mode;      /* cur_cu->intra.isp_mode of the CU the TU belongs to (0 for inter CUs): with
+                          * explicit MTS an ISP luma TU uses DST-7 (uvg_get_tr_type, dct-generic.c:2522) */
   int8_t chroma_qp_map[128]; /* encoder_control->qp_map[0][qp] for qp 0..127 (entry =   */
   int32_t has_chroma_qp_map; /*   mapped qp), valid when has_chroma_qp_map != 0        */
 } uvg_b200_quant_cfg;

@@ -117,6 +117,8 @@ void refh_set_state(int qp, int slice_is_intra)
   g_state->frame->slicetype = slice_is_intra ? UVG_SLICE_I : UVG_SLICE_P;
 }
 
+int refh_slice_is_intra(void) { return g_state->frame->slicetype == UVG_SLICE_I; }
+
 static void fill_cu(cu_info_t *cu, int cu_type, int tr_idx, int lfnst_idx, int cr_lfnst_idx, int isp_mode)
 {
   memset(cu, 0, sizeof(*cu));
@@ -170,6 +172,10 @@ int refh_dequant(const char *strategy, const int16_t *q_coef, int16_t *coef, int
   return 1;
 }
 
+/* cur_cu->intra.isp_mode for the next refh_quantize_residual calls (ISP + explicit MTS: DST-7) */
+static int g_isp_mode;
+void refh_set_isp_mode(int m) { g_isp_mode = m; }
+
 /* quantize_residual of the named strategy; returns has_coeffs, or -1. */
 int refh_quantize_residual(const char *strategy, int cu_type, int tr_idx, int lfnst_idx,
                            int w, int h, int color, int use_trskip, int in_stride,
@@ -179,7 +185,7 @@ int refh_quantize_residual(const char *strategy, int cu_type, int tr_idx, int lf
   quant_residual_func *f = refh_get("quantize_residual", strategy);
   if (!f) return -1;
   cu_info_t cu;
-  fill_cu(&cu, cu_type, tr_idx, lfnst_idx, 0, 0);
+  fill_cu(&cu, cu_type, tr_idx, lfnst_idx, 0, g_isp_mode);
   return (int)f(g_state, &cu, w, h, (color_t)color, SCAN_DIAG, use_trskip, in_stride,
                 out_stride, ref_in, pred_in, rec_out, coeff_out, early_skip != 0, 0,
                 UVG_BOTH_T);

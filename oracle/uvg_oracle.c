@@ -721,7 +721,7 @@ int orc_quantize_residual(const orc_quant_params *p, int cu_type, int tr_idx, in
   if (use_trskip) {
     memcpy(coeff, residual, sizeof(int16_t) * (size_t)w * h); /* uvg_transformskip :217 */
   } else if (p->mts || w != h) {
-    orc_mts_dct(p->bitdepth, color, cu_type, tr_idx, 0, 0, 0, w, h, residual, coeff, p->mts);
+    orc_mts_dct(p->bitdepth, color, cu_type, tr_idx, 0, 0, p->isp_mode, w, h, residual, coeff, p->mts);
   } else {
     orc_dct_nxn(w, p->bitdepth, residual, coeff);
   }
@@ -734,7 +734,7 @@ int orc_quantize_residual(const orc_quant_params *p, int cu_type, int tr_idx, in
     if (use_trskip) {
       memcpy(residual, coeff, sizeof(int16_t) * (size_t)w * h);
     } else if (p->mts || w != h) {
-      orc_mts_idct(p->bitdepth, color, cu_type, tr_idx, 0, 0, 0, w, h, coeff, residual, p->mts);
+      orc_mts_idct(p->bitdepth, color, cu_type, tr_idx, 0, 0, p->isp_mode, w, h, coeff, residual, p->mts);
     } else {
       orc_idct_nxn(w, p->bitdepth, coeff, residual);
     }

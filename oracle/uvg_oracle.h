@@ -94,6 +94,7 @@ typedef struct {
   int32_t signhide;        /* cfg.signhide_enable                        */
   int32_t mts;             /* cfg.mts (selects mts_dct in transform2d)   */
   const int8_t *chroma_qp_map; /* encoder_control->qp_map[0], or NULL    */
+  int32_t isp_mode;        /* cur_cu->intra.isp_mode (uvg_get_tr_type, dct-generic.c:2522) */
 } orc_quant_params;
 
 /* scan[(w*h)] of uvg_get_scan_order_table(SCAN_GROUP_4X4, SCAN_DIAG, log2w, log2h, 0) */

@@ -31,7 +31,8 @@ def _ensure_oracle_built():
 
 class OrcQuantParams(C.Structure):
     _fields_ = [("qp", C.c_int32), ("bitdepth", C.c_int32), ("slice_intra", C.c_int32),
-                ("signhide", C.c_int32), ("mts", C.c_int32), ("chroma_qp_map", C.c_void_p)]
+                ("signhide", C.c_int32), ("mts", C.c_int32), ("chroma_qp_map", C.c_void_p),
+                ("isp_mode", C.c_int32)]
 
 
 _oracles = {}

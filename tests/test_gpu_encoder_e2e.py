@@ -72,6 +72,30 @@ CASES = [
     ("intra_jccr_lfnst_mts", 8, 128, 64, 2, ["--preset=ultrafast", "-p", "1", "--rd=2", "--jccr", "--lfnst", "--mts=intra"]),
     # the tool set of BASELINE config 4 (10-bit, MTS + LFNST)
     ("intra_mts_lfnst_10bit", 10, 128, 64, 2, ["--preset=ultrafast", "-p", "1", "--rd=2", "--mts=intra", "--lfnst"]),
+    # transform skip: use_trskip = 1 / tr_idx == MTS_SKIP inside the fused kernels, luma and chroma
+    ("intra_trskip", 8, 128, 64, 2, ["--preset=ultrafast", "-p", "1", "--transform-skip", "--rd=2"]),
+    ("intra_trskip_chroma_mts", 8, 128, 64, 1, ["--preset=ultrafast", "-p", "1", "--transform-skip", "--chroma-transform-skip",
+                                                "--rd=2", "--mts=intra"]),
+    # LMCS chroma residual scaling: quantize_residual forwarded to the reference's composite, leaves on the GPU
+    ("intra_lmcs", 8, 128, 64, 2, ["--preset=ultrafast", "-p", "1", "--lmcs"]),
+    # ISP CUs with explicit MTS and no RDOQ: the fused kernel must pick DST-7 for them (uvg_get_tr_type :2522)
+    ("intra_isp_mts", 8, 128, 64, 2, ["--preset=ultrafast", "-p", "1", "--isp", "--mts=intra", "--rd=2"]),
+    # motion search patterns of BASELINE config 3 (TZ) and the exhaustive one
+    ("ldp_tz", 8, 192, 128, 3, ["--preset=ultrafast", "--gop=lp-g4d3t1", "--me=tz"]),
+    ("ldp_full8", 8, 128, 64, 2, ["--preset=ultrafast", "--gop=lp-g4d3t1", "--me=full8"]),
+]
+
+# One encode per BASELINE.json config at a frame size that has all four frame edges, interior CTUs and partial
+# CTUs at the right / bottom (832x480 = 13 x 7.5 CTUs), run with the encoder's worker threads so that the leaf
+# calls overlap. Scaling lists cannot get a case: the reference CLI itself dies with SIGFPE for
+# --scaling-list=default in every configuration tried (generic and avx2 alike), before any strategy is called.
+CONFIG_CASES = [
+    ("cfg1_intra_ultrafast_832x480", 8, 832, 480, 1, ["--preset=ultrafast", "-p", "1"], 8),
+    ("cfg2_intra_medium_832x480", 8, 832, 480, 1, ["--preset=medium", "-p", "1"], 8),
+    ("cfg3_ldp_tz_832x480", 8, 832, 480, 2, ["--preset=ultrafast", "--gop=lp-g4d3t1", "--me=tz"], 8),
+    ("cfg4_intra_10bit_mts_lfnst_832x480", 10, 832, 480, 1, ["--preset=ultrafast", "-p", "1", "--mts=intra", "--lfnst", "--rd=2"], 8),
+    ("cfg5_ra_gop16_tiles_832x480", 8, 832, 480, 3, ["--preset=ultrafast", "--gop=16", "--bipred", "--tiles=2x2", "--owf=1"], 8),
+    ("tiles_wpp_threads", 8, 256, 128, 2, ["--preset=ultrafast", "-p", "1", "--tiles=2x2", "--owf=1"], 4),
 ]
 
 
@@ -82,6 +106,16 @@ def test_bitstream_identity(tmp_path, name, bd, w, h, frames, opts):
     md5_gen, _, _ = encode(bd, yuv, w, h, frames, opts, cuda=False)
     md5_cuda, launches, err = encode(bd, yuv, w, h, frames, opts, cuda=True)
     assert launches and launches > 100, err[-1500:]
+    assert md5_cuda == md5_gen, "bitstream differs with the cuda strategies (%s)" % name
+
+
+@pytest.mark.parametrize("name,bd,w,h,frames,opts,threads", CONFIG_CASES, ids=[c[0] for c in CONFIG_CASES])
+def test_bitstream_identity_baseline_configs(tmp_path, name, bd, w, h, frames, opts, threads):
+    yuv = str(tmp_path / (name + ".yuv"))
+    make_yuv(yuv, w, h, frames, bd)
+    md5_gen, _, _ = encode(bd, yuv, w, h, frames, opts, cuda=False, threads=threads)
+    md5_cuda, launches, err = encode(bd, yuv, w, h, frames, opts, cuda=True, threads=threads)
+    assert launches and launches > 1000, err[-1500:]
     assert md5_cuda == md5_gen, "bitstream differs with the cuda strategies (%s)" % name
 
 

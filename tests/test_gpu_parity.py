@@ -69,6 +69,20 @@ def test_kat_reg_sad_shapes(w, h):
         assert not g
 
 
+def test_empty_blocks_cost_nothing():
+    """image_interpolated_sad (image.c:404-416) calls reg_sad / the width-specialised SADs / ver_sad with a
+    height of 0 when the motion vector points entirely above or below the frame: the reference's loops do
+    not run and return 0 (found by the --me=tz identity case)."""
+    pic, ref = K.sad_big_pictures()
+    L = U.lib()
+    assert U.dropin("reg_sad", 8)(ptr(pic), ptr(ref), 16, 0, 64, 64) == 0
+    assert U.dropin("reg_sad", 8)(ptr(pic), ptr(ref), 0, 16, 64, 64) == 0
+    fn = C.CFUNCTYPE(C.c_uint32, vp, vp, C.c_int32, C.c_uint32, C.c_uint32)(L.uvg_b200_get_optimized_sad_8(16))
+    assert fn(ptr(pic), ptr(ref), 0, 64, 64) == 0
+    assert U.dropin("ver_sad", 8)(ptr(pic), ptr(ref), 16, 0, 64) == 0
+    assert U.dropin("hor_sad", 8)(ptr(pic), ptr(ref), 16, 0, 64, 64, 4, 0) == 0
+
+
 def test_kat_coeff_abs_sum():
     data, expected = K.coeff_sum_case()
     assert U.lib().uvg_b200_coeff_abs_sum(ptr(data), data.size) == expected
@@ -280,6 +294,84 @@ def test_dropin_quantize_residual(bd, mts_val):
                             assert (rec1 == rec2).all(), (w, h, qp, color, tr_idx, early, alias)
                             n_cases += 1
     assert n_cases >= 256
+
+
+TS_COMBOS = ((1, 1, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (0, 0, 2), (0, 2, 1))   # (use_trskip, tr_idx, isp_mode)
+
+
+@pytest.mark.parametrize("bd", BDS)
+@pytest.mark.parametrize("signhide", [0, 1])
+def test_dropin_quantize_residual_transform_skip_and_isp(bd, signhide):
+    """use_trskip = 1 with / without tr_idx == MTS_SKIP, MTS_SKIP alone, and ISP CUs under explicit MTS
+    (oracle pinned on the reference for exactly these combinations: tests/test_oracle_vs_ref.py)."""
+    O = load_oracle(bd)
+    L = U.lib()
+    rng = np.random.default_rng(1420 + bd + signhide)
+    qptr, qlist = chroma_map(bd)
+    f = getattr(L, "uvg_b200_quantize_residual_%s" % U.suffix(bd))
+    n_cases = 0
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (16, 4), (4, 16), (8, 32), (32, 8)]:
+        for qp in (7, 22, 37):
+            for color in (0, 1):
+                for (trskip, tr_idx, isp) in TS_COMBOS:
+                    early = n_cases & 1
+                    slice_i = (n_cases >> 1) & 1
+                    p = OrcQuantParams(qp, bd, slice_i, signhide, 3, qptr, isp)
+                    cfg = U.QuantCfg.make(qp, bd, slice_i, signhide, 3, qlist, isp)
+                    stride = 64 if color == 0 else 32
+                    hi = 1 << bd
+                    ref = rng.integers(0, hi, stride * h).astype(pix_dtype(bd))
+                    noise = int(rng.choice([2, 12, 60, hi]))
+                    pred = np.clip(ref.astype(int) + rng.integers(-noise, noise + 1, stride * h), 0, hi - 1).astype(pix_dtype(bd))
+                    rec1 = np.full(stride * h, 7, pix_dtype(bd)); rec2 = rec1.copy()
+                    co1 = np.zeros(w * h, np.int16); co2 = np.zeros(w * h, np.int16)
+                    hc1 = f(C.byref(cfg), 1, tr_idx, w, h, color, trskip, stride, stride, ptr(ref), ptr(pred), ptr(rec1), ptr(co1), early)
+                    hc2 = O.orc_quantize_residual(C.byref(p), 1, tr_idx, w, h, color, trskip, stride, stride,
+                                                  ptr(ref), ptr(pred), ptr(rec2), ptr(co2), early)
+                    assert hc1 == hc2, (w, h, qp, color, trskip, tr_idx, isp)
+                    assert (co1 == co2).all(), (w, h, qp, color, trskip, tr_idx, isp)
+                    assert (rec1 == rec2).all(), (w, h, qp, color, trskip, tr_idx, isp, early)
+                    n_cases += 1
+    assert n_cases >= 250
+
+
+@pytest.mark.parametrize("bd", BDS)
+@pytest.mark.parametrize("signhide", [0, 1])
+def test_batched_quantize_residual_transform_skip_and_isp(bd, signhide):
+    """The same branches through the batched entry point, i.e. through every kernel family that accepts them
+    (registers-only 4x4 / 8x8 take use_trskip themselves; the tensor-core kernels hand transform skip to the
+    general kernel; ISP changes the transform pair the plans are built for)."""
+    O = load_oracle(bd)
+    L = U.lib()
+    rng = np.random.default_rng(1830 + bd + signhide)
+    hi = 1 << bd
+    dt = pix_dtype(bd)
+    weights = (28 << 0) | (300 << 16) | (700 << 32) | (1100 << 48)
+    for (n, nt) in ((4, 150), (8, 67), (16, 21), (32, 5)):
+        for (trskip, tr_idx, isp) in TS_COMBOS:
+            qp = int(rng.choice([12, 27, 37]))
+            ref = rng.integers(0, hi, nt * n * n).astype(dt)
+            pred = np.clip(ref.astype(int) + rng.integers(-30, 31, nt * n * n), 0, hi - 1).astype(dt)
+            pred[: n * n * 2] = ref[: n * n * 2]
+            rec = np.zeros(nt * n * n, dt)
+            coeff = np.zeros(nt * n * n, np.int16); has = np.zeros(nt, np.uint8)
+            ssd = np.zeros(nt, np.uint32); cost = np.zeros(nt, np.uint32)
+            cfg = U.QuantCfg.make(qp, bd, 1, signhide, 3, None, isp)
+            R, P, Rc = (U.Blocks.dense(a.ctypes.data, n, n) for a in (ref, pred, rec))
+            U.check(L.uvg_b200_quantize_residual_host(C.byref(cfg), 1, tr_idx, n, n, 0, trskip, 0, C.byref(R), ref.nbytes,
+                                                      C.byref(P), pred.nbytes, C.byref(Rc), rec.nbytes, ptr(coeff),
+                                                      ptr(has), ptr(ssd), ptr(cost), weights, nt))
+            p = OrcQuantParams(qp, bd, 1, signhide, 3, None, isp)
+            for t in range(nt):
+                sl = slice(t * n * n, (t + 1) * n * n)
+                r2 = np.zeros(n * n, dt); c2 = np.zeros(n * n, np.int16)
+                rr = np.ascontiguousarray(ref[sl]); pp = np.ascontiguousarray(pred[sl])
+                h2 = O.orc_quantize_residual(C.byref(p), 1, tr_idx, n, n, 0, trskip, n, n, ptr(rr), ptr(pp), ptr(r2), ptr(c2), 0)
+                assert has[t] == h2, (n, trskip, tr_idx, isp, t)
+                assert (coeff[sl] == c2).all(), (n, trskip, tr_idx, isp, t)
+                assert (rec[sl] == r2).all(), (n, trskip, tr_idx, isp, t)
+                assert ssd[t] == O.orc_pixels_calc_ssd(ptr(rr), ptr(r2), n, n, n, n)
+                assert cost[t] == O.orc_fast_coeff_cost(ptr(c2), n, n, weights)
 
 
 @pytest.mark.parametrize("bd", BDS)

@@ -270,6 +270,47 @@ def test_quantize_residual(bd, mts):
 
 
 @pytest.mark.parametrize("bd", BDS)
+@pytest.mark.parametrize("signhide", [0, 1])
+def test_quantize_residual_transform_skip_and_isp(bd, signhide):
+    """The branches the plain test never reaches: use_trskip = 1 (uvg_transformskip, transform.c:223) with and
+    without tr_idx == MTS_SKIP - quant only learns about the skip through tr_idx (quant-generic.c:538), so
+    (use_trskip 1, tr_idx 0), what chroma transform skip does, keeps the transform shift in q_bits -, tr_idx ==
+    MTS_SKIP without use_trskip, and ISP CUs with explicit MTS (DST-7 for 4..16, dct-generic.c:2522-2544)."""
+    O = load_oracle(bd)
+    R = load_ref(bd, "preset=ultrafast,signhide=%d,rdoq=0,mts=both,transform-skip=1" % signhide)
+    rng = np.random.default_rng(750 + bd + signhide)
+    qmap = R.H.refh_chroma_qp_map()
+    n_cases = 0
+    try:
+        for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (16, 4), (4, 16), (8, 32), (32, 8)]:
+            for qp in (7, 22, 37):
+                for color in (0, 1):
+                    for (trskip, tr_idx, isp) in ((1, 1, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (0, 0, 2), (0, 2, 1)):
+                        for early in (0, 1):
+                            R.H.refh_set_state(qp, int(rng.integers(0, 2)))
+                            R.H.refh_set_isp_mode(isp)
+                            p = OrcQuantParams(qp, bd, R.H.refh_slice_is_intra(), signhide, 3, qmap, isp)
+                            stride = 64 if color == 0 else 32
+                            hi = 1 << bd
+                            ref = rng.integers(0, hi, stride * h).astype(pix_dtype(bd))
+                            noise = int(rng.choice([2, 12, 60, hi]))
+                            pred = np.clip(ref.astype(int) + rng.integers(-noise, noise + 1, stride * h), 0, hi - 1).astype(pix_dtype(bd))
+                            rec1 = np.full(stride * h, 7, pix_dtype(bd)); rec2 = rec1.copy()
+                            co1 = np.zeros(w * h, np.int16); co2 = np.zeros(w * h, np.int16)
+                            hc1 = O.orc_quantize_residual(C.byref(p), 1, tr_idx, w, h, color, trskip, stride, stride,
+                                                          ptr(ref), ptr(pred), ptr(rec1), ptr(co1), early)
+                            hc2 = R.H.refh_quantize_residual(b"generic", 1, tr_idx, 0, w, h, color, trskip, stride, stride,
+                                                             ptr(ref), ptr(pred), ptr(rec2), ptr(co2), early)
+                            assert hc1 == hc2, (w, h, qp, color, trskip, tr_idx, isp)
+                            assert (co1 == co2).all(), (w, h, qp, color, trskip, tr_idx, isp)
+                            assert (rec1 == rec2).all(), (w, h, qp, color, trskip, tr_idx, isp, early)
+                            n_cases += 1
+    finally:
+        R.H.refh_set_isp_mode(0)
+    assert n_cases >= 500
+
+
+@pytest.mark.parametrize("bd", BDS)
 @pytest.mark.parametrize("signhide,mts", [(0, "off"), (1, "off"), (0, "both"), (1, "implicit")])
 def test_quant_cbcr_residual(bd, signhide, mts):
     """JCCR (quant-generic.c:241-442): all six joint modes, square and non-square chroma TUs, early skip;

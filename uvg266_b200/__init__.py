@@ -43,12 +43,12 @@ class Blocks(C.Structure):
 class QuantCfg(C.Structure):
     """uvg_b200_quant_cfg: what quant/dequant read through encoder_state_t."""
     _fields_ = [("qp", C.c_int32), ("bitdepth", C.c_int32), ("slice_intra", C.c_int32),
-                ("signhide", C.c_int32), ("mts", C.c_int32), ("reserved", C.c_int32),
+                ("signhide", C.c_int32), ("mts", C.c_int32), ("isp_mode", C.c_int32),
                 ("chroma_qp_map", C.c_int8 * 128), ("has_chroma_qp_map", C.c_int32)]
 
     @staticmethod
-    def make(qp, bitdepth=8, slice_intra=1, signhide=0, mts=0, chroma_map=None):
-        c = QuantCfg(qp, bitdepth, slice_intra, signhide, mts, 0)
+    def make(qp, bitdepth=8, slice_intra=1, signhide=0, mts=0, chroma_map=None, isp_mode=0):
+        c = QuantCfg(qp, bitdepth, slice_intra, signhide, mts, isp_mode)
         if chroma_map is not None:
             for i, v in enumerate(chroma_map[:128]):
                 c.chroma_qp_map[i] = int(v)

@@ -20,7 +20,7 @@ int init_quant_tables();
 std::atomic<uint64_t> g_launches{0};
 static thread_local char t_err[512] = "";
 static std::mutex g_init_mu;
-static int g_device = -1;
+static std::atomic<int> g_device{-1};
 static int g_sms = 0;
 static std::atomic<int> g_dropin_bd{10};
 
@@ -42,8 +42,8 @@ void fatal(const char *what, cudaError_t e, const char *file, int line)
 static int do_init(int device)
 {
   std::lock_guard<std::mutex> lk(g_init_mu);
-  if (g_device >= 0) {
-    if (device >= 0 && device != g_device) { set_error("already initialised on device %d", g_device); return 1; }
+  if (g_device.load() >= 0) {
+    if (device >= 0 && device != g_device.load()) { set_error("already initialised on device %d", g_device.load()); return 1; }
     return 0;
   }
   int n = 0;
@@ -65,16 +65,16 @@ static int do_init(int device)
   g_sms = prop.multiProcessorCount;
   if (init_transform_tables()) return 1;
   if (init_quant_tables()) return 1;
-  g_device = device;
+  g_device.store(device);
   return 0;
 }
 
 int ensure_init()
 {
-  if (g_device >= 0) {
+  if (g_device.load() >= 0) {
     // worker threads created after init still need the device selected
     static thread_local bool t_set = false;
-    if (!t_set) { if (cudaSetDevice(g_device) != cudaSuccess) { set_error("cudaSetDevice failed"); return 1; } t_set = true; }
+    if (!t_set) { if (cudaSetDevice(g_device.load()) != cudaSuccess) { set_error("cudaSetDevice failed"); return 1; } t_set = true; }
     return 0;
   }
   return do_init(-1);
@@ -100,6 +100,18 @@ int Staging::ensure(size_t host_bytes, size_t dev_bytes)
     d_cap = cap;
   }
   return 0;
+}
+
+// Worker threads come and go (uvg266 open/close as a library): give back what the thread held. At process
+// exit the driver may already be gone; every call then fails harmlessly and the error is dropped.
+Staging::~Staging()
+{
+  if (!stream && !h_pin && !d_buf) return;
+  if (cudaSetDevice(g_device.load()) != cudaSuccess) { cudaGetLastError(); return; }
+  if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+  if (h_pin) cudaFreeHost(h_pin);
+  if (d_buf) cudaFree(d_buf);
+  cudaGetLastError();
 }
 
 Staging &tls_staging()
@@ -129,6 +141,9 @@ template <typename Pix>
 static void dropin_distortion(int metric, int bitdepth, int w, int h, const Pix *a, size_t sa,
                               const Pix *const *cands, size_t sb, int k, unsigned *out)
 {
+  // A motion vector pointing entirely outside the frame leaves an empty middle part: the edge splitter calls
+  // reg_sad / the width-specialised SADs with height (or width) 0 (image.c:404-416), whose loops do not run.
+  if (w <= 0 || h <= 0) { for (int c = 0; c < k; ++c) out[c] = 0; return; }
   if (ensure_init()) { fprintf(stderr, "uvg266_b200: %s\n", t_err); abort(); }
   Staging &s = tls_staging();
   const size_t blk = (size_t)w * h * sizeof(Pix);

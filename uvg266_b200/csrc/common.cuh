@@ -122,6 +122,7 @@ struct Staging {
   uint8_t *h_pin = nullptr; size_t h_cap = 0;   // pinned host
   uint8_t *d_buf = nullptr; size_t d_cap = 0;   // device
   int ensure(size_t host_bytes, size_t dev_bytes);
+  ~Staging();     // releases the thread's stream and buffers when an encoder worker thread exits
 };
 Staging &tls_staging();
 

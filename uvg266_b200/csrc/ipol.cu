@@ -16,6 +16,7 @@
 // interpolated blocks never reach HBM (search_inter.c:1085-1250 interpolates into 4+4 block buffers
 // per step and scores them with satd_any_size_quad).
 #include "common.cuh"
+#include <mutex>
 #include "hadamard.cuh"
 
 namespace uvgb {
@@ -284,14 +285,17 @@ extern "C" int uvg_b200_frac_search_dev(int bitdepth, int w, int h, const void *
   const size_t slot = (size_t)((wh * P + 15) & ~15) + (size_t)w * h + (size_t)((a.nx * wh * w * 2 + 15) & ~15);
   const size_t smem = slot * G;
   if (smem > 200 * 1024) { set_error("frac_search: candidate set needs %zu bytes of shared memory", smem); return 1; }
-  static bool attr = false;
-  if (!attr) {
-    UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    UVGB_TRY(cudaFuncSetAttribute(frac_search_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  // callable from any number of threads: set the attributes exactly once
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    cudaError_t e = cudaFuncSetAttribute(frac_search_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(frac_search_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(frac_search_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(frac_search_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_err = e;
+  });
+  UVGB_TRY(attr_err);
   size_t grid = (n_blocks + G - 1) / G;
   const size_t cap = (size_t)sm_count() * 16;
   if (grid > cap) grid = cap;

@@ -597,7 +597,7 @@ static int run_quantize_residual(const uvg_b200_quant_cfg *cfg, int cu_type, int
   if (!use_trskip) {
     // uvg_transform2d (transform.c:256): mts_dct when cfg.mts or non-square, else dct_NxN -
     // both are this matrix product; with mts off the types are DCT2/DCT2.
-    derive_tr(w, h, color, cu_type, tr_idx, 0, 0, 0, cfg->mts, &th, &tv, &sw, &sh);
+    derive_tr(w, h, color, cu_type, tr_idx, 0, 0, cfg->isp_mode, cfg->mts, &th, &tv, &sw, &sh);
     if (make_fwd_plan(fp, cfg->bitdepth, w, h, th, tv, sw, sh)) return 1;
     if (make_inv_plan(ip, cfg->bitdepth, w, h, th, tv, sw, sh)) return 1;
   }

@@ -13,6 +13,7 @@
 // inside a row; the row pitch is chosen so that the second row a warp may touch starts on the
 // bank after the first row's last group.
 #include "common.cuh"
+#include <mutex>
 
 namespace uvgb {
 
@@ -83,11 +84,13 @@ int launch_sad_search_u8(const uint8_t *cur, const uint8_t *ref, int pic_w, int 
   if (g4 <= 32) while ((pitch_words & 31) != (g4 & 31)) ++pitch_words;   // see header comment
   const size_t smem = ((size_t)pitch_words * (h + 2 * range) + (size_t)(w / 4) * h) * 4;
   if (smem > 227 * 1024) return -1;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    UVGB_TRY(cudaFuncSetAttribute(sad_search_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  // callable from any number of threads: raise the limit once, to the 227 KB cap
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(sad_search_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  UVGB_TRY(attr_err);
   sad_search_u8_kernel<<<(unsigned)n_blocks, 256, smem, st>>>(cur, ref, pic_w, pic_h, stride, cur_x, cur_y, mv_x,
                                                               mv_y, range, w, h, pitch_words, out);
   UVGB_LAUNCH_CHECK();

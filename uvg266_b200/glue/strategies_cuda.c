@@ -91,9 +91,10 @@ static void generate_residual_cuda(const uvg_pixel *ref, const uvg_pixel *pred, 
 { B200(generate_residual)(ref, pred, residual, w, h, rs, ps); }
 
 /* ---- dct ------------------------------------------------------------------------- */
+/* dct_func is typed `unsigned (...)` (strategies-dct.h:44); the value is never read */
 #define DCTFN(name)                                                                              \
-  static void name##_cuda(int8_t bitdepth, const int16_t *in, int16_t *out)                      \
-  { uvg_b200_##name(bitdepth, in, out); }
+  static unsigned name##_cuda(int8_t bitdepth, const int16_t *in, int16_t *out)                  \
+  { uvg_b200_##name(bitdepth, in, out); return 0; }
 DCTFN(dct_4x4) DCTFN(dct_8x8) DCTFN(dct_16x16) DCTFN(dct_32x32)
 DCTFN(idct_4x4) DCTFN(idct_8x8) DCTFN(idct_16x16) DCTFN(idct_32x32)
 DCTFN(fast_forward_dst_4x4) DCTFN(fast_inverse_dst_4x4)
@@ -139,17 +140,24 @@ static uint32_t crc32c_4x4_cuda(const uvg_pixel *buf, uint32_t pic_stride) { ret
 static uint32_t crc32c_8x8_cuda(const uvg_pixel *buf, uint32_t pic_stride) { return B200(crc32c_8x8)(buf, pic_stride); }
 
 /* ---- quant ----------------------------------------------------------------------- */
-static void unsupported(const char *what)
+/* The implementations the reference itself registered for the quant group (highest priority below ours),
+ * captured at registration. Calls the cuda strategy does not cover are FORWARDED to them - the
+ * composites (quantize_residual, quant_cbcr_residual) then run their transform / quant / dequant steps
+ * through the strategy table, i.e. on the cuda leaves, and the encoder-side tools (LFNST, RDOQ, dep-quant,
+ * LMCS: transform.c, rdo.c, dep_quant.c, reshape.c) run where they live. Nothing aborts mid-encode. */
+static quant_func *ref_quant;
+static dequant_func *ref_dequant;
+static quant_residual_func *ref_quantize_residual;
+static quant_cbcr_func *ref_quant_cbcr_residual;
+
+static int scaling_lists_on(const encoder_control_t *const enc)
 {
-  fprintf(stderr, "uvg266_b200: %s is not supported by the cuda strategy; select the generic one with "
-                  "UVG266_OVERRIDE_quant=generic UVG266_OVERRIDE_dequant=generic "
-                  "UVG266_OVERRIDE_quantize_residual=generic\n", what);
-  abort();
+  return enc->cfg.scaling_list != UVG_SCALING_LIST_OFF || enc->scaling_list.enable;
 }
 
 /* Flatten what uvg_quant_generic / uvg_dequant_generic read through encoder_state_t
  * (quant-generic.c:62-84, 620-637). */
-static void fill_cfg(const encoder_state_t *const state, uvg_b200_quant_cfg *c)
+static void fill_cfg(const encoder_state_t *const state, const cu_info_t *const cu, uvg_b200_quant_cfg *c)
 {
   const encoder_control_t *const enc = state->encoder_control;
   memset(c, 0, sizeof(*c));
@@ -158,125 +166,63 @@ static void fill_cfg(const encoder_state_t *const state, uvg_b200_quant_cfg *c)
   c->slice_intra = state->frame->slicetype == UVG_SLICE_I;
   c->signhide = enc->cfg.signhide_enable;
   c->mts = enc->cfg.mts;
+  c->isp_mode = (cu && cu->type == CU_INTRA) ? cu->intra.isp_mode : 0;
   if (enc->qp_map[0]) {
     for (int i = 0; i < 64; ++i) c->chroma_qp_map[i] = enc->qp_map[0][i];
     c->has_chroma_qp_map = 1;
   }
-  if (enc->cfg.scaling_list != UVG_SCALING_LIST_OFF || enc->scaling_list.enable) unsupported("scaling lists");
 }
 
-static void quant_cuda(const encoder_state_t *const state, coeff_t *coef, coeff_t *q_coef, int32_t w,
-                       int32_t h, color_t color, int8_t scan_idx, int8_t block_type,
-                       int8_t transform_skip, uint8_t lfnst_idx)
+/* quant / dequant with scaling lists (quant-generic.c:74-94, :639-659) read per-position tables owned by
+ * the encoder (scalinglist.c); that branch stays with the reference's implementation. */
+static unsigned quant_cuda(const encoder_state_t *const state, coeff_t *coef, coeff_t *q_coef, int32_t w,
+                           int32_t h, color_t color, int8_t scan_idx, int8_t block_type,
+                           int8_t transform_skip, uint8_t lfnst_idx)
 {
+  if (scaling_lists_on(state->encoder_control))
+    return ref_quant(state, coef, q_coef, w, h, color, scan_idx, block_type, transform_skip, lfnst_idx);
   uvg_b200_quant_cfg c;
-  fill_cfg(state, &c);
+  fill_cfg(state, NULL, &c);
   uvg_b200_quant(&c, coef, q_coef, w, h, (int)color, scan_idx, block_type, transform_skip, lfnst_idx);
+  return 0;
 }
 
-static void dequant_cuda(const encoder_state_t *const state, coeff_t *q_coef, coeff_t *coef, int32_t w,
-                         int32_t h, color_t color, int8_t block_type, int8_t transform_skip)
+static unsigned dequant_cuda(const encoder_state_t *const state, coeff_t *q_coef, coeff_t *coef, int32_t w,
+                             int32_t h, color_t color, int8_t block_type, int8_t transform_skip)
 {
   const encoder_control_t *const enc = state->encoder_control;
-  if (enc->cfg.dep_quant && !transform_skip) {
-    /* trellis-coded quantisation has its own dequantiser in the encoder proper
-     * (dep_quant.c:1069); the strategy only forwards, like the generic one (:621-624) */
-    uvg_dep_quant_dequant(state, block_type, w, h, color, q_coef, coef, enc->cfg.scaling_list);
-    return;
-  }
+  /* trellis-coded quantisation has its own dequantiser in the encoder proper (dep_quant.c:1069), which
+   * the reference's dequant forwards to itself (:621-624) */
+  if ((enc->cfg.dep_quant && !transform_skip) || scaling_lists_on(enc))
+    return ref_dequant(state, q_coef, coef, w, h, color, block_type, transform_skip);
   uvg_b200_quant_cfg c;
-  fill_cfg(state, &c);
+  fill_cfg(state, NULL, &c);
   uvg_b200_dequant(&c, q_coef, coef, w, h, (int)color, block_type, transform_skip);
+  return 0;
 }
 
-/* quantize_residual: the plain chain (residual -> T -> quant -> dequant -> IT -> recon) is ONE
- * fused kernel. When a tool that lives in the encoder proper is switched on (LFNST, RDOQ,
- * dep-quant, LMCS chroma scaling: transform.c:880-1228, rdo.c, dep_quant.c, reshape.c - all
- * outside this path) the strategy walks the same chain step by step through
- * the strategy table, exactly as the reference's composite does (quant-generic.c:460-612),
- * so those steps still run on the GPU and the encoder-side tools run where they live. */
-static int quantize_residual_cuda(encoder_state_t *const state, const cu_info_t *const cur_cu,
-                                  const int width, const int height, const color_t color,
-                                  const coeff_scan_order_t scan_order, const int use_trskip,
-                                  const int in_stride, const int out_stride,
-                                  const uvg_pixel *const ref_in, const uvg_pixel *const pred_in,
-                                  uvg_pixel *rec_out, coeff_t *coeff_out, bool early_skip,
-                                  int lmcs_chroma_adj, enum uvg_tree_type tree_type)
+/* quantize_residual: the plain chain (residual -> T -> quant -> dequant -> IT -> recon) is ONE fused
+ * kernel. With a tool of the encoder proper switched on the call is forwarded (see above). */
+static unsigned quantize_residual_cuda(encoder_state_t *const state, const cu_info_t *const cur_cu,
+                                       const int width, const int height, const color_t color,
+                                       const coeff_scan_order_t scan_order, const int use_trskip,
+                                       const int in_stride, const int out_stride,
+                                       const uvg_pixel *const ref_in, const uvg_pixel *const pred_in,
+                                       uvg_pixel *rec_out, coeff_t *coeff_out, bool early_skip,
+                                       int lmcs_chroma_adj, enum uvg_tree_type tree_type)
 {
   const encoder_control_t *const enc = state->encoder_control;
   const bool lmcs = state->tile->frame->lmcs_aps->m_sliceReshapeInfo.enableChromaAdj && color != COLOR_Y;
   const bool lfnst = enc->cfg.lfnst && cur_cu->type == CU_INTRA;
   const bool rdoq = enc->cfg.rdoq_enable && ((width > 4 || !enc->cfg.rdoq_skip) || use_trskip);
   const bool dq = !use_trskip && enc->cfg.dep_quant;
-  if (!lmcs && !lfnst && !rdoq && !dq) {
-    uvg_b200_quant_cfg c;
-    fill_cfg(state, &c);
-#if UVG_BIT_DEPTH == 8
-    return uvg_b200_quantize_residual_8(&c, cur_cu->type, cur_cu->tr_idx, width, height, (int)color, use_trskip,
-                                        in_stride, out_stride, ref_in, pred_in, rec_out, coeff_out, early_skip);
-#else
-    return uvg_b200_quantize_residual_16(&c, cur_cu->type, cur_cu->tr_idx, width, height, (int)color, use_trskip,
-                                         in_stride, out_stride, ref_in, pred_in, rec_out, coeff_out, early_skip);
-#endif
-  }
-
-  ALIGNED(64) int16_t residual[TR_MAX_WIDTH * TR_MAX_WIDTH];
-  ALIGNED(64) coeff_t coeff[TR_MAX_WIDTH * TR_MAX_WIDTH];
-  const int n = width * height;
-  const int max_abs = (1 << UVG_BIT_DEPTH) - 1;
-  uvg_generate_residual(ref_in, pred_in, residual, width, height, in_stride, in_stride);
-  if (lmcs) {                                             /* forward chroma residual scaling */
-    for (int i = 0; i < n; ++i) {
-      const int s = residual[i] >= 0 ? 1 : -1;
-      const int a = s * residual[i];
-      residual[i] = (int16_t)CLIP(-max_abs, max_abs, s * (((a << CSCALE_FP_PREC) + (lmcs_chroma_adj >> 1)) / lmcs_chroma_adj));
-    }
-  }
-  if (use_trskip) uvg_transformskip(enc, residual, coeff, width, height);
-  else uvg_transform2d(enc, residual, coeff, width, height, color, cur_cu);
-  const uint8_t lfnst_index = (tree_type != UVG_CHROMA_T || color == COLOR_Y) ? cur_cu->lfnst_idx : cur_cu->cr_lfnst_idx;
-  if (lfnst) uvg_fwd_lfnst(cur_cu, width, height, color, lfnst_index, coeff, tree_type, state->collocated_luma_mode);
-
-  const int ts_flag = cur_cu->tr_idx == MTS_SKIP && color == COLOR_Y;
-  if (dq) {
-    int abs_sum = 0;
-    uvg_dep_quant(state, cur_cu, width, height, coeff, coeff_out, color, tree_type, &abs_sum, enc->cfg.scaling_list);
-  } else if (enc->cfg.rdoq_enable && (width > 4 || !enc->cfg.rdoq_skip) && !use_trskip) {
-    uvg_rdoq(state, coeff, coeff_out, width, height, color, scan_order, cur_cu->type, cur_cu->cbf, lfnst_index,
-             color == 0 ? cur_cu->tr_idx : 0);
-  } else if (enc->cfg.rdoq_enable && use_trskip) {
-    uvg_ts_rdoq(state, coeff, coeff_out, width, height, color, scan_order);
-  } else {
-    uvg_quant(state, coeff, coeff_out, width, height, color, scan_order, cur_cu->type, ts_flag, lfnst_index);
-  }
-
-  int has_coeffs = 0;
-  for (int i = 0; i < n && !has_coeffs; ++i) has_coeffs = coeff_out[i] != 0;
-
-  if (has_coeffs && !early_skip) {
-    uvg_dequant(state, coeff_out, coeff, width, height, color, cur_cu->type, ts_flag);
-    if (lfnst) uvg_inv_lfnst(cur_cu, width, height, color, lfnst_index, coeff, tree_type, state->collocated_luma_mode);
-    if (use_trskip) uvg_itransformskip(enc, residual, coeff, width, height);
-    else uvg_itransform2d(enc, residual, coeff, width, height, color, cur_cu);
-    if (lmcs) {                                           /* inverse chroma residual scaling */
-      for (int i = 0; i < n; ++i) {
-        const int16_t r = (int16_t)CLIP((int16_t)(-max_abs - 1), (int16_t)max_abs, residual[i]);
-        const int s = r >= 0 ? 1 : -1;
-        int v = s * (((s * r) * lmcs_chroma_adj + (1 << (CSCALE_FP_PREC - 1))) >> CSCALE_FP_PREC);
-        if (sizeof(uvg_pixel) == 2) v = CLIP(-32768, 32767, v);
-        residual[i] = (int16_t)v;
-      }
-    }
-    for (int y = 0; y < height; ++y)
-      for (int x = 0; x < width; ++x) {
-        const int16_t v = (int16_t)(residual[x + y * width] + pred_in[x + y * in_stride]);
-        rec_out[x + y * out_stride] = (uvg_pixel)CLIP(0, PIXEL_MAX, v);
-      }
-  } else if (rec_out != pred_in) {
-    for (int y = 0; y < height; ++y)
-      memcpy(&rec_out[y * out_stride], &pred_in[y * in_stride], width * sizeof(uvg_pixel));
-  }
-  return has_coeffs;
+  if (lmcs || lfnst || rdoq || dq || scaling_lists_on(enc))
+    return ref_quantize_residual(state, cur_cu, width, height, color, scan_order, use_trskip, in_stride, out_stride,
+                                 ref_in, pred_in, rec_out, coeff_out, early_skip, lmcs_chroma_adj, tree_type);
+  uvg_b200_quant_cfg c;
+  fill_cfg(state, cur_cu, &c);
+  return (unsigned)B200(quantize_residual)(&c, cur_cu->type, cur_cu->tr_idx, width, height, (int)color, use_trskip,
+                                           in_stride, out_stride, ref_in, pred_in, rec_out, coeff_out, early_skip);
 }
 
 static uint32_t coeff_abs_sum_cuda(const coeff_t *coeffs, size_t length)
@@ -361,32 +307,36 @@ static int device_ready(uint8_t bitdepth)
   return 1;
 }
 
-#define REG(type, fn) (ok &= uvg_strategyselector_register(opaque, type, STRATEGY_NAME, CUDA_PRIORITY, (void *)&fn))
+/* Every wrapper is first assigned to a pointer of the reference's own typedef for that strategy type, so a
+ * signature drift against the reference headers is a compile error here instead of corrupted arguments. */
+#define REG(type, fntype, fn)                                                                    \
+  do { fntype *const typed_ = fn;                                                                \
+       ok &= uvg_strategyselector_register(opaque, type, STRATEGY_NAME, CUDA_PRIORITY, (void *)typed_); } while (0)
 
 int uvg_strategy_register_picture_cuda(void *opaque, uint8_t bitdepth)
 {
   if (!device_ready(bitdepth)) return 0;
   int ok = 1;
-  REG("reg_sad", reg_sad_cuda);
-  REG("sad_4x4", sad_4_cuda); REG("sad_8x8", sad_8_cuda); REG("sad_16x16", sad_16_cuda);
-  REG("sad_32x32", sad_32_cuda); REG("sad_64x64", sad_64_cuda);
-  REG("satd_4x4", satd_4_cuda); REG("satd_8x8", satd_8_cuda); REG("satd_16x16", satd_16_cuda);
-  REG("satd_32x32", satd_32_cuda); REG("satd_64x64", satd_64_cuda);
-  REG("satd_any_size", satd_any_size_cuda); REG("satd_any_size_vtm", satd_any_size_vtm_cuda);
-  REG("sad_4x4_dual", sad_4_dual_cuda); REG("sad_8x8_dual", sad_8_dual_cuda);
-  REG("sad_16x16_dual", sad_16_dual_cuda); REG("sad_32x32_dual", sad_32_dual_cuda);
-  REG("satd_4x4_dual", satd_4_dual_cuda); REG("satd_8x8_dual", satd_8_dual_cuda);
-  REG("satd_16x16_dual", satd_16_dual_cuda); REG("satd_32x32_dual", satd_32_dual_cuda);
+  REG("reg_sad", reg_sad_func, reg_sad_cuda);
+  REG("sad_4x4", cost_pixel_nxn_func, sad_4_cuda); REG("sad_8x8", cost_pixel_nxn_func, sad_8_cuda); REG("sad_16x16", cost_pixel_nxn_func, sad_16_cuda);
+  REG("sad_32x32", cost_pixel_nxn_func, sad_32_cuda); REG("sad_64x64", cost_pixel_nxn_func, sad_64_cuda);
+  REG("satd_4x4", cost_pixel_nxn_func, satd_4_cuda); REG("satd_8x8", cost_pixel_nxn_func, satd_8_cuda); REG("satd_16x16", cost_pixel_nxn_func, satd_16_cuda);
+  REG("satd_32x32", cost_pixel_nxn_func, satd_32_cuda); REG("satd_64x64", cost_pixel_nxn_func, satd_64_cuda);
+  REG("satd_any_size", cost_pixel_any_size_func, satd_any_size_cuda); REG("satd_any_size_vtm", cost_pixel_any_size_func, satd_any_size_vtm_cuda);
+  REG("sad_4x4_dual", cost_pixel_nxn_multi_func, sad_4_dual_cuda); REG("sad_8x8_dual", cost_pixel_nxn_multi_func, sad_8_dual_cuda);
+  REG("sad_16x16_dual", cost_pixel_nxn_multi_func, sad_16_dual_cuda); REG("sad_32x32_dual", cost_pixel_nxn_multi_func, sad_32_dual_cuda);
+  REG("satd_4x4_dual", cost_pixel_nxn_multi_func, satd_4_dual_cuda); REG("satd_8x8_dual", cost_pixel_nxn_multi_func, satd_8_dual_cuda);
+  REG("satd_16x16_dual", cost_pixel_nxn_multi_func, satd_16_dual_cuda); REG("satd_32x32_dual", cost_pixel_nxn_multi_func, satd_32_dual_cuda);
   /* unreachable from the encoder (search_intra.c:1000) but in the table: pred_buffer semantics kept
    * literally - candidate 1 starts 1024 pixels after candidate 0 and both read 4096 pixels */
-  REG("sad_64x64_dual", sad_64_dual_cuda); REG("satd_64x64_dual", satd_64_dual_cuda);
-  REG("satd_any_size_quad", satd_any_size_quad_cuda);
-  REG("pixels_calc_ssd", pixels_calc_ssd_cuda);
-  REG("get_optimized_sad", get_optimized_sad_cuda);
-  REG("ver_sad", ver_sad_cuda); REG("hor_sad", hor_sad_cuda);
-  REG("generate_residual", generate_residual_cuda);
-  REG("bipred_average", bipred_average_cuda);
-  REG("crc32c_4x4", crc32c_4x4_cuda); REG("crc32c_8x8", crc32c_8x8_cuda);
+  REG("sad_64x64_dual", cost_pixel_nxn_multi_func, sad_64_dual_cuda); REG("satd_64x64_dual", cost_pixel_nxn_multi_func, satd_64_dual_cuda);
+  REG("satd_any_size_quad", cost_pixel_any_size_multi_func, satd_any_size_quad_cuda);
+  REG("pixels_calc_ssd", pixels_calc_ssd_func, pixels_calc_ssd_cuda);
+  REG("get_optimized_sad", get_optimized_sad_func, get_optimized_sad_cuda);
+  REG("ver_sad", ver_sad_func, ver_sad_cuda); REG("hor_sad", hor_sad_func, hor_sad_cuda);
+  REG("generate_residual", generate_residual_func, generate_residual_cuda);
+  REG("bipred_average", inter_recon_bipred_func, bipred_average_cuda);
+  REG("crc32c_4x4", crc32c_4x4_func, crc32c_4x4_cuda); REG("crc32c_8x8", crc32c_8x8_func, crc32c_8x8_cuda);
   /* pixel_var accumulates in double in index order: not reproducible by a parallel reduction, left to
    * the reference's implementation */
   return ok;
@@ -396,12 +346,12 @@ int uvg_strategy_register_dct_cuda(void *opaque, uint8_t bitdepth)
 {
   if (!device_ready(bitdepth)) return 0;
   int ok = 1;
-  REG("dct_4x4", dct_4x4_cuda); REG("dct_8x8", dct_8x8_cuda); REG("dct_16x16", dct_16x16_cuda);
-  REG("dct_32x32", dct_32x32_cuda);
-  REG("idct_4x4", idct_4x4_cuda); REG("idct_8x8", idct_8x8_cuda); REG("idct_16x16", idct_16x16_cuda);
-  REG("idct_32x32", idct_32x32_cuda);
-  REG("fast_forward_dst_4x4", fast_forward_dst_4x4_cuda); REG("fast_inverse_dst_4x4", fast_inverse_dst_4x4_cuda);
-  REG("mts_dct", mts_dct_cuda); REG("mts_idct", mts_idct_cuda);
+  REG("dct_4x4", dct_func, dct_4x4_cuda); REG("dct_8x8", dct_func, dct_8x8_cuda); REG("dct_16x16", dct_func, dct_16x16_cuda);
+  REG("dct_32x32", dct_func, dct_32x32_cuda);
+  REG("idct_4x4", dct_func, idct_4x4_cuda); REG("idct_8x8", dct_func, idct_8x8_cuda); REG("idct_16x16", dct_func, idct_16x16_cuda);
+  REG("idct_32x32", dct_func, idct_32x32_cuda);
+  REG("fast_forward_dst_4x4", dct_func, fast_forward_dst_4x4_cuda); REG("fast_inverse_dst_4x4", dct_func, fast_inverse_dst_4x4_cuda);
+  REG("mts_dct", mts_dct_func, mts_dct_cuda); REG("mts_idct", mts_idct_func, mts_idct_cuda);
   return ok;
 }
 
@@ -410,8 +360,8 @@ int uvg_strategy_register_intra_cuda(void *opaque, uint8_t bitdepth)
 {
   if (!device_ready(bitdepth)) return 0;
   int ok = 1;
-  REG("angular_pred", angular_pred_cuda); REG("intra_pred_planar", intra_pred_planar_cuda);
-  REG("pdpc_planar_dc", pdpc_planar_dc_cuda);
+  REG("angular_pred", angular_pred_func, angular_pred_cuda); REG("intra_pred_planar", intra_pred_planar_func, intra_pred_planar_cuda);
+  REG("pdpc_planar_dc", pdpc_planar_dc_func, pdpc_planar_dc_cuda);
   return ok;
 }
 
@@ -419,22 +369,18 @@ int uvg_strategy_register_ipol_cuda(void *opaque, uint8_t bitdepth)
 {
   if (!device_ready(bitdepth)) return 0;
   int ok = 1;
-  REG("sample_quarterpel_luma", sample_quarterpel_luma_cuda); REG("sample_quarterpel_luma_hi", sample_quarterpel_luma_hi_cuda);
-  REG("sample_octpel_chroma", sample_octpel_chroma_cuda); REG("sample_octpel_chroma_hi", sample_octpel_chroma_hi_cuda);
-  REG("filter_hpel_blocks_hor_ver_luma", filter_hpel_blocks_hor_ver_luma_cuda);
-  REG("filter_hpel_blocks_diag_luma", filter_hpel_blocks_diag_luma_cuda);
-  REG("filter_qpel_blocks_hor_ver_luma", filter_qpel_blocks_hor_ver_luma_cuda);
-  REG("filter_qpel_blocks_diag_luma", filter_qpel_blocks_diag_luma_cuda);
+  REG("sample_quarterpel_luma", uvg_sample_quarterpel_luma_func, sample_quarterpel_luma_cuda); REG("sample_quarterpel_luma_hi", uvg_sample_quarterpel_luma_hi_func, sample_quarterpel_luma_hi_cuda);
+  REG("sample_octpel_chroma", uvg_sample_octpel_chroma_func, sample_octpel_chroma_cuda); REG("sample_octpel_chroma_hi", uvg_sample_octpel_chroma_hi_func, sample_octpel_chroma_hi_cuda);
+  REG("filter_hpel_blocks_hor_ver_luma", ipol_blocks_func, filter_hpel_blocks_hor_ver_luma_cuda);
+  REG("filter_hpel_blocks_diag_luma", ipol_blocks_func, filter_hpel_blocks_diag_luma_cuda);
+  REG("filter_qpel_blocks_hor_ver_luma", ipol_blocks_func, filter_qpel_blocks_hor_ver_luma_cuda);
+  REG("filter_qpel_blocks_diag_luma", ipol_blocks_func, filter_qpel_blocks_diag_luma_cuda);
   /* get_extended_block(_wraparound): pure memcpy / border replication on the host side, left alone */
   return ok;
 }
 
 /* quant_cbcr_residual (JCCR, strategies-quant.h:62-80): the plain chain is one fused kernel over both chroma
- * planes. With LFNST, RDOQ or dep-quant in play (tools of the encoder proper) the call is
- * forwarded to the implementation the reference registered for this type - its composite then runs transform /
- * quant / dequant through the strategy table, i.e. on the cuda leaves. */
-static quant_cbcr_func *ref_quant_cbcr_residual;
-
+ * planes; with LFNST, RDOQ, dep-quant, LMCS or scaling lists in play the call is forwarded. */
 static unsigned quant_cbcr_residual_cuda(encoder_state_t *const state, const cu_info_t *const cur_cu, const int width,
                                          const int height, const coeff_scan_order_t scan_order, const int in_stride,
                                          const int out_stride, const uvg_pixel *const u_ref_in,
@@ -446,37 +392,50 @@ static unsigned quant_cbcr_residual_cuda(encoder_state_t *const state, const cu_
   const encoder_control_t *const enc = state->encoder_control;
   const uint8_t lfnst_idx = tree_type == UVG_CHROMA_T ? cur_cu->cr_lfnst_idx : cur_cu->lfnst_idx;
   const bool rdoq = enc->cfg.rdoq_enable && (width > 4 || !enc->cfg.rdoq_skip);
-  if (lfnst_idx || rdoq || enc->cfg.dep_quant) {
-    if (!ref_quant_cbcr_residual) unsupported("quant_cbcr_residual with LFNST / RDOQ / dep-quant");
+  const bool lmcs = state->tile->frame->lmcs_aps->m_sliceReshapeInfo.enableChromaAdj;
+  if (lfnst_idx || rdoq || enc->cfg.dep_quant || lmcs || scaling_lists_on(enc))
     return ref_quant_cbcr_residual(state, cur_cu, width, height, scan_order, in_stride, out_stride, u_ref_in, v_ref_in,
                                    u_pred_in, v_pred_in, u_rec_out, v_rec_out, coeff_out, early_skip, lmcs_chroma_adj,
                                    tree_type);
-  }
   uvg_b200_quant_cfg c;
-  fill_cfg(state, &c);
+  fill_cfg(state, cur_cu, &c);
   return (unsigned)B200(quant_cbcr_residual)(&c, cur_cu->type, cur_cu->tr_idx, width, height, cur_cu->joint_cb_cr,
                                              state->frame->jccr_sign ? 1 : 0, in_stride, out_stride, u_ref_in, v_ref_in,
                                              u_pred_in, v_pred_in, u_rec_out, v_rec_out, coeff_out, early_skip);
+}
+
+/* Highest-priority implementation of `type` registered so far that is not ours. */
+static void *registered_before_us(const strategy_list_t *const list, const char *type)
+{
+  void *f = NULL;
+  unsigned best = 0;
+  for (unsigned i = 0; i < list->count; ++i) {
+    const strategy_t *const st = &list->strategies[i];
+    if (!strcmp(st->type, type) && strcmp(st->strategy_name, STRATEGY_NAME) && (!f || st->priority >= best)) {
+      f = st->fptr;
+      best = st->priority;
+    }
+  }
+  return f;
 }
 
 int uvg_strategy_register_quant_cuda(void *opaque, uint8_t bitdepth)
 {
   if (!device_ready(bitdepth)) return 0;
   int ok = 1;
-  /* the reference's own quant_cbcr_residual (highest priority registered so far) for the forwarded cases */
   const strategy_list_t *const list = (const strategy_list_t *)opaque;
-  unsigned best = 0;
-  for (unsigned i = 0; i < list->count; ++i) {
-    const strategy_t *const st = &list->strategies[i];
-    if (!strcmp(st->type, "quant_cbcr_residual") && strcmp(st->strategy_name, STRATEGY_NAME) &&
-        (!ref_quant_cbcr_residual || st->priority >= best)) {
-      ref_quant_cbcr_residual = (quant_cbcr_func *)st->fptr;
-      best = st->priority;
-    }
+  ref_quant = (quant_func *)registered_before_us(list, "quant");
+  ref_dequant = (dequant_func *)registered_before_us(list, "dequant");
+  ref_quantize_residual = (quant_residual_func *)registered_before_us(list, "quantize_residual");
+  ref_quant_cbcr_residual = (quant_cbcr_func *)registered_before_us(list, "quant_cbcr_residual");
+  if (!ref_quant || !ref_dequant || !ref_quantize_residual || !ref_quant_cbcr_residual) {
+    /* fail at registration, never mid-encode */
+    fprintf(stderr, "uvg266_b200: the reference's quant strategies must be registered before the cuda ones\n");
+    return 0;
   }
-  REG("quant", quant_cuda); REG("dequant", dequant_cuda);
-  REG("quantize_residual", quantize_residual_cuda);
-  REG("quant_cbcr_residual", quant_cbcr_residual_cuda);
-  REG("coeff_abs_sum", coeff_abs_sum_cuda); REG("fast_coeff_cost", fast_coeff_cost_cuda);
+  REG("quant", quant_func, quant_cuda); REG("dequant", dequant_func, dequant_cuda);
+  REG("quantize_residual", quant_residual_func, quantize_residual_cuda);
+  REG("quant_cbcr_residual", quant_cbcr_func, quant_cbcr_residual_cuda);
+  REG("coeff_abs_sum", coeff_abs_sum_func, coeff_abs_sum_cuda); REG("fast_coeff_cost", fast_coeff_cost_func, fast_coeff_cost_cuda);
   return ok;
 }
