@@ -39,6 +39,20 @@ TUS = [(4, 240), (8, 120), (16, 24), (32, 5)]  # (n, TUs per CTU)
 QP = 27
 COST_WEIGHTS = (28 << 0) | (300 << 16) | (700 << 32) | (1100 << 48)   # Q8.8 weights, fast_coeff_cost
 METRIC = "CTUs/s at 3840x2160 8-bit all-intra hot path (distortion+transform+quant)"
+# frame pass (the end-to-end workload of both arms): rough levels and their candidate modes, candidates kept
+FRAME_LEVELS = [(8, list(range(0, 67, 3))), (16, list(range(0, 67, 3)) + [1])]     # 23 / 24 modes, as ROUGH
+FRAME_NBEST = 2
+
+
+def config_dict(n_ctu_per_gpu):
+    """The same dictionary in both arms (the driver compares them)."""
+    return {"workload": "ctu_pass 3840x2160 8-bit all-intra (per-CTU op mix of uvg266 ultrafast): rough 64x(8x8,23 modes)"
+                        "+16x(16x16,24 modes); TUs 240x4x4+120x8x8+24x16x16+5x32x32",
+            "e2e_workload": "frame_pass: the same op mix from the source plane alone - intra prediction of every candidate "
+                            "(open-loop reference samples), cost, 2 best modes, TU prediction + quantize_residual + ssd + "
+                            "coefficient cost; host buffers in, results out",
+            "ctus_per_step_per_gpu": n_ctu_per_gpu, "qp": QP, "sharding": "CTU-row bands, no collective",
+            "l2": "inputs 664 MB per step >> 126 MB L2, no flush"}
 
 
 def bytes_per_ctu():
@@ -167,6 +181,36 @@ def host_cores():
     return n
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and therefore the pinned host buffers it first-touches) to the NUMA node its GPU hangs
+    off. Without it 8 ranks land wherever the launcher put them and the H2D/D2H copies of half the GPUs cross
+    the socket interconnect (r1: per-GPU H2D 47.7 -> 37.0 GB/s at N=8)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            busid = out.lower()[-12:]                      # 00000000:1B:00.0 -> 0000:1b:00.0
+        else:
+            dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+            dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+            busid = "%04x:%02x:%02x.0" % (dom, bus, dev)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % busid).read())
+        if node < 0:
+            return {"node": None, "why": "no NUMA affinity reported"}
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed), "bus": busid}
+    except Exception as exc:                               # binding is an optimisation, never a failure
+        return {"node": None, "why": str(exc)[:100]}
+
+
 class CpuArm:
     """Runs the ctu_pass on `n_ctu` CTUs with the reference's own leaf functions."""
 
@@ -210,6 +254,46 @@ class CpuArm:
                                            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
 
+    def frame_setup(self, ctu_rows):
+        """Buffers for the frame pass (the e2e workload) over the first `ctu_rows` CTU rows of the synthetic picture."""
+        class RefFrameLevel(C.Structure):
+            _fields_ = [("n", C.c_int), ("k", C.c_int), ("modes", C.c_int8 * 68)]
+        self.f_rows = ctu_rows
+        self.f_plane = synth_plane_rows([(0, r) for r in range(CTU_ROWS)])
+        n_ctu = ctu_rows * CTU_COLS
+        self.f_nctu = n_ctu
+        lv = (RefFrameLevel * len(FRAME_LEVELS))()
+        for i, (n, modes) in enumerate(FRAME_LEVELS):
+            lv[i].n, lv[i].k = n, len(modes)
+            for j, m in enumerate(modes):
+                lv[i].modes[j] = m
+        self.f_lv = lv
+        self.f_tu = (RefLevel * len(TUS))(*[RefLevel(n, c, 0) for (n, c) in TUS])
+        fa = dict(cost=[np.zeros(n_ctu * (CTU // n) ** 2 * len(m), np.uint32) for (n, m) in FRAME_LEVELS],
+                  best=[np.zeros(n_ctu * (CTU // n) ** 2 * FRAME_NBEST, np.uint8) for (n, m) in FRAME_LEVELS],
+                  mode=[np.zeros(n_ctu * c, np.uint8) for (n, c) in TUS], has=[np.zeros(n_ctu * c, np.uint8) for (n, c) in TUS],
+                  ssd=[np.zeros(n_ctu * c, np.uint32) for (n, c) in TUS], tcost=[np.zeros(n_ctu * c, np.uint32) for (n, c) in TUS],
+                  coeff=[np.zeros(n_ctu * c * n * n, np.int16) for (n, c) in TUS],
+                  rec=[np.zeros(n_ctu * c * n * n, np.uint8) for (n, c) in TUS])
+        self.f_arrays = fa
+
+        def parr(lst):
+            a = (C.c_void_p * len(lst))(*[x.ctypes.data for x in lst])
+            self.keep.append(a)
+            return a
+        self.f_args = {k: parr(v) for k, v in fa.items()}
+        H = self.R.H
+        H.refh_frame_pass.restype = C.c_double
+        H.refh_frame_pass.argtypes = [C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + \
+                                     [C.c_void_p] * 6 + [C.c_uint64]
+
+    def frame_run(self, threads):
+        """Seconds for one frame pass over self.f_nctu CTUs with the unmodified reference's functions."""
+        a = self.f_args
+        return self.R.H.refh_frame_pass(threads, self.f_plane.ctypes.data, FRAME_W, CTU_ROWS * CTU, FRAME_W, 0, self.f_nctu,
+                                        len(FRAME_LEVELS), self.f_lv, a["cost"], a["best"], len(TUS), self.f_tu, FRAME_NBEST,
+                                        a["mode"], a["has"], a["ssd"], a["tcost"], a["coeff"], a["rec"], COST_WEIGHTS)
+
     def run(self, threads):
         (ro, rp, rc), (tr, tp, trec, tco, tss, tcs) = self.args
         return self.R.H.refh_ctu_pass(self.strategy, threads, self.n_ctu, len(ROUGH), self.rough, ro, rp, rc,
@@ -228,16 +312,27 @@ def reference_arm(args):
     t = [arm.run(cores) for _ in range(args.steps)]
     total = sum(t)
     v = n_ctu * args.steps / total
+    # the end-to-end workload (frame pass: prediction + cost + selection + residual chain from the source plane)
+    frows = max(1, min(CTU_ROWS, args.ref_frame_rows))
+    arm.frame_setup(frows)
+    arm.frame_run(cores)
+    fsteps = max(3, min(args.steps, 10))
+    ft = [arm.frame_run(cores) for _ in range(fsteps)]
+    fv = arm.f_nctu * fsteps / sum(ft)
     line = {
         "metric": METRIC, "value": v, "unit": "CTU/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "ctu_pass 3840x2160 8-bit all-intra (per-CTU op mix of uvg266 ultrafast)",
-                   "sample_ctus_per_step": n_ctu, "qp": QP},
+        "config": config_dict(2040),
         "cpu_baseline": {"value": v, "unit": "CTU/s", "cores": cores, "kind": arm.kind,
                          "sample": "%d CTUs per step x %d steps, generic-C strategies of the unmodified "
                                    "reference (oracle/_ref), %d pthreads" % (n_ctu, args.steps, cores)},
-        "e2e": {"value": v, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # e2e = the frame pass (see config.e2e_workload), the same work the GPU arm's e2e does from host buffers;
+        # `value` = the ctu_pass kernel step (predictions given), the same work as the GPU arm's `value`
+        "e2e": {"value": fv, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "workload": "frame_pass", "sample": "%d CTUs (%d CTU rows of the 4K picture) x %d passes, %d pthreads, "
+                "uvg_intra_predict + satd/sad duals + quantize_residual + ssd + fast_coeff_cost of the unmodified reference"
+                % (arm.f_nctu, frows, fsteps, cores), "ms_per_pass": 1e3 * sum(ft) / fsteps},
         "gpu_launches": 0,
     }
     emit(line)
@@ -258,6 +353,7 @@ def gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the uvg266_b200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"node": None, "why": "--no-numa-bind"}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     U.init(local_rank)
@@ -400,8 +496,11 @@ def gpu_arm(args):
                 except Exception as exc:  # reported, never silently replaced
                     extra["e2e_predict_on_device"] = {"unavailable": str(exc)}
 
-    # ---- e2e: the same step through the host-buffer C-ABI entry points (pinned host memory) ----
-    e2e = e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, dev)
+    # ---- e2e: the frame pass through the C ABI from host buffers (H2D of the source plane and D2H of every result
+    # inside the timed region); e2e_v1 = round 1's step (candidate predictions uploaded), kept for comparison ----
+    e2e = e2e_frame(torch, U, L, rank, world, args, barrier, dist, dev)
+    e2e["numa"] = numa
+    e2e_v1 = None if args.no_e2e_v1 else e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, dev)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -418,6 +517,12 @@ def gpu_arm(args):
                                       "4-CTU work units" % (arm.n_ctu, cores)}
             s1 = arm.run(1)
             cpu_baseline["value_1thread"] = arm.n_ctu / s1
+            # the e2e workload on the same host threads (bounded sample: a quarter of the picture)
+            arm.frame_setup(max(1, CTU_ROWS // 4))
+            arm.frame_run(cores)
+            fr = [arm.frame_run(cores) for _ in range(3)]
+            cpu_baseline["frame_pass"] = {"value": arm.f_nctu * len(fr) / sum(fr), "unit": "CTU/s", "cores": cores,
+                                          "sample": "%d CTUs x %d passes" % (arm.f_nctu, len(fr))}
         except Exception as exc:  # reported, never silently replaced
             cpu_baseline = {"value": None, "unit": "CTU/s", "cores": host_cores(), "kind": "reference",
                             "sample": "unavailable: %s" % exc}
@@ -427,12 +532,10 @@ def gpu_arm(args):
             "metric": METRIC, "value": value, "unit": "CTU/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "ctu_pass 3840x2160 8-bit all-intra (per-CTU op mix of uvg266 ultrafast): "
-                                   "rough 64x(8x8,23 modes)+16x(16x16,24 modes); TUs 240x4x4+120x8x8+24x16x16+5x32x32",
-                       "ctus_per_step_per_gpu": n_ctu, "qp": QP, "sharding": "CTU-row bands, no collective",
-                       "l2": "inputs %.0f MB per step >> 126 MB L2, no flush" % (step_bytes / 1e6),
-                       "algorithmic_bytes_per_step": step_bytes},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches) * world,
+            "config": config_dict(n_ctu),
+            "algorithmic_bytes_per_step": step_bytes,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_v1": e2e_v1,
+            "gpu_launches": int(launches) * world,
             "clocks": clocks, "step_gbps": step_bytes * args.steps / (ms_max * 1e-3) / 1e9,
         }
         line.update(extra)
@@ -520,9 +623,9 @@ def next_rows_bench(torch, U, L, dev, stream):
 
 
 def pair_bench(torch, U, L, dev, stream, hbm_peak):
-    """N = 2^17 independent 64x64 uint8 block pairs (1 GiB read, >> L2): the north_star's
+    """N = 2^18 independent 64x64 uint8 block pairs (2 GiB read, >> L2): the north_star's
     'SAD/SATD GB/s vs HBM roofline at 64x64' figure. Algorithmic bytes = 2*64*64 + 4 per pair."""
-    n, N = 64, 1 << 17
+    n, N = 64, 1 << 18
     g = torch.Generator(device=dev); g.manual_seed(1234)
     a = torch.randint(0, 256, (N * n * n,), dtype=torch.uint8, device=dev, generator=g)
     b = torch.randint(0, 256, (N * n * n,), dtype=torch.uint8, device=dev, generator=g)
@@ -535,6 +638,96 @@ def pair_bench(torch, U, L, dev, stream, hbm_peak):
         nbytes = N * (2 * n * n + 4)
         res[name] = {"ms": ms, "gbps": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / hbm_peak, "pairs": N}
     return res
+
+
+def e2e_frame(torch, U, L, rank, world, args, barrier, dist, dev):
+    """End to end through the frame-pipeline C ABI: every step hands the library a source picture in pinned HOST
+    memory (uvg_b200_frame_submit: H2D of the plane, all kernels, D2H of costs / candidate lists / per-TU results /
+    compact coefficients) and waits for the results in host memory (uvg_b200_frame_wait). `inflight` frame objects
+    alternate, like an encoder with --owf frames in flight, so one picture's D2H overlaps the next one's kernels.
+    Weak scaling: every rank processes its own pictures."""
+    H = CTU_ROWS * CTU
+    n_ctu = CTU_COLS * CTU_ROWS
+    inflight = max(1, args.e2e_inflight)
+    cfg = U.FrameCfg.make(FRAME_W, H, FRAME_LEVELS, TUS, FRAME_NBEST, U.QuantCfg.make(QP, 8, 1, 0, 0), COST_WEIGHTS)
+    frames, planes = [], []
+    for i in range(inflight):
+        f = L.uvg_b200_frame_create(C.byref(cfg))
+        if not f:
+            raise RuntimeError("uvg_b200_frame_create: " + L.uvg_b200_last_error().decode())
+        frames.append(f)
+        hp = torch.empty((H, FRAME_W), dtype=torch.uint8, pin_memory=True)
+        hp.copy_(torch.from_numpy(synth_plane_rows([(rank * inflight + i, r) for r in range(CTU_ROWS)])))
+        planes.append(hp)
+    res = U.FrameResult()
+    k = max(3, min(args.steps, args.e2e_steps))
+    d2h = [0]
+
+    def run(steps):
+        pending = []
+        for s_ in range(steps):
+            i = s_ % inflight
+            if len(pending) == inflight:
+                U.check(L.uvg_b200_frame_wait(pending.pop(0), C.byref(res)))
+            U.check(L.uvg_b200_frame_submit(frames[i], planes[i].data_ptr(), FRAME_W, 0, 0, 0))
+            pending.append(frames[i])
+        while pending:
+            U.check(L.uvg_b200_frame_wait(pending.pop(0), C.byref(res)))
+    run(inflight + 1)
+    # bytes that cross the link per picture: counted from what the result describes
+    fixed = sum(n_ctu * (CTU // n) ** 2 * (len(m) * 4 + FRAME_NBEST) for (n, m) in FRAME_LEVELS) + \
+        sum(n_ctu * c * (1 + 1 + 4 + 4 + 4) + (n_ctu * c * n * n + 31) // 32 * 4 for (n, c) in TUS) + 4
+    nnz = int(res.n_levels)
+    d2h_bytes = fixed + nnz * 2
+    launches0 = L.uvg_b200_launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    run(k)
+    barrier()
+    secs = time.perf_counter() - t0
+    launches = L.uvg_b200_launch_count() - launches0
+    t = torch.tensor([secs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    # one picture at a time (latency) and the device-resident pass (no copies) for the breakdown
+    t0 = time.perf_counter()
+    for _ in range(3):
+        U.check(L.uvg_b200_frame_submit(frames[0], planes[0].data_ptr(), FRAME_W, 0, 0, 0))
+        U.check(L.uvg_b200_frame_wait(frames[0], C.byref(res)))
+    lat_ms = (time.perf_counter() - t0) / 3 * 1e3
+    dev_ms = []
+    for _ in range(5):
+        U.check(L.uvg_b200_frame_submit(frames[0], None, FRAME_W, 0, 0, U.FRAME_NO_H2D | U.FRAME_NO_D2H))
+        U.check(L.uvg_b200_frame_wait(frames[0], C.byref(res)))
+        dev_ms.append(res.device_ms)
+    probe = pcie_probe(torch, dev)
+    for f in frames:
+        L.uvg_b200_frame_destroy(f)
+    return {"value": n_ctu * world * k / secs, "unit": "CTU/s", "workload": "frame_pass", "h2d_bytes_per_step": FRAME_W * H,
+            "d2h_bytes_per_step": d2h_bytes, "d2h_dense_equivalent_bytes": fixed + sum(n_ctu * c * n * n * 2 for (n, c) in TUS),
+            "nonzero_coefficients_per_step": nnz, "steps": k, "ms_per_step": 1e3 * secs / k,
+            "frames_in_flight": inflight, "latency_ms_one_frame": lat_ms, "device_ms_resident": float(np.median(dev_ms)),
+            "launches_per_step": int(launches) // k, "pcie_probe": probe,
+            "api": "uvg_b200_frame_submit + uvg_b200_frame_wait (pinned host source plane; results in host memory)"}
+
+
+def pcie_probe(torch, dev):
+    """What the link itself does on this box (one 256 MiB pinned copy per direction, best of 3): the ceiling for e2e."""
+    probe = {}
+    try:
+        hb = torch.empty(1 << 28, dtype=torch.uint8, pin_memory=True); db = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+        for name, (dst, src) in (("h2d_gbs", (db, hb)), ("d2h_gbs", (hb, db))):
+            best = 0.0
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); dst.copy_(src, non_blocking=True); b.record(); torch.cuda.synchronize()
+                best = max(best, (1 << 28) / (a.elapsed_time(b) * 1e-3) / 1e9)
+            probe[name] = round(best, 1)
+        del hb, db
+    except RuntimeError:
+        pass
+    return probe
 
 
 def e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, dev):
@@ -606,7 +799,7 @@ def e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, d
 
     def step():
         list(pool.map(work, range(T)))
-    k = max(3, min(args.steps, args.e2e_steps))
+    k = max(3, min(args.steps, args.e2e_steps, 5))
     for _ in range(2):
         step()
     barrier()
@@ -619,20 +812,7 @@ def e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, d
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     secs = float(t.item())
-    # what the link itself does on this box (one 256 MiB pinned copy per direction, best of 3): the ceiling for e2e
     probe = {}
-    try:
-        hb = torch.empty(1 << 28, dtype=torch.uint8, pin_memory=True); db = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
-        for name, (dst, src) in (("h2d_gbs", (db, hb)), ("d2h_gbs", (hb, db))):
-            best = 0.0
-            for _ in range(3):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); dst.copy_(src, non_blocking=True); b.record(); torch.cuda.synchronize()
-                best = max(best, (1 << 28) / (a.elapsed_time(b) * 1e-3) / 1e9)
-            probe[name] = round(best, 1)
-        del hb, db
-    except RuntimeError:
-        pass
     return {"value": n_ctu * world * k / secs, "unit": "CTU/s", "h2d_bytes_per_step": int(h2d), "pcie_probe": probe,
             "h2d_gbs_in_e2e": round(h2d / (secs / k) / 1e9, 1),
             "d2h_bytes_per_step": int(d2h), "steps": k, "ms_per_step": 1e3 * secs / k,
@@ -648,11 +828,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-ctus", type=int, default=2040, help="CTUs per step of the reference arm")
     ap.add_argument("--cpu-ctus", type=int, default=2040, help="CTUs of the cpu_baseline sample")
+    ap.add_argument("--ref-frame-rows", type=int, default=CTU_ROWS, help="CTU rows per pass of the reference frame pass")
+    ap.add_argument("--e2e-inflight", type=int, default=2, help="frame objects in flight in the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the *_host calls")
     ap.add_argument("--e2e-order", default="interleaved", choices=["interleaved", "sequential"],
                     help="order of the independent *_host calls inside a host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--no-e2e-v1", action="store_true", help="skip the round-1 e2e step (predictions uploaded)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

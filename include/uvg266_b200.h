@@ -283,6 +283,116 @@ UVG_B200_API int uvg_b200_quantize_residual_host(const uvg_b200_quant_cfg *cfg, 
                                                  uint32_t *ssd, uint32_t *cost,
                                                  uint64_t cost_weights, size_t n_tus);
 
+/* ---------------------------------------------------------------------------------- */
+/* (4) Frame pipeline: the batched call site, device-resident        */
+/* ---------------------------------------------------------------------------------- */
+/* What the encoder does per CTU of an all-intra picture, for a whole picture (or a band of CTU rows) per call:
+ *   search_intra_rough (search_intra.c:986-1062): every n x n block of every rough level is predicted with the level's
+ *     k candidate modes and scored cost = min(SATD, 2 SAD) (get_cost, search_intra.c:133-192);
+ *   mode selection (search_intra.c:1064-1105): the n_best cheapest candidates per block, best first, ties in
+ *     candidate order;
+ *   uvg_quantize_lcu_residual (transform.c:1487-1600) for every TU of the configured sizes: intra prediction with the
+ *     TU's mode, quantize_residual (quant-generic.c:460-612), pixels_calc_ssd, fast_coeff_cost.
+ * Only the source plane goes to the device; predictions, residuals, reconstructions stay in HBM. Reference samples
+ * are the SOURCE picture's neighbouring samples (open loop; border replication outside the picture).
+ *
+ * Addressing (all arrays): CTU-major, index = (ctu - ctu_begin) * per_ctu + j; CTUs in raster order, 64x64, the
+ * picture padded to whole CTUs by border replication. A rough level has (64/n)^2 blocks per CTU, j = raster position
+ * in the CTU. TU j of a CTU sits at raster position j % (64/n)^2 and is visit r = j / (64/n)^2 of that position
+ * (the encoder's RDO revisits positions): it is predicted with candidate min(r, n_best-1) of the covering block of
+ * the smallest rough level that is at least as large as the TU (else the largest level). */
+#define UVG_B200_FRAME_MAX_LEVELS 4
+typedef struct uvg_b200_frame_level { int32_t n; int32_t k; int8_t modes[68]; } uvg_b200_frame_level;
+typedef struct uvg_b200_frame_tu { int32_t n; int32_t per_ctu; } uvg_b200_frame_tu;
+typedef struct uvg_b200_frame_cfg {
+  int32_t width, height;            /* luma plane, pixels                                              */
+  int32_t bitdepth;                 /* 8                                                               */
+  int32_t n_levels;                 /* rough-search levels, n in {8, 16, 32}                           */
+  uvg_b200_frame_level level[UVG_B200_FRAME_MAX_LEVELS];
+  int32_t n_tus;                    /* TU sizes of the residual pass, n in {4, 8, 16, 32}              */
+  uvg_b200_frame_tu tu[UVG_B200_FRAME_MAX_LEVELS];
+  int32_t n_best;                   /* candidates kept per rough block, 1..4                           */
+  uvg_b200_quant_cfg quant;         /* as for uvg_b200_quantize_residual_dev                           */
+  uint64_t cost_weights;            /* fast_coeff_cost weights                                         */
+} uvg_b200_frame_cfg;
+
+/* Results of one pass: HOST pointers into pinned buffers owned by the frame object, valid until the next submit.
+ * Coefficients come back compact: tu_sig[i] is a bit array over the dense [n_tus][n*n] coefficient array of TU size
+ * i (coefficient g = bit (g & 31) of word g >> 5), `levels` holds the non-zero coefficients of all TUs (sizes in
+ * configuration order, TUs in index order, coefficients in index order) and tu_level_off[i][t] is where TU t's
+ * begin. uvg_b200_frame_expand_coeffs rebuilds the dense array. tu_coeff_dense is set only with
+ * UVG_B200_FRAME_DENSE_COEFF. */
+typedef struct uvg_b200_frame_result {
+  int32_t ctu_begin, ctu_end;
+  const uint32_t *rough_cost[UVG_B200_FRAME_MAX_LEVELS];   /* [blocks][k]                                */
+  const uint8_t *rough_best[UVG_B200_FRAME_MAX_LEVELS];    /* [blocks][n_best] mode values               */
+  const uint8_t *tu_mode[UVG_B200_FRAME_MAX_LEVELS];       /* [tus] the mode each TU was predicted with  */
+  const uint8_t *tu_has_coeffs[UVG_B200_FRAME_MAX_LEVELS];
+  const uint32_t *tu_ssd[UVG_B200_FRAME_MAX_LEVELS];
+  const uint32_t *tu_cost[UVG_B200_FRAME_MAX_LEVELS];
+  const uint32_t *tu_sig[UVG_B200_FRAME_MAX_LEVELS];
+  const uint32_t *tu_level_off[UVG_B200_FRAME_MAX_LEVELS];
+  const int16_t *tu_coeff_dense[UVG_B200_FRAME_MAX_LEVELS];
+  const int16_t *levels;
+  uint64_t n_levels;                /* non-zero coefficients of the pass                               */
+  float device_ms;                  /* device time of the pass (H2D + kernels; CUDA events)            */
+} uvg_b200_frame_result;
+
+/* Device-side views for callers that keep working on the GPU (reconstruction for the next pictures, tests). */
+typedef struct uvg_b200_frame_device {
+  const void *plane;
+  const uint32_t *rough_cost[UVG_B200_FRAME_MAX_LEVELS];
+  const uint8_t *rough_best[UVG_B200_FRAME_MAX_LEVELS];
+  const void *tu_pred[UVG_B200_FRAME_MAX_LEVELS], *tu_rec[UVG_B200_FRAME_MAX_LEVELS];
+  const int16_t *tu_coeff[UVG_B200_FRAME_MAX_LEVELS];
+  void *stream;
+} uvg_b200_frame_device;
+
+enum {
+  UVG_B200_FRAME_NO_H2D = 1,        /* the source rows are already on the device (previous submit)     */
+  UVG_B200_FRAME_NO_D2H = 2,        /* leave the results on the device                                 */
+  UVG_B200_FRAME_DENSE_COEFF = 4    /* additionally return the dense coefficient arrays                */
+};
+
+typedef struct uvg_b200_frame uvg_b200_frame;
+UVG_B200_API uvg_b200_frame *uvg_b200_frame_create(const uvg_b200_frame_cfg *cfg);   /* NULL on failure */
+UVG_B200_API void uvg_b200_frame_destroy(uvg_b200_frame *f);
+/* Asynchronous: enqueues the H2D copy of the rows the band needs from `src` (host, `src_stride` bytes per row; pinned
+ * memory makes the copy asynchronous), the kernels and the D2H copies on the object's own streams and returns.
+ * CTU rows [ctu_row_begin, ctu_row_end); ctu_row_end <= 0 means "to the last row". One pass in flight per object;
+ * several objects (pictures, or bands of one picture on several GPUs) run concurrently. */
+UVG_B200_API int uvg_b200_frame_submit(uvg_b200_frame *f, const void *src, size_t src_stride,
+                                       int ctu_row_begin, int ctu_row_end, int flags);
+/* Blocks until the pass has finished and its results are in host memory. */
+UVG_B200_API int uvg_b200_frame_wait(uvg_b200_frame *f, uvg_b200_frame_result *out);
+UVG_B200_API int uvg_b200_frame_device_buffers(uvg_b200_frame *f, uvg_b200_frame_device *out);
+/* Synchronous device -> host copy of `bytes` bytes from a pointer handed out by uvg_b200_frame_device_buffers. */
+UVG_B200_API int uvg_b200_device_read(void *host_dst, const void *dev_src, size_t bytes);
+UVG_B200_API void uvg_b200_frame_expand_coeffs(const uint32_t *sig, const uint32_t *level_off,
+                                               const int16_t *levels, int coeffs_per_tu, size_t n_tus,
+                                               int16_t *dense);
+
+/* ---------------------------------------------------------------------------------- */
+/* (5) Multi-GPU: the reference-picture exchange                       */
+/* ---------------------------------------------------------------------------------- */
+/* A picture is sharded across GPUs by CTU-row bands (one process per GPU). All-intra pictures need no communication.
+ * For inter pictures every GPU must hold the whole reconstructed reference picture before the next picture's motion
+ * search while it only reconstructs its own band: one broadcast per band, issued as ONE NCCL group over NVLink, in
+ * place on the picture buffer. NCCL is bound at run time (libnccl.so.2); nothing of NCCL appears in this ABI.
+ * Bootstrap: rank 0 calls uvg_b200_comm_unique_id and hands the 128 bytes to every rank through the host
+ * application's own channel; every rank then calls uvg_b200_comm_create (collective). */
+#define UVG_B200_COMM_ID_BYTES 128
+typedef struct uvg_b200_comm uvg_b200_comm;
+UVG_B200_API void uvg_b200_band_rows(int rank, int world, int ctu_rows, int *lo, int *hi);
+UVG_B200_API int uvg_b200_comm_unique_id(void *id_out /* UVG_B200_COMM_ID_BYTES */);
+UVG_B200_API uvg_b200_comm *uvg_b200_comm_create(const void *id, int rank, int world);   /* NULL on failure */
+UVG_B200_API void uvg_b200_comm_destroy(uvg_b200_comm *c);
+UVG_B200_API int uvg_b200_comm_nccl_version(void);                                       /* 0: NCCL not available */
+/* plane: DEVICE pointer, `stride_bytes` per pixel row, `height` pixel rows; band r = CTU rows uvg_b200_band_rows(r).
+ * Asynchronous on `stream`. */
+UVG_B200_API int uvg_b200_refpic_exchange(uvg_b200_comm *c, void *plane, size_t stride_bytes, int height,
+                                          void *stream);
+
 /* Pinned host memory for callers that want the fast H2D path (optional). */
 UVG_B200_API void *uvg_b200_host_alloc(size_t bytes);
 UVG_B200_API void uvg_b200_host_free(void *p);

@@ -477,6 +477,7 @@ typedef struct {
   int *next_unit;                       /* shared work counter */
   int pin_cpu;                          /* unused */
   int static_threads, worker_id;        /* static_threads > 0: static CTU slices */
+  const struct frame_job *fj;           /* non-NULL: frame pass instead of the ctu_pass */
 } refh_job_t;
 
 /* Work is handed out dynamically: unit u = (level, chunk of CTU_CHUNK CTUs), popped from one
@@ -546,9 +547,140 @@ static void ctu_pass_range(refh_job_t *j, int level, int c0, int c1)
   }
 }
 
+/* ------------------------------------------------------------------------------------
+ * Frame pass: the CPU arm of the device-resident frame pipeline (uvg_b200_frame_*, include/uvg266_b200.h
+ * section 4), run with the reference's own functions - the same per-CTU work, the same open-loop reference
+ * samples (source-picture neighbours, border replication), the same CTU-major output layout:
+ *   rough search  : uvg_intra_predict for the level's candidate modes, two at a time into a pred_buffer like
+ *                   search_intra_rough (search_intra.c:1012-1062), cost = MIN(satd, 2 * sad) from the dual functions
+ *   selection     : the n_best cheapest candidates, ties in candidate order
+ *   residual pass : uvg_intra_predict with the TU's mode -> quantize_residual -> pixels_calc_ssd -> fast_coeff_cost
+ * ---------------------------------------------------------------------------------- */
+typedef struct { int n, k; int8_t modes[68]; } refh_frame_level_t;
+
+typedef struct frame_job {
+  const uvg_pixel *plane; int W, H, stride, ctu_cols, ctu_begin, ctu_end;
+  int n_levels; const refh_frame_level_t *levels;
+  uint32_t *const *rough_cost; uint8_t *const *rough_best;
+  int n_tus; const refh_level_t *tus; int n_best;
+  uint8_t *const *tu_mode; uint8_t *const *tu_has; uint32_t *const *tu_ssd; uint32_t *const *tu_cost;
+  int16_t *const *tu_coeff; uvg_pixel *const *tu_rec;
+  uint64_t weights;
+} frame_job_t;
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+static void frame_refs(const frame_job_t *f, int X, int Y, int n, uvg_intra_references *refs)
+{
+  memset(refs, 0, sizeof(*refs));
+  for (int i = 0; i < 3 * n + 3; ++i) {
+    const int k = i < 2 * n ? i : 2 * n;              /* the rows continue with the last sample, intra.c:879-886 */
+    refs->ref.top[i] = f->plane[(size_t)clampi(Y - 1, 0, f->H - 1) * f->stride + clampi(X - 1 + k, 0, f->W - 1)];
+    refs->ref.left[i] = f->plane[(size_t)clampi(Y - 1 + k, 0, f->H - 1) * f->stride + clampi(X - 1, 0, f->W - 1)];
+  }
+}
+
+static void frame_block(const frame_job_t *f, int X, int Y, int n, uvg_pixel *dst)
+{
+  for (int y = 0; y < n; ++y)
+    for (int x = 0; x < n; ++x)
+      dst[y * n + x] = f->plane[(size_t)MIN(Y + y, f->H - 1) * f->stride + MIN(X + x, f->W - 1)];
+}
+
+static void frame_ctu(const frame_job_t *f, int ctu)
+{
+  const int cx = (ctu % f->ctu_cols) * LCU_WIDTH, cy = (ctu / f->ctu_cols) * LCU_WIDTH;
+  const int rel = ctu - f->ctu_begin;
+  uvg_intra_references refs;
+  ALIGNED(64) uvg_pixel preds[2][32 * 32];
+  ALIGNED(64) uvg_pixel orig[32 * 32];
+  intra_search_data_t data;
+  memset(&data, 0, sizeof(data));
+  data.pred_cu.type = CU_INTRA;
+  for (int l = 0; l < f->n_levels; ++l) {
+    const int n = f->levels[l].n, k = f->levels[l].k, bpr = LCU_WIDTH / n, ppc = bpr * bpr;
+    cost_pixel_nxn_multi_func *satd = uvg_pixels_get_satd_dual_func(n, n);
+    cost_pixel_nxn_multi_func *sad = uvg_pixels_get_sad_dual_func(n, n);
+    cu_loc_t loc;
+    uvg_cu_loc_ctor(&loc, 0, 0, n, n);
+    data.pred_cu.log2_width = data.pred_cu.log2_height = uvg_g_convert_to_log2[n];
+    for (int j = 0; j < ppc; ++j) {
+      const int X = cx + (j % bpr) * n, Y = cy + (j / bpr) * n;
+      const size_t b = (size_t)rel * ppc + j;
+      frame_refs(f, X, Y, n, &refs);
+      frame_block(f, X, Y, n, orig);
+      uint32_t *cost = f->rough_cost[l] + b * k;
+      for (int m = 0; m < k; m += 2) {
+        const int m1 = m + 1 < k ? m + 1 : m;
+        data.pred_cu.intra.mode = f->levels[l].modes[m];
+        uvg_intra_predict(g_state, &refs, &loc, &loc, COLOR_Y, preds[0], &data, NULL);
+        data.pred_cu.intra.mode = f->levels[l].modes[m1];
+        uvg_intra_predict(g_state, &refs, &loc, &loc, COLOR_Y, preds[1], &data, NULL);
+        unsigned s[2], t[2];
+        satd((const pred_buffer)preds, orig, 2, s);
+        sad((const pred_buffer)preds, orig, 2, t);
+        cost[m] = MIN(s[0], 2 * t[0]);
+        if (m1 != m) cost[m1] = MIN(s[1], 2 * t[1]);
+      }
+      /* the n_best cheapest, ties in candidate order */
+      uint8_t *best = f->rough_best[l] + b * f->n_best;
+      uint32_t bc[4] = { UINT32_MAX, UINT32_MAX, UINT32_MAX, UINT32_MAX };
+      int bi[4] = { 0, 0, 0, 0 };
+      for (int m = 0; m < k; ++m) {
+        uint32_t c = cost[m];
+        int idx = m;
+        for (int s2 = 0; s2 < f->n_best; ++s2)
+          if (c < bc[s2]) { const uint32_t tc = bc[s2]; const int ti = bi[s2]; bc[s2] = c; bi[s2] = idx; c = tc; idx = ti; }
+      }
+      for (int s2 = 0; s2 < f->n_best; ++s2) best[s2] = (uint8_t)f->levels[l].modes[bi[s2 < k ? s2 : k - 1]];
+    }
+  }
+  quant_residual_func *qr = refh_get("quantize_residual", "generic");
+  pixels_calc_ssd_func *ssd = refh_get("pixels_calc_ssd", "generic");
+  fast_coeff_cost_func *fcc = refh_get("fast_coeff_cost", "generic");
+  cu_info_t cu;
+  fill_cu(&cu, CU_INTRA, 0, 0, 0, 0);
+  for (int i = 0; i < f->n_tus; ++i) {
+    const int n = f->tus[i].n, per_ctu = f->tus[i].count, bpr = LCU_WIDTH / n, ppc = bpr * bpr;
+    int src = -1;                                      /* mode source level: smallest level >= n, else the largest */
+    for (int l = 0; l < f->n_levels; ++l) if (f->levels[l].n >= n && (src < 0 || f->levels[l].n < f->levels[src].n)) src = l;
+    if (src < 0) for (int l = 0; l < f->n_levels; ++l) if (src < 0 || f->levels[l].n > f->levels[src].n) src = l;
+    const int sn = f->levels[src].n, sb = LCU_WIDTH / sn;
+    cu_loc_t loc;
+    uvg_cu_loc_ctor(&loc, 0, 0, n, n);
+    data.pred_cu.log2_width = data.pred_cu.log2_height = uvg_g_convert_to_log2[n];
+    for (int j = 0; j < per_ctu; ++j) {
+      const int p = j % ppc, rank = MIN(j / ppc, f->n_best - 1);
+      const int X = cx + (p % bpr) * n, Y = cy + (p / bpr) * n;
+      const size_t t = (size_t)rel * per_ctu + j;
+      const size_t sblk = (size_t)rel * sb * sb + ((Y - cy) / sn) * sb + (X - cx) / sn;
+      const int mode = f->rough_best[src][sblk * f->n_best + rank];
+      frame_refs(f, X, Y, n, &refs);
+      frame_block(f, X, Y, n, orig);
+      data.pred_cu.intra.mode = (int8_t)mode;
+      uvg_intra_predict(g_state, &refs, &loc, &loc, COLOR_Y, preds[0], &data, NULL);
+      uvg_pixel *rec = f->tu_rec[i] + t * n * n;
+      int16_t *coeff = f->tu_coeff[i] + t * n * n;
+      f->tu_mode[i][t] = (uint8_t)mode;
+      f->tu_has[i][t] = (uint8_t)qr(g_state, &cu, n, n, COLOR_Y, SCAN_DIAG, 0, n, n, orig, preds[0], rec, coeff, false, 0, UVG_BOTH_T);
+      f->tu_ssd[i][t] = ssd(orig, rec, n, n, n, n);
+      f->tu_cost[i][t] = fcc(coeff, n, n, f->weights);
+    }
+  }
+}
+
 static void *ctu_pass_worker(void *arg)
 {
   refh_job_t *j = arg;
+  if (j->fj) {                                         /* frame pass: one unit = one CTU */
+    const int n_units = j->fj->ctu_end - j->fj->ctu_begin;
+    for (;;) {
+      const int u = __atomic_fetch_add(j->next_unit, 1, __ATOMIC_RELAXED);
+      if (u >= n_units) break;
+      frame_ctu(j->fj, j->fj->ctu_begin + u);
+    }
+    return NULL;
+  }
   const int n_ctu = j->ctu_end;
   if (j->static_threads > 0) {
     /* static partition: worker w always owns the same contiguous CTU slice (NUMA-friendly:
@@ -659,6 +791,47 @@ double refh_ctu_pass(const char *strategy, int threads, int n_ctu,
   pthread_mutex_unlock(&g_pool.mu);
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+static double run_pool_job(refh_job_t *j, int threads)
+{
+  if (threads < 1) threads = 1;
+  if (threads > POOL_MAX) threads = POOL_MAX;
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.n_threads < threads) {
+    pthread_create(&g_pool.th[g_pool.n_threads], NULL, pool_main, (void *)(intptr_t)g_pool.n_threads);
+    ++g_pool.n_threads;
+  }
+  pthread_mutex_unlock(&g_pool.mu);
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_mutex_lock(&g_pool.mu);
+  g_pool.job = *j;
+  g_pool.active = threads;
+  g_pool.remaining = threads;
+  ++g_pool.generation;
+  pthread_cond_broadcast(&g_pool.cv_work);
+  while (g_pool.remaining > 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* Runs the frame pass over CTUs [ctu_begin, ctu_end) on `threads` pool workers; returns seconds. */
+double refh_frame_pass(int threads, const uvg_pixel *plane, int W, int H, int stride, int ctu_begin, int ctu_end,
+                       int n_levels, const refh_frame_level_t *levels, uint32_t *const *rough_cost,
+                       uint8_t *const *rough_best, int n_tus, const refh_level_t *tus, int n_best,
+                       uint8_t *const *tu_mode, uint8_t *const *tu_has, uint32_t *const *tu_ssd,
+                       uint32_t *const *tu_cost, int16_t *const *tu_coeff, uvg_pixel *const *tu_rec, uint64_t weights)
+{
+  frame_job_t f = { plane, W, H, stride, (W + LCU_WIDTH - 1) / LCU_WIDTH, ctu_begin, ctu_end, n_levels, levels, rough_cost,
+                    rough_best, n_tus, tus, n_best, tu_mode, tu_has, tu_ssd, tu_cost, tu_coeff, tu_rec, weights };
+  int next_unit = 0;
+  refh_job_t j;
+  memset(&j, 0, sizeof j);
+  j.next_unit = &next_unit;
+  j.fj = &f;
+  return run_pool_job(&j, threads);
 }
 
 /* Pair-batch micro-baseline: n_pairs dense n*n block pairs through one nxn cost function

@@ -55,3 +55,18 @@ def test_bands_partition():
             lo, hi = refpic.band_rows(r, world, 34)
             rows += list(range(lo, hi))
         assert rows == list(range(34))
+
+
+def test_c_abi_band_partition_matches_python():
+    """uvg_b200_band_rows (the partition uvg_b200_refpic_exchange broadcasts by) is the rule of refpic.band_rows and
+    of bench.py's bands; needs no GPU."""
+    import ctypes as C
+    import uvg266_b200 as U
+    from uvg266_b200 import refpic
+    L = U.lib()
+    for world in (1, 2, 3, 4, 8):
+        for ctu_rows in (1, 5, 34, 68):
+            for r in range(world):
+                lo, hi = C.c_int(), C.c_int()
+                L.uvg_b200_band_rows(r, world, ctu_rows, C.byref(lo), C.byref(hi))
+                assert (lo.value, hi.value) == refpic.band_rows(r, world, ctu_rows)

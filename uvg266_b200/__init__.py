@@ -56,6 +56,66 @@ class QuantCfg(C.Structure):
         return c
 
 
+FRAME_MAX_LEVELS = 4
+FRAME_NO_H2D, FRAME_NO_D2H, FRAME_DENSE_COEFF = 1, 2, 4
+
+
+class FrameLevel(C.Structure):
+    _fields_ = [("n", C.c_int32), ("k", C.c_int32), ("modes", C.c_int8 * 68)]
+
+
+class FrameTu(C.Structure):
+    _fields_ = [("n", C.c_int32), ("per_ctu", C.c_int32)]
+
+
+class FrameCfg(C.Structure):
+    """uvg_b200_frame_cfg"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bitdepth", C.c_int32), ("n_levels", C.c_int32),
+                ("level", FrameLevel * FRAME_MAX_LEVELS), ("n_tus", C.c_int32), ("tu", FrameTu * FRAME_MAX_LEVELS),
+                ("n_best", C.c_int32), ("quant", QuantCfg), ("cost_weights", C.c_uint64)]
+
+    @staticmethod
+    def make(width, height, levels, tus, n_best, quant, cost_weights):
+        """levels: [(n, [modes])], tus: [(n, per_ctu)]"""
+        c = FrameCfg()
+        c.width, c.height, c.bitdepth = width, height, 8
+        c.n_levels = len(levels)
+        for i, (n, modes) in enumerate(levels):
+            c.level[i].n, c.level[i].k = n, len(modes)
+            for j, m in enumerate(modes):
+                c.level[i].modes[j] = m
+        c.n_tus = len(tus)
+        for i, (n, cnt) in enumerate(tus):
+            c.tu[i].n, c.tu[i].per_ctu = n, cnt
+        c.n_best = n_best
+        c.quant = quant
+        c.cost_weights = cost_weights
+        return c
+
+
+class FrameResult(C.Structure):
+    """uvg_b200_frame_result: host pointers owned by the frame object"""
+    _A = C.c_void_p * FRAME_MAX_LEVELS
+    _fields_ = [("ctu_begin", C.c_int32), ("ctu_end", C.c_int32), ("rough_cost", _A), ("rough_best", _A),
+                ("tu_mode", _A), ("tu_has_coeffs", _A), ("tu_ssd", _A), ("tu_cost", _A), ("tu_sig", _A),
+                ("tu_level_off", _A), ("tu_coeff_dense", _A), ("levels", C.c_void_p), ("n_levels", C.c_uint64),
+                ("device_ms", C.c_float)]
+
+
+class FrameDevice(C.Structure):
+    _A = C.c_void_p * FRAME_MAX_LEVELS
+    _fields_ = [("plane", C.c_void_p), ("rough_cost", _A), ("rough_best", _A), ("tu_pred", _A), ("tu_rec", _A),
+                ("tu_coeff", _A), ("stream", C.c_void_p)]
+
+
+def np_view(ptr, dtype, count):
+    """numpy view of `count` items at a host pointer handed out by the library (no copy)."""
+    if not ptr or count == 0:
+        return np.zeros(0, dtype)
+    n = count * np.dtype(dtype).itemsize
+    return np.frombuffer((C.c_uint8 * n).from_address(ptr), dtype=dtype, count=count)
+
+
 class LibraryMissing(RuntimeError):
     pass
 
@@ -108,6 +168,20 @@ def lib():
     L.uvg_b200_intra_rough_dev.argtypes = [i, i, BP, vp, vp, i, vp, sz, vp]
     L.uvg_b200_intra_predict_host.argtypes = [i, i, vp, vp, i, vp, sz]
     L.uvg_b200_intra_rough_host.argtypes = [i, i, BP, sz, vp, vp, i, vp, sz]
+    FP = C.POINTER(FrameCfg)
+    L.uvg_b200_frame_create.argtypes = [FP]; L.uvg_b200_frame_create.restype = vp
+    L.uvg_b200_frame_destroy.argtypes = [vp]; L.uvg_b200_frame_destroy.restype = None
+    L.uvg_b200_frame_submit.argtypes = [vp, vp, sz, i, i, i]
+    L.uvg_b200_frame_wait.argtypes = [vp, C.POINTER(FrameResult)]
+    L.uvg_b200_frame_device_buffers.argtypes = [vp, C.POINTER(FrameDevice)]
+    L.uvg_b200_device_read.argtypes = [vp, vp, sz]
+    L.uvg_b200_band_rows.argtypes = [i, i, i, vp, vp]; L.uvg_b200_band_rows.restype = None
+    L.uvg_b200_comm_unique_id.argtypes = [vp]
+    L.uvg_b200_comm_create.argtypes = [vp, i, i]; L.uvg_b200_comm_create.restype = vp
+    L.uvg_b200_comm_destroy.argtypes = [vp]; L.uvg_b200_comm_destroy.restype = None
+    L.uvg_b200_comm_nccl_version.restype = i
+    L.uvg_b200_refpic_exchange.argtypes = [vp, vp, sz, i, vp]
+    L.uvg_b200_frame_expand_coeffs.argtypes = [vp, vp, vp, i, sz, vp]; L.uvg_b200_frame_expand_coeffs.restype = None
     # drop-ins
     for suf in ("8", "16"):
         for n in (4, 8, 16, 32, 64):

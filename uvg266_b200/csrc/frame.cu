@@ -1,0 +1,635 @@
+// frame.cu - device-resident all-intra frame pipeline behind the C ABI (uvg_b200_frame_*).
+//
+// The batched call site of SURVEY.md 8(f)-4: what the encoder does per CTU for an all-intra picture -
+//   search_intra_rough          search_intra.c:986-1062   predict k candidate modes per block, cost = min(SATD, 2 SAD)
+//   (mode selection)            search_intra.c:1064-1105  keep the best candidates
+//   uvg_quantize_lcu_residual   transform.c:1487-1600     predict with the chosen mode -> quantize_residual ->
+//                                                          pixels_calc_ssd -> coefficient cost
+// - done for a whole picture (or a band of CTU rows) in one call, with everything between the source plane and the
+// results resident in HBM: one H2D copy of the source rows, kernels, D2H of costs / modes / per-TU results and the
+// quantised coefficients in compact form (significance bit array + packed non-zero levels).
+//
+// The reference samples of every block are taken from the SOURCE picture's neighbours (open loop): the closed-loop
+// dependency on the reconstruction of the neighbouring CUs is control flow of the encoder proper, which stays on the
+// host; the reference arm of bench.py (oracle/ref_harness.c::refh_frame_pass) makes the same choice so both arms do
+// the same arithmetic. Sample (x, y) outside the picture = the nearest picture sample (border replication).
+//
+// Layout. All per-block arrays are CTU-major: block index = (ctu - ctu_begin) * blocks_per_ctu + j, j = raster
+// position inside the 64x64 CTU; TU j of a CTU sits at raster position j % positions and is the (j / positions)-th
+// visit of that position: visit r uses the r-th best candidate mode of the rough block that covers it.
+#include "common.cuh"
+#include "intra.cuh"
+#include <cub/device/device_scan.cuh>
+#include <new>
+#include <string.h>
+
+namespace uvgb {
+
+namespace {
+
+constexpr int kCtu = 64;
+constexpr int kMaxLv = UVG_B200_FRAME_MAX_LEVELS;
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// CTU-major block index -> top-left pixel of the block
+struct Geo {
+  int W, H, ctu_cols, ctu_begin;
+  __device__ __forceinline__ void pos(size_t blk, int per_ctu, int n, int &X, int &Y, int &ctu, int &j) const
+  {
+    ctu = (int)(blk / per_ctu) + ctu_begin;
+    j = (int)(blk % per_ctu);
+    const int bpr = kCtu / n, p = j % (bpr * bpr);
+    X = (ctu % ctu_cols) * kCtu + (p % bpr) * n;
+    Y = (ctu / ctu_cols) * kCtu + (p / bpr) * n;
+  }
+};
+
+// Rough-search operands of one level: the original blocks (dense n*n) and their reference rows in the layout of
+// uvg_b200_intra_rough_dev (top[2n+1] then left[2n+1], pitch 2n+4, index 0 = corner sample).
+__global__ void __launch_bounds__(256)
+frame_gather_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, int n, int per_ctu, size_t n_blocks,
+                    uint8_t *__restrict__ orig, uint8_t *__restrict__ refs)
+{
+  const int gp = 2 * n + 4, E = n * n + 2 * gp;
+  const size_t total = n_blocks * (size_t)E;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t blk = t / E;
+    const int e = (int)(t - blk * E);
+    int X, Y, ctu, j;
+    g.pos(blk, per_ctu, n, X, Y, ctu, j);
+    if (e < n * n) {
+      const int y = e / n, x = e - y * n;
+      orig[blk * (size_t)(n * n) + e] = plane[(size_t)min(Y + y, g.H - 1) * stride + min(X + x, g.W - 1)];
+    } else {
+      const int r = e - n * n, row = r / gp, i = min(r - row * gp, 2 * n);
+      const int sx = row ? X - 1 : X - 1 + i, sy = row ? Y - 1 + i : Y - 1;
+      refs[blk * (size_t)(2 * gp) + r] = plane[(size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1)];
+    }
+  }
+}
+
+// The n_best cheapest candidate modes of every block, best first; ties keep the earlier candidate (a stable sort
+// of the cost list, like the insertion into the sorted mode list of search_intra.c:1064).
+__global__ void __launch_bounds__(256)
+frame_topk_kernel(const uint32_t *__restrict__ cost, size_t n_blocks, int k, int n_best,
+                  const int8_t *__restrict__ mode_values, uint8_t *__restrict__ best)
+{
+  const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  uint32_t bc[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
+  int bi[4] = { 0, 0, 0, 0 };
+  for (int m = 0; m < k; ++m) {
+    uint32_t c = cost[b * k + m];
+    int idx = m;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      if (s < n_best && c < bc[s]) { const uint32_t tc = bc[s]; const int ti = bi[s]; bc[s] = c; bi[s] = idx; c = tc; idx = ti; }
+    }
+  }
+  for (int s = 0; s < n_best; ++s) best[b * n_best + s] = (uint8_t)mode_values[bi[s < k ? s : k - 1]];
+}
+
+// Residual-pass operands of one TU size: the original block and the intra prediction with the TU's mode, both
+// dense n*n. The reference rows come straight from the source plane (clamped), the mode from the covering rough
+// block's candidate list.
+struct TuSel { int src_n, src_per_ctu, n_best; const uint8_t *best; };
+
+template <int TPC>
+__global__ void __launch_bounds__(256)
+frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, int n, int per_ctu, size_t n_tus, TuSel sel,
+                        ModeTable mt /* index = mode value 0..66 */, uint8_t *__restrict__ ref_out,
+                        uint8_t *__restrict__ pred_out, uint8_t *__restrict__ mode_out)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int spitch = 2 * n + 12;
+  uint8_t *s_rows = smem_raw;                              // [TPC][4][spitch]
+  __shared__ int s_dc[TPC], s_mode[TPC], s_X[TPC], s_Y[TPC];
+  const int tid = threadIdx.x, l2 = ilog2_dev(n);
+  const size_t first = (size_t)blockIdx.x * TPC;
+  if (tid < TPC) {
+    const size_t t = min(first + tid, n_tus - 1);
+    int X, Y, ctu, j;
+    g.pos(t, per_ctu, n, X, Y, ctu, j);
+    s_X[tid] = X; s_Y[tid] = Y;
+    // candidate rank = how many times this position was visited before; covering block of the source level
+    const int bpr = kCtu / n, rank = min(j / (bpr * bpr), sel.n_best - 1);
+    const int sb = kCtu / sel.src_n;
+    const int lx = (X & (kCtu - 1)) / sel.src_n, ly = (Y & (kCtu - 1)) / sel.src_n;
+    const size_t sblk = (size_t)(ctu - g.ctu_begin) * sel.src_per_ctu + ly * sb + lx;
+    s_mode[tid] = sel.best[sblk * sel.n_best + rank];
+  }
+  __syncthreads();
+  for (int i = tid; i < TPC * 2 * spitch; i += 256) {
+    const int tu = i / (2 * spitch), rem = i - tu * 2 * spitch, row = rem / spitch, x = min(rem - row * spitch, 2 * n);
+    const int X = s_X[tu], Y = s_Y[tu];
+    const int sx = row ? X - 1 : X - 1 + x, sy = row ? Y - 1 + x : Y - 1;
+    s_rows[(tu * 4 + row) * spitch + (rem - row * spitch)] =
+        __ldg(plane + (size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1));
+  }
+  __syncthreads();
+  for (int i = tid; i < TPC * 2 * spitch; i += 256) {        // intra_filter_reference, intra.c:190-225
+    const int tu = i / (2 * spitch), rem = i - tu * 2 * spitch, row = rem / spitch, x = rem - row * spitch;
+    const uint8_t *top = s_rows + tu * 4 * spitch, *left = top + spitch, *src = row ? left : top;
+    int v;
+    if (x == 0) v = ((int)left[1] + 2 * (int)left[0] + (int)top[1] + 2) >> 2;
+    else if (x < 2 * n) v = ((int)src[x - 1] + 2 * (int)src[x] + (int)src[x + 1] + 2) >> 2;
+    else v = src[2 * n];
+    s_rows[(tu * 4 + 2 + row) * spitch + x] = (uint8_t)v;
+  }
+  if (tid < TPC) {                                           // intra_pred_dc, intra.c:236-273
+    const uint8_t *top = s_rows + tid * 4 * spitch, *left = top + spitch;
+    int sum = 0;
+    for (int i = 1; i <= n; ++i) sum += (int)top[i] + (int)left[i];
+    s_dc[tid] = (sum + n) >> (l2 + 1);
+  }
+  __syncthreads();
+  const int nn = n * n;
+  for (int e = tid; e < TPC * nn; e += 256) {
+    const int tu = e / nn, p = e - tu * nn, y = p >> l2, x = p & (n - 1);
+    const size_t t = first + tu;
+    if (t >= n_tus) break;
+    const uint8_t *r0 = s_rows + tu * 4 * spitch;
+    const RefRows<uint8_t> rr{ r0, r0 + spitch, r0 + 2 * spitch, r0 + 3 * spitch };
+    const int mode = s_mode[tu];
+    pred_out[t * (size_t)nn + p] = (uint8_t)pred_pixel<uint8_t>(mt.m[mode], rr, n, l2, x, y, s_dc[tu], 255);
+    ref_out[t * (size_t)nn + p] = __ldg(plane + (size_t)min(s_Y[tu] + y, g.H - 1) * stride + min(s_X[tu] + x, g.W - 1));
+    if (p == 0) mode_out[t] = (uint8_t)mode;
+  }
+}
+
+// ---- compact coefficient output -----------------------------------------------------------------------------------
+// The dense coefficient arrays of the residual pass ([n_tus][n*n] int16) are mostly zeros. What crosses PCIe is
+//   sig    : one bit per coefficient of the dense array (bit i of the array = bit (i & 31) of word i >> 5)
+//   levels : the non-zero coefficients, TU after TU, each TU's in index order
+//   off    : per TU, where its levels start (exclusive prefix sum of the per-TU non-zero counts)
+// Lane l of a warp owns coefficients [8l, 8l+8) of a 256-coefficient chunk.
+template <int S /* coefficients per TU: 16, 64, 256, 1024 */>
+__device__ __forceinline__ void chunk_masks(const int16_t *__restrict__ coeff, size_t chunk, size_t n_chunks, int lane,
+                                            uint32_t &mask8, uint4 &v)
+{
+  v = make_uint4(0, 0, 0, 0);
+  if (chunk < n_chunks) v = __ldg(reinterpret_cast<const uint4 *>(coeff) + chunk * 32 + lane);
+  const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+  mask8 = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (w[i] & 0xffffu) mask8 |= 1u << (2 * i);
+    if (w[i] >> 16) mask8 |= 1u << (2 * i + 1);
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256)
+coeff_count_kernel(const int16_t *__restrict__ coeff, size_t n_coeffs, uint32_t *__restrict__ sig, uint32_t *__restrict__ cnt)
+{
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t n_chunks = (n_coeffs + 255) / 256;            // n_coeffs is a multiple of 16; a tail chunk reads zeros
+  constexpr int CPT = S > 256 ? S / 256 : 1;                 // chunks per TU (32x32: 4)
+  for (size_t c0 = warp * CPT; c0 < n_chunks; c0 += n_warps * CPT) {
+    unsigned acc = 0;
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc) {
+      const size_t chunk = c0 + cc;
+      uint32_t m8; uint4 v;
+      // the last chunk may be partial (n_coeffs % 256 != 0 only for 4x4 / 8x8 TU counts): guard the load
+      if ((chunk * 256 + (size_t)lane * 8) < n_coeffs) chunk_masks<S>(coeff, chunk, n_chunks, lane, m8, v); else m8 = 0;
+      uint32_t m = m8 << (8 * (lane & 3));
+      m |= __shfl_xor_sync(0xffffffffu, m, 1);
+      m |= __shfl_xor_sync(0xffffffffu, m, 2);
+      if ((lane & 3) == 0 && (chunk * 256 + (size_t)lane * 8) < n_coeffs) sig[chunk * 8 + (lane >> 2)] = m;
+      unsigned c = __popc(m8);
+      constexpr int LPT = S >= 256 ? 32 : S / 8;              // lanes per TU inside a chunk
+#pragma unroll
+      for (int d = LPT / 2; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+      if (S <= 256) {
+        if ((lane % LPT) == 0) {
+          const size_t tu = (chunk * 256 + (size_t)lane * 8) / S;
+          if (tu * S < n_coeffs) cnt[tu] = c;
+        }
+      } else {
+        acc += c;
+      }
+    }
+    if (S > 256 && lane == 0) cnt[c0 / CPT] = acc;
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256)
+coeff_pack_kernel(const int16_t *__restrict__ coeff, size_t n_coeffs, const uint32_t *__restrict__ off,
+                  int16_t *__restrict__ levels)
+{
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t n_chunks = (n_coeffs + 255) / 256;
+  constexpr int CPT = S > 256 ? S / 256 : 1;
+  constexpr int LPT = S >= 256 ? 32 : S / 8;
+  for (size_t c0 = warp * CPT; c0 < n_chunks; c0 += n_warps * CPT) {
+    unsigned carried = 0;
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc) {
+      const size_t chunk = c0 + cc;
+      const bool live = (chunk * 256 + (size_t)lane * 8) < n_coeffs;
+      uint32_t m8 = 0; uint4 v = make_uint4(0, 0, 0, 0);
+      if (live) chunk_masks<S>(coeff, chunk, n_chunks, lane, m8, v);
+      const unsigned c = __popc(m8);
+      unsigned incl = c;                                     // inclusive scan over the warp
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      const unsigned excl = incl - c;
+      const unsigned seg0 = __shfl_sync(0xffffffffu, excl, lane - (lane % LPT));
+      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+      if (live && m8) {
+        const size_t tu = (chunk * 256 + (size_t)lane * 8) / S;
+        int16_t *dst = levels + off[tu] + carried + (excl - seg0);
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (w[i] & 0xffffu) *dst++ = (int16_t)(w[i] & 0xffffu);
+          if (w[i] >> 16) *dst++ = (int16_t)(w[i] >> 16);
+        }
+      }
+      carried += total;
+    }
+  }
+}
+
+struct Level {
+  int n = 0, k = 0, ppc = 0;
+  int8_t modes[68];
+  ModeTable mt;                                   // candidates in the order given
+  size_t nb = 0;                                  // blocks of the whole picture
+  uint8_t *d_orig = nullptr, *d_refs = nullptr, *d_best = nullptr;
+  int8_t *d_modes = nullptr;
+  uint32_t *d_cost = nullptr;
+  uint32_t *h_cost = nullptr; uint8_t *h_best = nullptr;
+};
+
+struct TuSize {
+  int n = 0, per_ctu = 0, src = 0;
+  size_t nt = 0;
+  ModeTable mt;                                   // all 67 modes of this size, index = mode value
+  uint8_t *d_ref = nullptr, *d_pred = nullptr, *d_rec = nullptr, *d_mode = nullptr, *d_has = nullptr;
+  int16_t *d_coeff = nullptr;
+  uint32_t *d_ssd = nullptr, *d_cost = nullptr, *d_sig = nullptr;
+  uint8_t *h_mode = nullptr, *h_has = nullptr;
+  uint32_t *h_ssd = nullptr, *h_cost = nullptr, *h_sig = nullptr;
+  int16_t *h_coeff = nullptr;                     // dense, only with UVG_B200_FRAME_DENSE_COEFF
+};
+
+}  // namespace
+
+struct Frame {
+  uvg_b200_frame_cfg cfg;
+  int W = 0, H = 0, ctu_cols = 0, ctu_rows = 0, n_ctu = 0;
+  cudaStream_t s_main = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_level[kMaxLv] = {}, ev_tu[kMaxLv] = {}, ev_pack = nullptr, ev_total = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  uint8_t *d_plane = nullptr;
+  Level lv[kMaxLv];
+  TuSize tu[kMaxLv];
+  size_t total_tus = 0, total_coeffs = 0;
+  uint32_t *d_cnt = nullptr, *d_off = nullptr, *h_off = nullptr;
+  void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+  int16_t *d_levels = nullptr, *h_levels = nullptr;
+  uvg_b200_frame_result res;
+  int ctu_begin = 0, ctu_end = 0, flags = 0;
+  bool in_flight = false;
+};
+
+static void frame_release(Frame *f)
+{
+  if (f->s_main) cudaStreamSynchronize(f->s_main);
+  if (f->s_copy) cudaStreamSynchronize(f->s_copy);
+  auto D = [](void *p) { if (p) cudaFree(p); };
+  auto Hh = [](void *p) { if (p) cudaFreeHost(p); };
+  D(f->d_plane); D(f->d_cnt); D(f->d_off); D(f->d_scan_tmp); D(f->d_levels);
+  Hh(f->h_off); Hh(f->h_levels);
+  for (int i = 0; i < kMaxLv; ++i) {
+    Level &l = f->lv[i];
+    D(l.d_orig); D(l.d_refs); D(l.d_best); D(l.d_cost); D(l.d_modes); Hh(l.h_cost); Hh(l.h_best);
+    TuSize &t = f->tu[i];
+    D(t.d_ref); D(t.d_pred); D(t.d_rec); D(t.d_mode); D(t.d_has); D(t.d_coeff); D(t.d_ssd); D(t.d_cost); D(t.d_sig);
+    Hh(t.h_mode); Hh(t.h_has); Hh(t.h_ssd); Hh(t.h_cost); Hh(t.h_sig); Hh(t.h_coeff);
+    if (f->ev_level[i]) cudaEventDestroy(f->ev_level[i]);
+    if (f->ev_tu[i]) cudaEventDestroy(f->ev_tu[i]);
+  }
+  for (cudaEvent_t e : { f->ev_pack, f->ev_total, f->ev_t0, f->ev_t1 }) if (e) cudaEventDestroy(e);
+  if (f->s_main) cudaStreamDestroy(f->s_main);
+  if (f->s_copy) cudaStreamDestroy(f->s_copy);
+  cudaGetLastError();
+}
+
+template <typename T> static int dalloc(T *&p, size_t count) { UVGB_TRY(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T) + 64)); return 0; }
+template <typename T> static int halloc(T *&p, size_t count) { UVGB_TRY(cudaMallocHost(reinterpret_cast<void **>(&p), count * sizeof(T) + 64)); return 0; }
+
+static int frame_build(Frame *f, const uvg_b200_frame_cfg *c)
+{
+  f->cfg = *c;
+  f->W = c->width; f->H = c->height;
+  f->ctu_cols = (c->width + kCtu - 1) / kCtu; f->ctu_rows = (c->height + kCtu - 1) / kCtu;
+  f->n_ctu = f->ctu_cols * f->ctu_rows;
+  UVGB_TRY(cudaStreamCreateWithFlags(&f->s_main, cudaStreamNonBlocking));
+  UVGB_TRY(cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < kMaxLv; ++i) {
+    UVGB_TRY(cudaEventCreateWithFlags(&f->ev_level[i], cudaEventDisableTiming));
+    UVGB_TRY(cudaEventCreateWithFlags(&f->ev_tu[i], cudaEventDisableTiming));
+  }
+  UVGB_TRY(cudaEventCreateWithFlags(&f->ev_pack, cudaEventDisableTiming));
+  UVGB_TRY(cudaEventCreateWithFlags(&f->ev_total, cudaEventDisableTiming));
+  UVGB_TRY(cudaEventCreate(&f->ev_t0));
+  UVGB_TRY(cudaEventCreate(&f->ev_t1));
+  if (dalloc(f->d_plane, (size_t)f->W * f->H)) return 1;
+  for (int i = 0; i < c->n_levels; ++i) {
+    Level &l = f->lv[i];
+    l.n = c->level[i].n; l.k = c->level[i].k; l.ppc = (kCtu / l.n) * (kCtu / l.n);
+    memcpy(l.modes, c->level[i].modes, sizeof(l.modes));
+    l.mt.k = l.k;
+    for (int m = 0; m < l.k; ++m) l.mt.m[m] = make_mode(l.n, l.modes[m]);
+    l.nb = (size_t)f->n_ctu * l.ppc;
+    if (dalloc(l.d_orig, l.nb * l.n * l.n) || dalloc(l.d_refs, l.nb * 2 * (2 * l.n + 4)) || dalloc(l.d_cost, l.nb * l.k) ||
+        dalloc(l.d_best, l.nb * c->n_best) || dalloc(l.d_modes, (size_t)68) || halloc(l.h_cost, l.nb * l.k) ||
+        halloc(l.h_best, l.nb * c->n_best)) return 1;
+    UVGB_TRY(cudaMemcpy(l.d_modes, l.modes, 68, cudaMemcpyHostToDevice));
+  }
+  for (int i = 0; i < c->n_tus; ++i) {
+    TuSize &t = f->tu[i];
+    t.n = c->tu[i].n; t.per_ctu = c->tu[i].per_ctu;
+    // mode source: the smallest rough level that is at least as large as the TU, else the largest level
+    int src = -1;
+    for (int l = 0; l < c->n_levels; ++l) if (f->lv[l].n >= t.n && (src < 0 || f->lv[l].n < f->lv[src].n)) src = l;
+    if (src < 0) for (int l = 0; l < c->n_levels; ++l) if (src < 0 || f->lv[l].n > f->lv[src].n) src = l;
+    t.src = src;
+    t.mt.k = kMaxModes;
+    for (int m = 0; m < kMaxModes; ++m) t.mt.m[m] = make_mode(t.n, m);
+    t.nt = (size_t)f->n_ctu * t.per_ctu;
+    const size_t px = t.nt * t.n * t.n;
+    if (dalloc(t.d_ref, px) || dalloc(t.d_pred, px) || dalloc(t.d_rec, px) || dalloc(t.d_mode, t.nt) || dalloc(t.d_has, t.nt) ||
+        dalloc(t.d_coeff, px) || dalloc(t.d_ssd, t.nt) || dalloc(t.d_cost, t.nt) || dalloc(t.d_sig, px / 32 + 8) ||
+        halloc(t.h_mode, t.nt) || halloc(t.h_has, t.nt) || halloc(t.h_ssd, t.nt) || halloc(t.h_cost, t.nt) ||
+        halloc(t.h_sig, px / 32 + 8)) return 1;
+    f->total_tus += t.nt; f->total_coeffs += px;
+  }
+  if (dalloc(f->d_cnt, f->total_tus + 1) || dalloc(f->d_off, f->total_tus + 1) || halloc(f->h_off, f->total_tus + 1) ||
+      dalloc(f->d_levels, f->total_coeffs) || halloc(f->h_levels, f->total_coeffs)) return 1;
+  UVGB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, f->scan_tmp_bytes, f->d_cnt, f->d_off, (int)(f->total_tus + 1), f->s_main));
+  UVGB_TRY(cudaMalloc(&f->d_scan_tmp, f->scan_tmp_bytes + 64));
+  return 0;
+}
+
+static int cfg_check(const uvg_b200_frame_cfg *c)
+{
+  if (!c) { set_error("frame: NULL configuration"); return 1; }
+  if (c->bitdepth != 8) { set_error("frame: the pipeline is built for 8-bit video (bitdepth %d)", c->bitdepth); return 1; }
+  if (c->width < 16 || c->height < 16 || c->width > 16384 || c->height > 16384) { set_error("frame: %dx%d out of range", c->width, c->height); return 1; }
+  if (c->n_levels < 1 || c->n_levels > kMaxLv || c->n_tus < 0 || c->n_tus > kMaxLv) { set_error("frame: 1..4 rough levels, 0..4 TU sizes"); return 1; }
+  if (c->n_best < 1 || c->n_best > 4) { set_error("frame: n_best must be 1..4"); return 1; }
+  for (int i = 0; i < c->n_levels; ++i) {
+    const int n = c->level[i].n, k = c->level[i].k;
+    if (n != 8 && n != 16 && n != 32) { set_error("frame: rough level size %d unsupported (8, 16, 32)", n); return 1; }
+    if (k < 1 || k > 67) { set_error("frame: 1..67 candidate modes per level"); return 1; }
+    for (int m = 0; m < k; ++m) if (c->level[i].modes[m] < 0 || c->level[i].modes[m] > 66) { set_error("frame: mode out of range"); return 1; }
+  }
+  for (int i = 0; i < c->n_tus; ++i) {
+    const int n = c->tu[i].n;
+    if (n != 4 && n != 8 && n != 16 && n != 32) { set_error("frame: TU size %d unsupported", n); return 1; }
+    if (c->tu[i].per_ctu < 1 || c->tu[i].per_ctu > 4 * (kCtu / n) * (kCtu / n)) { set_error("frame: per_ctu out of range"); return 1; }
+  }
+  return 0;
+}
+
+template <int S>
+static void launch_count_pack(bool pack, const int16_t *coeff, size_t n_coeffs, uint32_t *sig, uint32_t *cnt,
+                              const uint32_t *off, int16_t *levels, cudaStream_t st)
+{
+  const size_t chunks = (n_coeffs + 255) / 256;
+  size_t grid = (chunks + 7) / 8;
+  const size_t cap = (size_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  if (!pack) coeff_count_kernel<S><<<(unsigned)grid, 256, 0, st>>>(coeff, n_coeffs, sig, cnt);
+  else coeff_pack_kernel<S><<<(unsigned)grid, 256, 0, st>>>(coeff, n_coeffs, off, levels);
+}
+
+static int count_pack(bool pack, int n, const int16_t *coeff, size_t n_coeffs, uint32_t *sig, uint32_t *cnt,
+                      const uint32_t *off, int16_t *levels, cudaStream_t st)
+{
+  switch (n) {
+    case 4: launch_count_pack<16>(pack, coeff, n_coeffs, sig, cnt, off, levels, st); break;
+    case 8: launch_count_pack<64>(pack, coeff, n_coeffs, sig, cnt, off, levels, st); break;
+    case 16: launch_count_pack<256>(pack, coeff, n_coeffs, sig, cnt, off, levels, st); break;
+    default: launch_count_pack<1024>(pack, coeff, n_coeffs, sig, cnt, off, levels, st); break;
+  }
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace uvgb
+
+using namespace uvgb;
+
+struct uvg_b200_frame { Frame f; };
+
+extern "C" uvg_b200_frame *uvg_b200_frame_create(const uvg_b200_frame_cfg *cfg)
+{
+  if (ensure_init()) return nullptr;
+  if (cfg_check(cfg)) return nullptr;
+  uvg_b200_frame *h = new (std::nothrow) uvg_b200_frame();
+  if (!h) { set_error("frame: out of memory"); return nullptr; }
+  if (frame_build(&h->f, cfg)) { frame_release(&h->f); delete h; return nullptr; }
+  return h;
+}
+
+extern "C" void uvg_b200_frame_destroy(uvg_b200_frame *h)
+{
+  if (!h) return;
+  frame_release(&h->f);
+  delete h;
+}
+
+extern "C" int uvg_b200_frame_submit(uvg_b200_frame *h, const void *src, size_t src_stride, int ctu_row_begin,
+                                     int ctu_row_end, int flags)
+{
+  if (!h) { set_error("frame: NULL handle"); return 1; }
+  Frame *f = &h->f;
+  if (f->in_flight) { set_error("frame: submit while a pass is in flight (call uvg_b200_frame_wait first)"); return 1; }
+  if (ctu_row_end <= 0 || ctu_row_end > f->ctu_rows) ctu_row_end = f->ctu_rows;
+  if (ctu_row_begin < 0 || ctu_row_begin >= ctu_row_end) { set_error("frame: CTU row range [%d,%d) is empty", ctu_row_begin, ctu_row_end); return 1; }
+  const uvg_b200_frame_cfg &c = f->cfg;
+  const int W = f->W, H = f->H;
+  const int ctu_begin = ctu_row_begin * f->ctu_cols, ctu_end = ctu_row_end * f->ctu_cols, band_ctus = ctu_end - ctu_begin;
+  f->ctu_begin = ctu_begin; f->ctu_end = ctu_end; f->flags = flags;
+  cudaStream_t st = f->s_main, sc = f->s_copy;
+  const bool d2h = !(flags & UVG_B200_FRAME_NO_D2H);
+  UVGB_TRY(cudaEventRecord(f->ev_t0, st));
+  if (!(flags & UVG_B200_FRAME_NO_H2D)) {
+    if (!src) { set_error("frame: NULL source plane"); return 1; }
+    // rows the band reads: one above, and below it what the left reference column of a 32x32 block at the band's
+    // last rows reaches (Y - 1 + 2n)
+    const int y0 = max(0, ctu_row_begin * kCtu - 1), y1 = min(H, ctu_row_end * kCtu + kCtu);
+    UVGB_TRY(cudaMemcpy2DAsync(f->d_plane + (size_t)y0 * W, W, static_cast<const uint8_t *>(src) + (size_t)y0 * src_stride,
+                               src_stride, W, y1 - y0, cudaMemcpyHostToDevice, st));
+  }
+  Geo g{ W, H, f->ctu_cols, ctu_begin };
+  const size_t cap = (size_t)sm_count() * 16;
+  // ---- rough search --------------------------------------------------------------------------------------------
+  for (int i = 0; i < c.n_levels; ++i) {
+    Level &l = f->lv[i];
+    const size_t nb = (size_t)band_ctus * l.ppc;
+    const size_t total = nb * (size_t)(l.n * l.n + 2 * (2 * l.n + 4));
+    size_t grid = (total + 255) / 256;
+    if (grid > cap) grid = cap;
+    frame_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(f->d_plane, W, g, l.n, l.ppc, nb, l.d_orig, l.d_refs);
+    UVGB_LAUNCH_CHECK();
+    uvg_b200_blocks A; A.base = l.d_orig; A.stride = (uint32_t)l.n; A.blocks_per_row = 1; A.col_pitch = 0; A.row_pitch = (uint64_t)l.n * l.n;
+    if (uvg_b200_intra_rough_dev(8, l.n, &A, l.d_refs, l.modes, l.k, l.d_cost, nb, st)) return 1;
+    frame_topk_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(l.d_cost, nb, l.k, c.n_best, l.d_modes, l.d_best);
+    UVGB_LAUNCH_CHECK();
+    if (d2h) {
+      UVGB_TRY(cudaEventRecord(f->ev_level[i], st));
+      UVGB_TRY(cudaStreamWaitEvent(sc, f->ev_level[i], 0));
+      UVGB_TRY(cudaMemcpyAsync(l.h_cost, l.d_cost, nb * l.k * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+      UVGB_TRY(cudaMemcpyAsync(l.h_best, l.d_best, nb * c.n_best, cudaMemcpyDeviceToHost, sc));
+    }
+  }
+  // ---- residual pass -----------------------------------------------------------------------------------------------
+  size_t tu_base = 0;
+  for (int i = 0; i < c.n_tus; ++i) {
+    TuSize &t = f->tu[i];
+    const Level &sl = f->lv[t.src];
+    const size_t nt = (size_t)band_ctus * t.per_ctu;
+    const int nn = t.n * t.n, tpc = nn >= 256 ? 1 : 256 / nn;
+    const size_t smem = (size_t)tpc * 4 * (2 * t.n + 12);
+    const TuSel sel{ sl.n, sl.ppc, c.n_best, sl.d_best };
+    const unsigned grid = (unsigned)((nt + tpc - 1) / tpc);
+    if (tpc == 16) frame_tu_predict_kernel<16><<<grid, 256, smem, st>>>(f->d_plane, W, g, t.n, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
+    else if (tpc == 4) frame_tu_predict_kernel<4><<<grid, 256, smem, st>>>(f->d_plane, W, g, t.n, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
+    else frame_tu_predict_kernel<1><<<grid, 256, smem, st>>>(f->d_plane, W, g, t.n, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
+    UVGB_LAUNCH_CHECK();
+    uvg_b200_blocks R, P, O;
+    R.base = t.d_ref; P.base = t.d_pred; O.base = t.d_rec;
+    for (uvg_b200_blocks *b : { &R, &P, &O }) { b->stride = (uint32_t)t.n; b->blocks_per_row = 1; b->col_pitch = 0; b->row_pitch = (uint64_t)nn; }
+    if (uvg_b200_quantize_residual_dev(&c.quant, 1 /* CU_INTRA */, 0, t.n, t.n, 0, 0, 0, &R, &P, &O, t.d_coeff, t.d_has, t.d_ssd,
+                                       t.d_cost, c.cost_weights, nt, st)) return 1;
+    if (count_pack(false, t.n, t.d_coeff, nt * (size_t)nn, t.d_sig, f->d_cnt + tu_base, nullptr, nullptr, st)) return 1;
+    if (d2h) {
+      UVGB_TRY(cudaEventRecord(f->ev_tu[i], st));
+      UVGB_TRY(cudaStreamWaitEvent(sc, f->ev_tu[i], 0));
+      UVGB_TRY(cudaMemcpyAsync(t.h_mode, t.d_mode, nt, cudaMemcpyDeviceToHost, sc));
+      UVGB_TRY(cudaMemcpyAsync(t.h_has, t.d_has, nt, cudaMemcpyDeviceToHost, sc));
+      UVGB_TRY(cudaMemcpyAsync(t.h_ssd, t.d_ssd, nt * 4, cudaMemcpyDeviceToHost, sc));
+      UVGB_TRY(cudaMemcpyAsync(t.h_cost, t.d_cost, nt * 4, cudaMemcpyDeviceToHost, sc));
+      UVGB_TRY(cudaMemcpyAsync(t.h_sig, t.d_sig, (nt * (size_t)nn + 31) / 32 * 4, cudaMemcpyDeviceToHost, sc));
+      if (flags & UVG_B200_FRAME_DENSE_COEFF) {
+        if (!t.h_coeff && halloc(t.h_coeff, t.nt * (size_t)nn)) return 1;
+        UVGB_TRY(cudaMemcpyAsync(t.h_coeff, t.d_coeff, nt * (size_t)nn * 2, cudaMemcpyDeviceToHost, sc));
+      }
+    }
+    tu_base += nt;
+  }
+  // ---- compact coefficients: offsets = exclusive scan of the counts, then the packed levels -----------------------------
+  if (c.n_tus) {
+    UVGB_TRY(cudaMemsetAsync(f->d_cnt + tu_base, 0, sizeof(uint32_t), st));
+    size_t tmp = f->scan_tmp_bytes;
+    UVGB_TRY(cub::DeviceScan::ExclusiveSum(f->d_scan_tmp, tmp, f->d_cnt, f->d_off, (int)(tu_base + 1), st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    size_t b2 = 0;
+    for (int i = 0; i < c.n_tus; ++i) {
+      TuSize &t = f->tu[i];
+      const size_t nt = (size_t)band_ctus * t.per_ctu;
+      if (count_pack(true, t.n, t.d_coeff, nt * (size_t)(t.n * t.n), nullptr, nullptr, f->d_off + b2, f->d_levels, st)) return 1;
+      b2 += nt;
+    }
+    if (d2h) {
+      UVGB_TRY(cudaEventRecord(f->ev_pack, st));
+      UVGB_TRY(cudaStreamWaitEvent(sc, f->ev_pack, 0));
+      UVGB_TRY(cudaMemcpyAsync(f->h_off, f->d_off, (tu_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+    }
+  }
+  UVGB_TRY(cudaEventRecord(f->ev_t1, st));
+  if (d2h) UVGB_TRY(cudaEventRecord(f->ev_total, sc));
+  f->in_flight = true;
+  return 0;
+}
+
+extern "C" int uvg_b200_frame_wait(uvg_b200_frame *h, uvg_b200_frame_result *out)
+{
+  if (!h) { set_error("frame: NULL handle"); return 1; }
+  Frame *f = &h->f;
+  if (!f->in_flight) { set_error("frame: wait without submit"); return 1; }
+  f->in_flight = false;
+  const uvg_b200_frame_cfg &c = f->cfg;
+  const bool d2h = !(f->flags & UVG_B200_FRAME_NO_D2H);
+  const int band_ctus = f->ctu_end - f->ctu_begin;
+  uvg_b200_frame_result &r = f->res;
+  memset(&r, 0, sizeof(r));
+  r.ctu_begin = f->ctu_begin; r.ctu_end = f->ctu_end;
+  size_t tu_total = 0;
+  for (int i = 0; i < c.n_tus; ++i) tu_total += (size_t)band_ctus * f->tu[i].per_ctu;
+  if (d2h) {
+    UVGB_TRY(cudaEventSynchronize(f->ev_total));
+    if (c.n_tus) {
+      // only now does the host know how many levels there are: one more copy of exactly that size
+      const uint64_t total = f->h_off[tu_total];
+      r.n_levels = total;
+      if (total) UVGB_TRY(cudaMemcpyAsync(f->h_levels, f->d_levels, total * sizeof(int16_t), cudaMemcpyDeviceToHost, f->s_copy));
+      UVGB_TRY(cudaStreamSynchronize(f->s_copy));
+    }
+  }
+  UVGB_TRY(cudaStreamSynchronize(f->s_main));
+  float ms = 0.f;
+  UVGB_TRY(cudaEventElapsedTime(&ms, f->ev_t0, f->ev_t1));
+  r.device_ms = ms;
+  if (d2h) {
+    size_t base = 0;
+    for (int i = 0; i < c.n_levels; ++i) { r.rough_cost[i] = f->lv[i].h_cost; r.rough_best[i] = f->lv[i].h_best; }
+    for (int i = 0; i < c.n_tus; ++i) {
+      TuSize &t = f->tu[i];
+      r.tu_mode[i] = t.h_mode; r.tu_has_coeffs[i] = t.h_has; r.tu_ssd[i] = t.h_ssd; r.tu_cost[i] = t.h_cost; r.tu_sig[i] = t.h_sig;
+      r.tu_level_off[i] = f->h_off + base;
+      r.tu_coeff_dense[i] = (f->flags & UVG_B200_FRAME_DENSE_COEFF) ? t.h_coeff : nullptr;
+      base += (size_t)band_ctus * t.per_ctu;
+    }
+    r.levels = f->h_levels;
+  }
+  if (out) *out = r;
+  return 0;
+}
+
+extern "C" int uvg_b200_frame_device_buffers(uvg_b200_frame *h, uvg_b200_frame_device *out)
+{
+  if (!h || !out) { set_error("frame: NULL argument"); return 1; }
+  Frame *f = &h->f;
+  memset(out, 0, sizeof(*out));
+  out->plane = f->d_plane;
+  for (int i = 0; i < f->cfg.n_levels; ++i) { out->rough_cost[i] = f->lv[i].d_cost; out->rough_best[i] = f->lv[i].d_best; }
+  for (int i = 0; i < f->cfg.n_tus; ++i) {
+    out->tu_pred[i] = f->tu[i].d_pred; out->tu_rec[i] = f->tu[i].d_rec; out->tu_coeff[i] = f->tu[i].d_coeff;
+  }
+  out->stream = f->s_main;
+  return 0;
+}
+
+extern "C" int uvg_b200_device_read(void *host_dst, const void *dev_src, size_t bytes)
+{
+  if (ensure_init()) return 1;
+  if (!bytes) return 0;
+  if (!host_dst || !dev_src) { set_error("device_read: NULL argument"); return 1; }
+  UVGB_TRY(cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Host-side inverse of the compact coefficient format: dense[i] for the n_coeffs coefficients of one TU size.
+extern "C" void uvg_b200_frame_expand_coeffs(const uint32_t *sig, const uint32_t *level_off, const int16_t *levels,
+                                             int coeffs_per_tu, size_t n_tus, int16_t *dense)
+{
+  for (size_t t = 0; t < n_tus; ++t) {
+    const int16_t *lv = levels + level_off[t];
+    for (int i = 0; i < coeffs_per_tu; ++i) {
+      const size_t gidx = t * (size_t)coeffs_per_tu + i;
+      const int bit = (sig[gidx >> 5] >> (gidx & 31)) & 1;
+      dense[gidx] = bit ? *lv++ : 0;
+    }
+  }
+}
