@@ -142,7 +142,24 @@ typedef struct uvg_b200_quant_cfg {
                           * explicit MTS an ISP luma TU uses DST-7 (uvg_get_tr_type, dct-generic.c:2522) */
   int8_t chroma_qp_map[128]; /* encoder_control->qp_map[0][qp] for qp 0..127 (entry =   */
   int32_t has_chroma_qp_map; /*   mapped qp), valid when has_chroma_qp_map != 0        */
+  /* LFNST (cfg.lfnst, intra CUs; uvg_quantize_residual_generic quant-generic.c:503-509, :561-563; uvg_fwd_lfnst /
+   * uvg_inv_lfnst transform.c:965-1200). All zero = LFNST off. Read by quantize_residual only.               */
+  int32_t cu_lfnst_idx;      /* cur_cu->lfnst_idx    } the transform's zero-out depends on the CU fields      */
+  int32_t cu_cr_lfnst_idx;   /* cur_cu->cr_lfnst_idx }   (mts_dct_generic, dct-generic.c:2589-2600)            */
+  int32_t lfnst_index;       /* the index of this colour / tree (:503): what quant is told (first 8 / 16 scan   */
+                             /*   positions only)                                                               */
+  int32_t lfnst_apply;       /* uvg_fwd_lfnst's own gate (transform.c:990): lfnst_index && !mts_skip &&         */
+                             /*   (luma || separate tree)                                                       */
+  int32_t lfnst_mode;        /* the intra mode that picks the kernel: luma / chroma mode after the CCLM         */
+                             /*   (-> collocated luma mode) and MIP (-> planar) substitutions (:1001-1006)      */
+  int32_t lfnst_wa_log2_w;   /* block dims of the wide-angle correction (:1009-1014): cur_cu->log2_width/height  */
+  int32_t lfnst_wa_log2_h;   /*   for luma, the TU's for chroma                                                  */
 } uvg_b200_quant_cfg;
+
+/* The two trained LFNST kernels, uvg_lfnst_8x8[4][2][16][48] and uvg_lfnst_4x4[4][2][16][16] (lfnst_tables.h:56,
+ * :211): HOST pointers to the encoder's own exported read-only tables, copied to the device once. This library does
+ * not contain them. Until it is called, quantize_residual with lfnst_apply != 0 fails. */
+UVG_B200_API int uvg_b200_set_lfnst_tables(const int8_t *t8x8, const int8_t *t4x4);
 
 /* q_coef = quant(coef) for n_tus dense w*h blocks (uvg_quant_generic, flat lists). */
 UVG_B200_API int uvg_b200_quant_dev(const uvg_b200_quant_cfg *cfg, const int16_t *coef,

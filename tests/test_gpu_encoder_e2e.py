@@ -28,7 +28,7 @@ def make_yuv(path, w, h, frames, bd=8, seed=1234):
             f.write(c.tobytes()); f.write(c[::-1].copy().tobytes())
 
 
-def encode(bd, yuv, w, h, frames, opts, cuda, threads=0, groups=None):
+def encode(bd, yuv, w, h, frames, opts, cuda, threads=0, groups=None, extra_env=None):
     d = os.path.join(ROOT, "oracle", "_ref", "bd%d" % bd)
     exe = os.path.join(d, "uvg266")
     glue = os.path.join(ROOT, "uvg266_b200", "lib", "libuvg266_b200_glue%d.so" % bd)
@@ -48,6 +48,8 @@ def encode(bd, yuv, w, h, frames, opts, cuda, threads=0, groups=None):
         env["UVG266_B200_VERBOSE"] = "1"
         if groups:
             env["UVG266_B200_GROUPS"] = groups
+        if extra_env:
+            env.update(extra_env)
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
     launches = None
@@ -117,6 +119,22 @@ def test_bitstream_identity_baseline_configs(tmp_path, name, bd, w, h, frames, o
     md5_cuda, launches, err = encode(bd, yuv, w, h, frames, opts, cuda=True, threads=threads)
     assert launches and launches > 1000, err[-1500:]
     assert md5_cuda == md5_gen, "bitstream differs with the cuda strategies (%s)" % name
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_lfnst_blocks_stay_in_the_fused_kernel(tmp_path, bd):
+    """Row 8(f)-3 stage 1 at the encoder level (the tool set of BASELINE config 4): with the encoder's LFNST kernels
+    handed to the device, an LFNST TU is ONE launch (residual .. forward LFNST .. quant .. inverse LFNST ..
+    reconstruction); with UVG266_B200_LFNST=host the same TU walks the reference's composite leaf by leaf. Same
+    bitstream all three ways, far fewer launches."""
+    yuv = str(tmp_path / "lfnst.yuv")
+    make_yuv(yuv, 128, 64, 2, bd)
+    opts = ["--preset=ultrafast", "-p", "1", "--rd=2", "--mts=intra", "--lfnst"]
+    md5_gen, _, _ = encode(bd, yuv, 128, 64, 2, opts, cuda=False)
+    md5_dev, launches_dev, err = encode(bd, yuv, 128, 64, 2, opts, cuda=True)
+    md5_host, launches_host, _ = encode(bd, yuv, 128, 64, 2, opts, cuda=True, extra_env={"UVG266_B200_LFNST": "host"})
+    assert md5_dev == md5_gen and md5_host == md5_gen, err[-1500:]
+    assert launches_dev and launches_host and launches_dev < 0.8 * launches_host, (launches_dev, launches_host)
 
 
 def test_multithreaded_encode_is_identical(tmp_path):

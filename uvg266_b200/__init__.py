@@ -44,7 +44,10 @@ class QuantCfg(C.Structure):
     """uvg_b200_quant_cfg: what quant/dequant read through encoder_state_t."""
     _fields_ = [("qp", C.c_int32), ("bitdepth", C.c_int32), ("slice_intra", C.c_int32),
                 ("signhide", C.c_int32), ("mts", C.c_int32), ("isp_mode", C.c_int32),
-                ("chroma_qp_map", C.c_int8 * 128), ("has_chroma_qp_map", C.c_int32)]
+                ("chroma_qp_map", C.c_int8 * 128), ("has_chroma_qp_map", C.c_int32),
+                ("cu_lfnst_idx", C.c_int32), ("cu_cr_lfnst_idx", C.c_int32), ("lfnst_index", C.c_int32),
+                ("lfnst_apply", C.c_int32), ("lfnst_mode", C.c_int32), ("lfnst_wa_log2_w", C.c_int32),
+                ("lfnst_wa_log2_h", C.c_int32)]
 
     @staticmethod
     def make(qp, bitdepth=8, slice_intra=1, signhide=0, mts=0, chroma_map=None, isp_mode=0):
@@ -175,6 +178,7 @@ def lib():
     L.uvg_b200_frame_wait.argtypes = [vp, C.POINTER(FrameResult)]
     L.uvg_b200_frame_device_buffers.argtypes = [vp, C.POINTER(FrameDevice)]
     L.uvg_b200_device_read.argtypes = [vp, vp, sz]
+    L.uvg_b200_set_lfnst_tables.argtypes = [vp, vp]
     L.uvg_b200_band_rows.argtypes = [i, i, i, vp, vp]; L.uvg_b200_band_rows.restype = None
     L.uvg_b200_comm_unique_id.argtypes = [vp]
     L.uvg_b200_comm_create.argtypes = [vp, i, i]; L.uvg_b200_comm_create.restype = vp

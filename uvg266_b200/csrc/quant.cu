@@ -73,6 +73,48 @@ int init_quant_tables()
 }
 
 // -------------------------------------------------------------------------------------
+// LFNST (transform.c:878-1200): the trained kernels are the encoder's own tables, handed in at run time
+// -------------------------------------------------------------------------------------
+static int8_t *d_lfnst8 = nullptr, *d_lfnst4 = nullptr;     // [4][2][16][48], [4][2][16][16]
+static std::mutex lfnst_mu;
+
+// uvg_lfnst_lut (lfnst_tables.h:51-54) as intervals of the extended mode index 0..94
+static int lfnst_set(int m) { return m < 2 ? 0 : m <= 12 ? 1 : m <= 23 ? 2 : m <= 44 ? 3 : m <= 55 ? 2 : 1; }
+
+// uvg_wide_angle_correction, intra.c:637-658
+static int wide_angle_mode(int mode, int l2w, int l2h, int account_for_dc_planar)
+{
+  static const int shift[6] = { 0, 6, 10, 12, 14, 15 };
+  if (l2w != l2h && mode > 1 && mode <= 66) {
+    const int d = l2w > l2h ? l2w - l2h : l2h - l2w;
+    if (l2w > l2h && mode < 2 + shift[d]) return mode + 65;
+    if (l2h > l2w && mode > 66 - shift[d]) return mode - 65 - (account_for_dc_planar ? 2 : 0);
+  }
+  return mode;
+}
+
+// Position of LFNST scan entry j in a block of width w: up-right diagonal order inside a 4x4 group and over the
+// 2x2 groups of the top-left 8x8 (uvg_coef_top_left_diag_scan_8x8 / the first group of uvg_g_sig_last_scan).
+__device__ __forceinline__ int lfnst_scan_pos(int j, int w, int whge3)
+{
+  // x / y of the 16 diagonal positions, 2 bits each: dx = {0,0,1,0,1,2,0,1,2,3,1,2,3,2,3,3},
+  // dy = {0,1,0,2,1,0,3,2,1,0,3,2,1,3,2,3}
+  const unsigned DX = 0xfb9e4910u, DY = 0xedb1b184u;
+  const int g = whge3 ? j >> 4 : 0, i = j & 15;
+  const int gx = g >> 1, gy = g & 1;              // 4x4 groups of the 8x8 corner in the order (0,0), (0,1), (1,0), (1,1) as (x, y)
+  return (gy * 4 + (int)((DY >> (2 * i)) & 3)) * w + gx * 4 + (int)((DX >> (2 * i)) & 3);
+}
+
+// index into the gathered input vector `in` (48 or 16 entries) of region coefficient (x, y) - the order in which
+// uvg_fwd_lfnst reads the top-left region (row-major, or transposed; 8x8 regions are the L-shaped 48), :1030-1066
+__device__ __forceinline__ int lfnst_in_index(int x, int y, int sb, int transpose)
+{
+  if (!transpose) return sb == 4 ? 4 * y + x : (y < 4 ? 8 * y + x : 32 + 4 * (y - 4) + x);
+  if (sb == 4) return 4 * x + y;
+  return x < 4 ? 8 * x + y : 32 + 4 * (x - 4) + y;
+}
+
+// -------------------------------------------------------------------------------------
 // quantiser parameters (host)
 // -------------------------------------------------------------------------------------
 static const int16_t k_quant_scales[2][6] = { { 26214, 23302, 20560, 18396, 16384, 14564 },
@@ -104,6 +146,7 @@ static int make_qparams(QParams &q, const uvg_b200_quant_cfg *c, int w, int h, i
   const int needs_scale = !transform_skip && ((l2w + l2h) % 2 == 1);
   const int transform_shift = 15 - c->bitdepth - ((l2w + l2h) >> 1) - needs_scale;       // :76
   q.w = w; q.h = h; q.area = w * h;
+  q.lfnst_apply = 0; q.lfnst_transpose = 0; q.lfnst_sb = 0; q.lfnst_zero_out = 0; q.lfnst_whge3 = 0; q.lfnst_mat = nullptr;
   q.q_bits = 14 + qp_scaled / 6 + (transform_skip ? 0 : transform_shift);                // :77
   if (q.q_bits < 9 || q.q_bits > 30) { set_error("q_bits %d out of range", q.q_bits); return 1; }
   q.add = (c->slice_intra ? 171 : 85) << (q.q_bits - 9);                                 // :78
@@ -355,6 +398,7 @@ quantize_residual_kernel(FusedArgs a, size_t n_tus, QParams q, TrPlan fp, TrPlan
   unsigned *s_acc = reinterpret_cast<unsigned *>(sbuf + (size_t)slots * 3 * q.area);
   unsigned *s_red = s_acc + slots;                       // [slots][3]: nonzero, ssd, cost
   unsigned char *s_cgnz = reinterpret_cast<unsigned char *>(s_red + slots * 3);
+  int16_t *s_lfnst = reinterpret_cast<int16_t *>(s_cgnz + slots * 64);        // [slots][64]: LFNST input / output vectors
   if (!a.use_trskip) {
     for (int t = threadIdx.x; t < fp.n1 * fp.n1; t += blockDim.x) { const int k = t / fp.n1, i = t - k * fp.n1; sF1[i * fp.n1 + k] = fp.t1[t]; }
     for (int t = threadIdx.x; t < fp.n2 * fp.n2; t += blockDim.x) { const int k = t / fp.n2, i = t - k * fp.n2; sF2[i * fp.n2 + k] = fp.t2[t]; }
@@ -413,6 +457,32 @@ quantize_residual_kernel(FusedArgs a, size_t n_tus, QParams q, TrPlan fp, TrPlan
       }
       __syncthreads();
     }
+    // 2b. forward LFNST on the low-frequency corner (uvg_fwd_lfnst, transform.c:965-1083): gather the 4x4 / L-shaped
+    // 8x8 region (transposed for modes > 34), 16 x 16|48 matrix-vector product, scatter in scan order
+    if (q.lfnst_apply) {
+      int16_t *lf = s_lfnst + slot * 64;
+      const int sb = q.lfnst_sb, tr = sb > 4 ? 48 : 16;
+      if (active)
+        for (int e = tid; e < sb * sb; e += tps) {
+          const int y = e / sb, x = e - y * sb;
+          if (sb == 8 && y >= 4 && x >= 4) continue;
+          lf[lfnst_in_index(x, y, sb, q.lfnst_transpose)] = bufA[y * w + x];
+        }
+      __syncthreads();
+      int16_t o[3] = { 0, 0, 0 };
+      if (active)
+        for (int j = tid, r = 0; j < tr; j += tps, ++r) {
+          if (j < q.lfnst_zero_out) {
+            int acc = 0;
+            for (int i = 0; i < tr; ++i) acc += (int)lf[i] * (int)q.lfnst_mat[j * tr + i];
+            o[r] = (int16_t)((acc + 64) >> 7);
+          }
+        }
+      __syncthreads();
+      if (active)
+        for (int j = tid, r = 0; j < tr; j += tps, ++r) bufA[lfnst_scan_pos(j, w, q.lfnst_whge3)] = o[r];
+      __syncthreads();
+    }
     // 3. quant (+ sign hiding) :536-539
     quant_step(bufA, bufQ, q, s_acc, s_cgnz, slot, tid, tps, active);
     // 4. coefficients out, has_coeffs (:542-550), fast coefficient cost
@@ -434,6 +504,27 @@ quantize_residual_kernel(FusedArgs a, size_t n_tus, QParams q, TrPlan fp, TrPlan
     // 5. dequant + inverse transform (:553-570) -> residual' in bufA
     if (recon) dequant_elems(bufQ, a.use_trskip ? bufA : bufB, q, tid, tps);
     __syncthreads();
+    // 5b. inverse LFNST (uvg_inv_lfnst, transform.c:1104-1200) on the dequantised coefficients (bufB)
+    if (q.lfnst_apply) {
+      int16_t *lf = s_lfnst + slot * 64;
+      const int sb = q.lfnst_sb, tr = sb > 4 ? 48 : 16;
+      if (recon) for (int j = tid; j < 16; j += tps) lf[48 + j] = bufB[lfnst_scan_pos(j, w, q.lfnst_whge3)];
+      __syncthreads();
+      if (recon)
+        for (int j = tid; j < tr; j += tps) {
+          int acc = 0;
+          for (int i = 0; i < q.lfnst_zero_out; ++i) acc += (int)lf[48 + i] * (int)q.lfnst_mat[i * tr + j];
+          lf[j] = (int16_t)((acc + 64) >> 7);
+        }
+      __syncthreads();
+      if (recon)
+        for (int e = tid; e < sb * sb; e += tps) {
+          const int y = e / sb, x = e - y * sb;
+          if (sb == 8 && y >= 4 && x >= 4) continue;
+          bufB[y * w + x] = lf[lfnst_in_index(x, y, sb, q.lfnst_transpose)];
+        }
+      __syncthreads();
+    }
     if (!a.use_trskip) {
       // bufB holds dequantised coefficients
       if (recon) inv_pass(bufB, ip.n2 ? bufQ : bufA, sI1, ip.n1, ip.line1, ip.reduced1, ip.cutoff1, ip.shift1, tid, tps);
@@ -591,13 +682,31 @@ static int run_quantize_residual(const uvg_b200_quant_cfg *cfg, int cu_type, int
   QParams q;
   // quant is called with transform_skip = (tr_idx == MTS_SKIP && luma), quant-generic.c:538
   const int ts_flag = (tr_idx == 1 && color == 0) ? 1 : 0;
-  if (make_qparams(q, cfg, w, h, color, ts_flag, 0)) return 1;
+  // quant is told the LFNST index of this colour / tree even where uvg_fwd_lfnst's own gate keeps the transform
+  // off (quant-generic.c:503, :538): only the first 8 / 16 scan positions survive
+  if (make_qparams(q, cfg, w, h, color, ts_flag, jccr ? 0 : cfg->lfnst_index)) return 1;
+  if (cfg->lfnst_apply) {
+    if (use_trskip || jccr || cu_type != 1 || !cfg->lfnst_index || cfg->lfnst_index > 2) { set_error("quantize_residual: LFNST with transform skip / JCCR / inter CU is not covered"); return 1; }
+    const int8_t *t8, *t4;
+    { std::lock_guard<std::mutex> lk(lfnst_mu); t8 = d_lfnst8; t4 = d_lfnst4; }
+    if (!t8 || !t4) { set_error("quantize_residual: LFNST kernels not set (uvg_b200_set_lfnst_tables)"); return 1; }
+    int m = wide_angle_mode(cfg->lfnst_mode, cfg->lfnst_wa_log2_w, cfg->lfnst_wa_log2_h, 1);
+    m = m < 0 ? m + 14 + 67 : m >= 67 ? m + 14 : m;                    // get_lfnst_intra_mode, transform.c:917-936
+    if (m < 0 || m > 94) { set_error("quantize_residual: LFNST mode %d out of range", cfg->lfnst_mode); return 1; }
+    q.lfnst_apply = 1;
+    q.lfnst_transpose = (m >= 67 && m >= 81) || (m < 67 && m > 34);    // get_transpose_flag, :938-942
+    q.lfnst_whge3 = w >= 8 && h >= 8;
+    q.lfnst_sb = q.lfnst_whge3 ? 8 : 4;
+    q.lfnst_zero_out = ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 8 : 16;
+    const size_t sel = (size_t)(lfnst_set(m) * 2 + cfg->lfnst_index - 1) * 16;
+    q.lfnst_mat = q.lfnst_sb > 4 ? t8 + sel * 48 : t4 + sel * 16;
+  }
   TrPlan fp{}, ip{};
   int th = UVG_B200_DCT2, tv = UVG_B200_DCT2, sw = 0, sh = 0;
   if (!use_trskip) {
     // uvg_transform2d (transform.c:256): mts_dct when cfg.mts or non-square, else dct_NxN -
     // both are this matrix product; with mts off the types are DCT2/DCT2.
-    derive_tr(w, h, color, cu_type, tr_idx, 0, 0, cfg->isp_mode, cfg->mts, &th, &tv, &sw, &sh);
+    derive_tr(w, h, color, cu_type, tr_idx, jccr ? 0 : cfg->cu_lfnst_idx, jccr ? 0 : cfg->cu_cr_lfnst_idx, cfg->isp_mode, cfg->mts, &th, &tv, &sw, &sh);
     if (make_fwd_plan(fp, cfg->bitdepth, w, h, th, tv, sw, sh)) return 1;
     if (make_inv_plan(ip, cfg->bitdepth, w, h, th, tv, sw, sh)) return 1;
   }
@@ -615,7 +724,8 @@ static int run_quantize_residual(const uvg_b200_quant_cfg *cfg, int cu_type, int
   else { a.ref2 = a.ref; a.pred2 = a.pred; a.rec2 = a.rec; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // shape-specialised kernels first: registers-only for 4x4/8x8, tensor cores for 16x16/32x32
-  if (!jccr) {
+  const bool lfnst_involved = !jccr && (cfg->lfnst_apply || cfg->lfnst_index || cfg->cu_lfnst_idx || cfg->cu_cr_lfnst_idx);
+  if (!jccr && !lfnst_involved) {
     // UVG266_B200_FUSED = imma | small | hmma | generic restricts the choice (A/B measurements)
     static const char *force = getenv("UVG266_B200_FUSED");
     int rc = -1;
@@ -628,7 +738,8 @@ static int run_quantize_residual(const uvg_b200_quant_cfg *cfg, int cu_type, int
   }
   const int slots = slots_for(q.area);
   const int mat_bytes = (fp.n1 * fp.n1 + fp.n2 * fp.n2 + ip.n1 * ip.n1 + ip.n2 * ip.n2 + 15) & ~15;
-  const size_t smem = mat_bytes + (size_t)slots * 3 * q.area * sizeof(int16_t) + slots * 4 * sizeof(unsigned) + slots * 64;
+  const size_t smem = mat_bytes + (size_t)slots * 3 * q.area * sizeof(int16_t) + slots * 4 * sizeof(unsigned) + slots * 64 +
+                      (size_t)slots * 64 * sizeof(int16_t);
   size_t grid = (n_tus + slots - 1) / slots;
   const size_t cap = (size_t)sm_count() * 8;
   if (grid > cap) grid = cap;
@@ -696,5 +807,21 @@ extern "C" int uvg_b200_fast_coeff_cost_dev(const int16_t *coeffs, int w, int h,
       coeffs, (size_t)w * h, out, n_tus, 1, (unsigned)(weights & 0xffff), (unsigned)((weights >> 16) & 0xffff),
       (unsigned)((weights >> 32) & 0xffff), (unsigned)((weights >> 48) & 0xffff));
   UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int uvg_b200_set_lfnst_tables(const int8_t *t8x8, const int8_t *t4x4)
+{
+  if (ensure_init()) return 1;
+  if (!t8x8 || !t4x4) { set_error("set_lfnst_tables: NULL table"); return 1; }
+  std::lock_guard<std::mutex> lk(lfnst_mu);
+  if (!d_lfnst8) {
+    int8_t *p8 = nullptr, *p4 = nullptr;
+    UVGB_TRY(cudaMalloc(reinterpret_cast<void **>(&p8), 4 * 2 * 16 * 48));
+    UVGB_TRY(cudaMalloc(reinterpret_cast<void **>(&p4), 4 * 2 * 16 * 16));
+    d_lfnst8 = p8; d_lfnst4 = p4;
+  }
+  UVGB_TRY(cudaMemcpy(d_lfnst8, t8x8, 4 * 2 * 16 * 48, cudaMemcpyHostToDevice));
+  UVGB_TRY(cudaMemcpy(d_lfnst4, t4x4, 4 * 2 * 16 * 16, cudaMemcpyHostToDevice));
   return 0;
 }

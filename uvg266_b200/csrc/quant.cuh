@@ -14,6 +14,9 @@ struct QParams {
   int dq_shift, dq_scale, dq_add;
   // reconstruction
   int pixel_max, ssd_shift;
+  // LFNST stage of the general kernel (0 = off): kernel matrix [16][tr_size] of the (set, index) pair on the device
+  int lfnst_apply, lfnst_transpose, lfnst_sb, lfnst_zero_out, lfnst_whge3;
+  const int8_t *lfnst_mat;
 };
 
 

@@ -16,6 +16,8 @@
  * then fails and uvg266_open reports "Failed to initialize strategies." (uvg266.c:96-99) -
  * there is no silent CPU fallback.
  */
+#define _GNU_SOURCE
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -145,6 +147,7 @@ static uint32_t crc32c_8x8_cuda(const uvg_pixel *buf, uint32_t pic_stride) { ret
  * composites (quantize_residual, quant_cbcr_residual) then run their transform / quant / dequant steps
  * through the strategy table, i.e. on the cuda leaves, and the encoder-side tools (LFNST, RDOQ, dep-quant,
  * LMCS: transform.c, rdo.c, dep_quant.c, reshape.c) run where they live. Nothing aborts mid-encode. */
+static int lfnst_on_device;              /* the encoder's LFNST kernels were found and copied to the device */
 static quant_func *ref_quant;
 static dequant_func *ref_dequant;
 static quant_residual_func *ref_quantize_residual;
@@ -216,11 +219,28 @@ static unsigned quantize_residual_cuda(encoder_state_t *const state, const cu_in
   const bool lfnst = enc->cfg.lfnst && cur_cu->type == CU_INTRA;
   const bool rdoq = enc->cfg.rdoq_enable && ((width > 4 || !enc->cfg.rdoq_skip) || use_trskip);
   const bool dq = !use_trskip && enc->cfg.dep_quant;
-  if (lmcs || lfnst || rdoq || dq || scaling_lists_on(enc))
+  /* LFNST stays inside the fused kernel when the encoder's kernel tables could be handed to the device */
+  if (lmcs || rdoq || dq || scaling_lists_on(enc) || (lfnst && (!lfnst_on_device || use_trskip)))
     return ref_quantize_residual(state, cur_cu, width, height, color, scan_order, use_trskip, in_stride, out_stride,
                                  ref_in, pred_in, rec_out, coeff_out, early_skip, lmcs_chroma_adj, tree_type);
   uvg_b200_quant_cfg c;
   fill_cfg(state, cur_cu, &c);
+  if (lfnst) {
+    /* what uvg_quantize_residual_generic (:503-509) and uvg_fwd_lfnst (transform.c:979-1014) derive from the CU */
+    const uint8_t lfnst_index = (tree_type != UVG_CHROMA_T || color == COLOR_Y) ? cur_cu->lfnst_idx : cur_cu->cr_lfnst_idx;
+    const bool sep_tree = cur_cu->log2_height + cur_cu->log2_width < 6 || tree_type != UVG_BOTH_T;
+    const bool mts_skip = cur_cu->tr_idx == MTS_SKIP && color == COLOR_Y;
+    int mode = color == COLOR_Y ? cur_cu->intra.mode : cur_cu->intra.mode_chroma;
+    if (mode >= 81 && mode <= 83) mode = state->collocated_luma_mode;          /* CCLM */
+    if (color == COLOR_Y && cur_cu->intra.mip_flag) mode = 0;                 /* MIP -> planar */
+    c.cu_lfnst_idx = cur_cu->lfnst_idx;
+    c.cu_cr_lfnst_idx = cur_cu->cr_lfnst_idx;
+    c.lfnst_index = lfnst_index;
+    c.lfnst_apply = lfnst_index && !mts_skip && (color == COLOR_Y || sep_tree);
+    c.lfnst_mode = mode;
+    c.lfnst_wa_log2_w = color == COLOR_Y ? cur_cu->log2_width : uvg_g_convert_to_log2[width];
+    c.lfnst_wa_log2_h = color == COLOR_Y ? cur_cu->log2_height : uvg_g_convert_to_log2[height];
+  }
   return (unsigned)B200(quantize_residual)(&c, cur_cu->type, cur_cu->tr_idx, width, height, (int)color, use_trskip,
                                            in_stride, out_stride, ref_in, pred_in, rec_out, coeff_out, early_skip);
 }
@@ -432,6 +452,15 @@ int uvg_strategy_register_quant_cuda(void *opaque, uint8_t bitdepth)
     /* fail at registration, never mid-encode */
     fprintf(stderr, "uvg266_b200: the reference's quant strategies must be registered before the cuda ones\n");
     return 0;
+  }
+  /* The trained LFNST kernels are exported read-only data of the encoder itself (lfnst_tables.h:56, :211): hand the
+   * library their addresses; without them (a build that hides the symbols) LFNST blocks are forwarded as before.
+   * UVG266_B200_LFNST=host keeps LFNST on the host for A/B runs. */
+  {
+    const int8_t *t8 = (const int8_t *)dlsym(RTLD_DEFAULT, "uvg_lfnst_8x8");
+    const int8_t *t4 = (const int8_t *)dlsym(RTLD_DEFAULT, "uvg_lfnst_4x4");
+    const char *where = getenv("UVG266_B200_LFNST");
+    lfnst_on_device = t8 && t4 && !(where && !strcmp(where, "host")) && uvg_b200_set_lfnst_tables(t8, t4) == 0;
   }
   REG("quant", quant_func, quant_cuda); REG("dequant", dequant_func, dequant_cuda);
   REG("quantize_residual", quant_residual_func, quantize_residual_cuda);
