@@ -45,30 +45,6 @@ struct Geo {
   }
 };
 
-// Rough-search operands of one level: the original blocks (dense n*n) and their reference rows in the layout of
-// uvg_b200_intra_rough_dev (top[2n+1] then left[2n+1], pitch 2n+4, index 0 = corner sample).
-__global__ void __launch_bounds__(256)
-frame_gather_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, int n, int per_ctu, size_t n_blocks,
-                    uint8_t *__restrict__ orig, uint8_t *__restrict__ refs)
-{
-  const int gp = 2 * n + 4, E = n * n + 2 * gp;
-  const size_t total = n_blocks * (size_t)E;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const size_t blk = t / E;
-    const int e = (int)(t - blk * E);
-    int X, Y, ctu, j;
-    g.pos(blk, per_ctu, n, X, Y, ctu, j);
-    if (e < n * n) {
-      const int y = e / n, x = e - y * n;
-      orig[blk * (size_t)(n * n) + e] = plane[(size_t)min(Y + y, g.H - 1) * stride + min(X + x, g.W - 1)];
-    } else {
-      const int r = e - n * n, row = r / gp, i = min(r - row * gp, 2 * n);
-      const int sx = row ? X - 1 : X - 1 + i, sy = row ? Y - 1 + i : Y - 1;
-      refs[blk * (size_t)(2 * gp) + r] = plane[(size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1)];
-    }
-  }
-}
-
 // The n_best cheapest candidate modes of every block, best first; ties keep the earlier candidate (a stable sort
 // of the cost list, like the insertion into the sorted mode list of search_intra.c:1064).
 __global__ void __launch_bounds__(256)
@@ -95,17 +71,22 @@ frame_topk_kernel(const uint32_t *__restrict__ cost, size_t n_blocks, int k, int
 // block's candidate list.
 struct TuSel { int src_n, src_per_ctu, n_best; const uint8_t *best; };
 
-template <int TPC>
+template <int N, int TPC>
 __global__ void __launch_bounds__(256)
-frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, int n, int per_ctu, size_t n_tus, TuSel sel,
+frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, int per_ctu, size_t n_tus, TuSel sel,
                         ModeTable mt /* index = mode value 0..66 */, uint8_t *__restrict__ ref_out,
                         uint8_t *__restrict__ pred_out, uint8_t *__restrict__ mode_out)
 {
+  // Work item = 8 horizontally adjacent pixels of one row of a prediction in its WORK orientation (horizontal angular
+  // modes are generated transposed, intra-generic.c:286-298), one dp4a per pixel (angular_row8 / planar_dc_row8 of
+  // intra.cuh - the row generators of the fused rough-search kernel). Rows land in a shared-memory tile in picture
+  // orientation and leave as 32-bit words.
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int spitch = 2 * n + 12;
-  uint8_t *s_rows = smem_raw;                              // [TPC][4][spitch]
+  constexpr int n = N, RS = 2 * n + 12, HEAD = n + 8, nn = n * n;
+  constexpr int per_tu = 4 * RS + HEAD + nn;                 // all multiples of 4
+  constexpr int l2 = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5;
   __shared__ int s_dc[TPC], s_mode[TPC], s_X[TPC], s_Y[TPC];
-  const int tid = threadIdx.x, l2 = ilog2_dev(n);
+  const int tid = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * TPC;
   if (tid < TPC) {
     const size_t t = min(first + tid, n_tus - 1);
@@ -120,41 +101,85 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
     s_mode[tid] = sel.best[sblk * sel.n_best + rank];
   }
   __syncthreads();
-  for (int i = tid; i < TPC * 2 * spitch; i += 256) {
-    const int tu = i / (2 * spitch), rem = i - tu * 2 * spitch, row = rem / spitch, x = min(rem - row * spitch, 2 * n);
+  for (int i = tid; i < TPC * 2 * RS; i += 256) {            // reference rows from the plane, tail replicated
+    const int tu = i / (2 * RS), rem = i - tu * 2 * RS, row = rem / RS, x = min(rem - row * RS, 2 * n);
     const int X = s_X[tu], Y = s_Y[tu];
     const int sx = row ? X - 1 : X - 1 + x, sy = row ? Y - 1 + x : Y - 1;
-    s_rows[(tu * 4 + row) * spitch + (rem - row * spitch)] =
-        __ldg(plane + (size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1));
+    smem_raw[tu * per_tu + row * RS + (rem - row * RS)] = __ldg(plane + (size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1));
   }
   __syncthreads();
-  for (int i = tid; i < TPC * 2 * spitch; i += 256) {        // intra_filter_reference, intra.c:190-225
-    const int tu = i / (2 * spitch), rem = i - tu * 2 * spitch, row = rem / spitch, x = rem - row * spitch;
-    const uint8_t *top = s_rows + tu * 4 * spitch, *left = top + spitch, *src = row ? left : top;
+  for (int i = tid; i < TPC * 2 * RS; i += 256) {            // intra_filter_reference, intra.c:190-225
+    const int tu = i / (2 * RS), rem = i - tu * 2 * RS, row = rem / RS, x = rem - row * RS;
+    const uint8_t *top = smem_raw + tu * per_tu, *left = top + RS, *src = row ? left : top;
     int v;
     if (x == 0) v = ((int)left[1] + 2 * (int)left[0] + (int)top[1] + 2) >> 2;
     else if (x < 2 * n) v = ((int)src[x - 1] + 2 * (int)src[x] + (int)src[x + 1] + 2) >> 2;
     else v = src[2 * n];
-    s_rows[(tu * 4 + 2 + row) * spitch + x] = (uint8_t)v;
+    smem_raw[tu * per_tu + (2 + row) * RS + x] = (uint8_t)v;
   }
   if (tid < TPC) {                                           // intra_pred_dc, intra.c:236-273
-    const uint8_t *top = s_rows + tid * 4 * spitch, *left = top + spitch;
+    const uint8_t *top = smem_raw + tid * per_tu, *left = top + RS;
     int sum = 0;
     for (int i = 1; i <= n; ++i) sum += (int)top[i] + (int)left[i];
     s_dc[tid] = (sum + n) >> (l2 + 1);
   }
   __syncthreads();
-  const int nn = n * n;
-  for (int e = tid; e < TPC * nn; e += 256) {
-    const int tu = e / nn, p = e - tu * nn, y = p >> l2, x = p & (n - 1);
+  // negative angles: main-reference indices -HEAD..-1 = the side reference projected through the inverse angle
+  // (intra-generic.c:145-156)
+  for (int i = tid; i < TPC * HEAD; i += 256) {
+    const int tu = i / HEAD, j = i - tu * HEAD + 1;
+    const ModeParam mp = mt.m[s_mode[tu]];
+    if (mp.kind == 2 && mp.sample_disp < 0) {
+      const uint8_t *top = smem_raw + tu * per_tu + (mp.filtered ? 2 * RS : 0), *left = top + RS;
+      const uint8_t *side = mp.vertical ? left : top;
+      smem_raw[tu * per_tu + 4 * RS + HEAD - j] = side[min((j * mp.inv_angle + 256) >> 9, n)];
+    }
+  }
+  __syncthreads();
+  constexpr int ns = n >= 8 ? n / 8 : 1, items_per_tu = n * ns;
+  for (int e = tid; e < TPC * items_per_tu; e += 256) {
+    const int tu = e / items_per_tu, it = e - tu * items_per_tu, r = it / ns, sx = it - r * ns;
+    if (first + tu >= n_tus) break;
+    const ModeParam mp = mt.m[s_mode[tu]];
+    const uint8_t *base = smem_raw + tu * per_tu;
+    const uint8_t *top = base + (mp.filtered ? 2 * RS : 0), *left = top + RS;
+    uint8_t *tile = smem_raw + tu * per_tu + 4 * RS + HEAD;
+    uint32_t lo, hi;
+    bool transposed = false;
+    if (mp.kind == 2) {
+      const uint8_t *mainr = mp.vertical ? top : left, *side = mp.vertical ? left : top;
+      angular_row8(mp, mainr, side, base + 4 * RS + HEAD, r, sx, min(3 << max((int)mp.scale, 0), n), lo, hi);
+      transposed = !mp.vertical;
+    } else {
+      planar_dc_row8(mp, top, left, s_dc[tu], n, l2, r, sx, lo, hi);
+    }
+    if (!transposed) {
+      *reinterpret_cast<uint32_t *>(tile + r * n + 8 * sx) = lo;
+      if (n >= 8) *reinterpret_cast<uint32_t *>(tile + r * n + 8 * sx + 4) = hi;
+    } else {
+      const int cnt = n >= 8 ? 8 : 4;
+      for (int c = 0; c < cnt; ++c) tile[(8 * sx + c) * n + r] = (uint8_t)(((c < 4 ? lo : hi) >> (8 * (c & 3))) & 0xffu);
+    }
+  }
+  __syncthreads();
+  constexpr int wpt = nn / 4;                                // words per TU
+  for (int e = tid; e < TPC * wpt; e += 256) {
+    const int tu = e / wpt, wi = e - tu * wpt, y = (4 * wi) >> l2, x = (4 * wi) & (n - 1);
     const size_t t = first + tu;
     if (t >= n_tus) break;
-    const uint8_t *r0 = s_rows + tu * 4 * spitch;
-    const RefRows<uint8_t> rr{ r0, r0 + spitch, r0 + 2 * spitch, r0 + 3 * spitch };
-    const int mode = s_mode[tu];
-    pred_out[t * (size_t)nn + p] = (uint8_t)pred_pixel<uint8_t>(mt.m[mode], rr, n, l2, x, y, s_dc[tu], 255);
-    ref_out[t * (size_t)nn + p] = __ldg(plane + (size_t)min(s_Y[tu] + y, g.H - 1) * stride + min(s_X[tu] + x, g.W - 1));
-    if (p == 0) mode_out[t] = (uint8_t)mode;
+    const uint8_t *tile = smem_raw + tu * per_tu + 4 * RS + HEAD;
+    reinterpret_cast<uint32_t *>(pred_out + t * (size_t)nn)[wi] = *reinterpret_cast<const uint32_t *>(tile + 4 * wi);
+    const int X = s_X[tu] + x, Y = s_Y[tu] + y;
+    uint32_t ow;
+    if (X + 3 < g.W && Y < g.H) {
+      ow = __ldg(reinterpret_cast<const uint32_t *>(plane + (size_t)Y * stride + X));
+    } else {
+      const uint8_t *row = plane + (size_t)min(Y, g.H - 1) * stride;
+      ow = (uint32_t)row[min(X, g.W - 1)] | ((uint32_t)row[min(X + 1, g.W - 1)] << 8) | ((uint32_t)row[min(X + 2, g.W - 1)] << 16) |
+           ((uint32_t)row[min(X + 3, g.W - 1)] << 24);
+    }
+    reinterpret_cast<uint32_t *>(ref_out + t * (size_t)nn)[wi] = ow;
+    if (wi == 0) mode_out[t] = (uint8_t)s_mode[tu];
   }
 }
 
@@ -283,7 +308,7 @@ struct TuSize {
 
 struct Frame {
   uvg_b200_frame_cfg cfg;
-  int W = 0, H = 0, ctu_cols = 0, ctu_rows = 0, n_ctu = 0;
+  int W = 0, H = 0, pitch = 0, ctu_cols = 0, ctu_rows = 0, n_ctu = 0;
   cudaStream_t s_main = nullptr, s_copy = nullptr;
   cudaEvent_t ev_level[kMaxLv] = {}, ev_tu[kMaxLv] = {}, ev_pack = nullptr, ev_total = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   uint8_t *d_plane = nullptr;
@@ -340,7 +365,8 @@ static int frame_build(Frame *f, const uvg_b200_frame_cfg *c)
   UVGB_TRY(cudaEventCreateWithFlags(&f->ev_total, cudaEventDisableTiming));
   UVGB_TRY(cudaEventCreate(&f->ev_t0));
   UVGB_TRY(cudaEventCreate(&f->ev_t1));
-  if (dalloc(f->d_plane, (size_t)f->W * f->H)) return 1;
+  f->pitch = (f->W + 15) & ~15;                                  // rows start 16-byte aligned: word loads of block rows
+  if (dalloc(f->d_plane, (size_t)f->pitch * f->H)) return 1;
   for (int i = 0; i < c->n_levels; ++i) {
     Level &l = f->lv[i];
     l.n = c->level[i].n; l.k = c->level[i].k; l.ppc = (kCtu / l.n) * (kCtu / l.n);
@@ -348,7 +374,7 @@ static int frame_build(Frame *f, const uvg_b200_frame_cfg *c)
     l.mt.k = l.k;
     for (int m = 0; m < l.k; ++m) l.mt.m[m] = make_mode(l.n, l.modes[m]);
     l.nb = (size_t)f->n_ctu * l.ppc;
-    if (dalloc(l.d_orig, l.nb * l.n * l.n) || dalloc(l.d_refs, l.nb * 2 * (2 * l.n + 4)) || dalloc(l.d_cost, l.nb * l.k) ||
+    if (dalloc(l.d_cost, l.nb * l.k) ||
         dalloc(l.d_best, l.nb * c->n_best) || dalloc(l.d_modes, (size_t)68) || halloc(l.h_cost, l.nb * l.k) ||
         halloc(l.h_best, l.nb * c->n_best)) return 1;
     UVGB_TRY(cudaMemcpy(l.d_modes, l.modes, 68, cudaMemcpyHostToDevice));
@@ -468,7 +494,7 @@ extern "C" int uvg_b200_frame_submit(uvg_b200_frame *h, const void *src, size_t 
     // rows the band reads: one above, and below it what the left reference column of a 32x32 block at the band's
     // last rows reaches (Y - 1 + 2n)
     const int y0 = max(0, ctu_row_begin * kCtu - 1), y1 = min(H, ctu_row_end * kCtu + kCtu);
-    UVGB_TRY(cudaMemcpy2DAsync(f->d_plane + (size_t)y0 * W, W, static_cast<const uint8_t *>(src) + (size_t)y0 * src_stride,
+    UVGB_TRY(cudaMemcpy2DAsync(f->d_plane + (size_t)y0 * f->pitch, f->pitch, static_cast<const uint8_t *>(src) + (size_t)y0 * src_stride,
                                src_stride, W, y1 - y0, cudaMemcpyHostToDevice, st));
   }
   Geo g{ W, H, f->ctu_cols, ctu_begin };
@@ -477,13 +503,8 @@ extern "C" int uvg_b200_frame_submit(uvg_b200_frame *h, const void *src, size_t 
   for (int i = 0; i < c.n_levels; ++i) {
     Level &l = f->lv[i];
     const size_t nb = (size_t)band_ctus * l.ppc;
-    const size_t total = nb * (size_t)(l.n * l.n + 2 * (2 * l.n + 4));
-    size_t grid = (total + 255) / 256;
-    if (grid > cap) grid = cap;
-    frame_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(f->d_plane, W, g, l.n, l.ppc, nb, l.d_orig, l.d_refs);
-    UVGB_LAUNCH_CHECK();
-    uvg_b200_blocks A; A.base = l.d_orig; A.stride = (uint32_t)l.n; A.blocks_per_row = 1; A.col_pitch = 0; A.row_pitch = (uint64_t)l.n * l.n;
-    if (uvg_b200_intra_rough_dev(8, l.n, &A, l.d_refs, l.modes, l.k, l.d_cost, nb, st)) return 1;
+    const PlaneSrc ps{ f->d_plane, f->pitch, W, H, f->ctu_cols, ctu_begin };
+    if (launch_intra_rough_plane(l.n, ps, l.modes, l.k, l.d_cost, nb, st)) return 1;
     frame_topk_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(l.d_cost, nb, l.k, c.n_best, l.d_modes, l.d_best);
     UVGB_LAUNCH_CHECK();
     if (d2h) {
@@ -499,13 +520,15 @@ extern "C" int uvg_b200_frame_submit(uvg_b200_frame *h, const void *src, size_t 
     TuSize &t = f->tu[i];
     const Level &sl = f->lv[t.src];
     const size_t nt = (size_t)band_ctus * t.per_ctu;
-    const int nn = t.n * t.n, tpc = nn >= 256 ? 1 : 256 / nn;
-    const size_t smem = (size_t)tpc * 4 * (2 * t.n + 12);
+    // TUs per CTA chosen so that the 8-pixel row items of a CTA's TUs fill its 256 threads
+    const int nn = t.n * t.n, tpc = t.n == 4 ? 64 : t.n == 8 ? 32 : t.n == 16 ? 8 : 2;
+    const size_t smem = (size_t)tpc * (4 * (2 * t.n + 12) + t.n + 8 + nn);
     const TuSel sel{ sl.n, sl.ppc, c.n_best, sl.d_best };
     const unsigned grid = (unsigned)((nt + tpc - 1) / tpc);
-    if (tpc == 16) frame_tu_predict_kernel<16><<<grid, 256, smem, st>>>(f->d_plane, W, g, t.n, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
-    else if (tpc == 4) frame_tu_predict_kernel<4><<<grid, 256, smem, st>>>(f->d_plane, W, g, t.n, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
-    else frame_tu_predict_kernel<1><<<grid, 256, smem, st>>>(f->d_plane, W, g, t.n, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
+    if (t.n == 4) frame_tu_predict_kernel<4, 64><<<grid, 256, smem, st>>>(f->d_plane, f->pitch, g, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
+    else if (t.n == 8) frame_tu_predict_kernel<8, 32><<<grid, 256, smem, st>>>(f->d_plane, f->pitch, g, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
+    else if (t.n == 16) frame_tu_predict_kernel<16, 8><<<grid, 256, smem, st>>>(f->d_plane, f->pitch, g, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
+    else frame_tu_predict_kernel<32, 2><<<grid, 256, smem, st>>>(f->d_plane, f->pitch, g, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
     UVGB_LAUNCH_CHECK();
     uvg_b200_blocks R, P, O;
     R.base = t.d_ref; P.base = t.d_pred; O.base = t.d_rec;

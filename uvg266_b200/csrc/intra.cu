@@ -95,13 +95,6 @@ intra_predict_kernel(const Pix *__restrict__ refs, Pix *__restrict__ preds, size
 // reference is fetched as 4 aligned words and funnel-shifted; the filter is a packed s8x4 word.
 // Negative angles extend the main reference with the projected side reference (:145-156) into a
 // small per-warp scratch row that ends exactly where index 0 of the main row begins.
-__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
-{
-  int d;
-  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-
 template <int N>
 struct RoughCfg {
   static constexpr int NS = N / 8;                   // 8-pixel strips per block row
@@ -112,58 +105,12 @@ struct RoughCfg {
   static constexpr int OP = N * N + 8 * NS;          // per-block stride of the original (bank spread)
 };
 
-// One row (8 pixels: work-row r, work-columns 8*sx..8*sx+7) of an angular prediction.
-template <int N>
-__device__ __forceinline__ void angular_row8(const ModeParam &mp, const uint8_t *mainr, const uint8_t *side,
-                                             const uint8_t *ext0, int r, int sx, int lim, uint32_t &lo, uint32_t &hi)
-{
-  const int dpos = (r + 1) * mp.sample_disp, di = dpos >> 5, fr = dpos & 31;
-  int cw;
-  if (!mp.frac) cw = 64 << 8;                                              // integer slope: copy tap 1
-  else if (mp.cubic) cw = *reinterpret_cast<const int *>(c_cubic[fr]);
-  else { const int h = fr >> 1; cw = (16 - h) | ((32 - h) << 8) | ((16 + h) << 16) | (h << 24); }
-  const int i0 = di + 8 * sx, b0 = i0 & ~3, sh = (i0 & 3) * 8;
-  uint32_t W[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int b = b0 + 4 * j;
-    W[j] = *reinterpret_cast<const uint32_t *>((b >= 0 ? mainr : ext0) + b);
-  }
-  const uint32_t A0 = __funnelshift_r(W[0], W[1], sh), A1 = __funnelshift_r(W[1], W[2], sh),
-                 A2 = __funnelshift_r(W[2], W[3], sh);
-  int v[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t a = c < 4 ? A0 : A1, b = c < 4 ? A1 : A2;
-    const uint32_t win = (c & 3) ? __funnelshift_r(a, b, 8 * (c & 3)) : a;
-    v[c] = min(max(dp4a_us(win, cw, 32) >> 6, 0), 255);
-  }
-  if (mp.pdpc) {
-    if (mp.sample_disp == 0) {                                            // :254-280
-      const int d = (int)side[1 + r] - (int)mainr[0];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int cc = 8 * sx + c;
-        if (cc < lim) v[c] = min(max(v[c] + (((32 >> ((2 * cc) >> mp.scale)) * d + 32) >> 6), 0), 255);
-      }
-    } else {                                                               // :234-251
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int cc = 8 * sx + c;
-        if (cc < lim) {
-          const int l = side[r + ((256 + (cc + 1) * mp.inv_angle) >> 9) + 1];
-          v[c] = (v[c] + (((32 >> ((2 * cc) >> mp.scale)) * (l - v[c]) + 32) >> 6)) & 255;
-        }
-      }
-    }
-  }
-  lo = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-  hi = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
-}
-
-template <int N>
+// PLANE: block gb is CTU-major block (gb % per_ctu) of CTU ctu_begin + gb / per_ctu of the picture `src` (frame.cu);
+// original and reference rows come from the plane with border replication, `A` / `refs` are unused.
+template <int N, bool PLANE>
 __global__ void __launch_bounds__(128)
-intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restrict__ out, size_t n_blocks, ModeTable mt)
+intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restrict__ out, size_t n_blocks, ModeTable mt,
+                   PlaneSrc src)
 {
   using Cfg = RoughCfg<N>;
   constexpr int NS = Cfg::NS, BPC = Cfg::BPC, RS = Cfg::RS, BS = Cfg::BS, HEAD = Cfg::HEAD, OP = Cfg::OP;
@@ -172,19 +119,41 @@ intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restr
   __shared__ __align__(16) uint8_t s_ext[4][BPC][HEAD];
   __shared__ __align__(16) uint8_t s_orig[BPC * OP], s_origT[BPC * OP];
   __shared__ int s_dc[BPC];
+  __shared__ int s_X[BPC], s_Y[BPC];
   const size_t first = (size_t)blockIdx.x * BPC;
   const int tid = threadIdx.x;
+  if (PLANE) {
+    if (tid < BPC) {
+      constexpr int BPR = 64 / N, PPC = BPR * BPR;
+      const size_t gb = min(first + tid, n_blocks - 1);
+      const int ctu = (int)(gb / PPC) + src.ctu_begin, j = (int)(gb % PPC);
+      s_X[tid] = (ctu % src.ctu_cols) * 64 + (j % BPR) * N;
+      s_Y[tid] = (ctu / src.ctu_cols) * 64 + (j / BPR) * N;
+    }
+    __syncthreads();
+  }
   // reference rows (tail replicated)
   for (int i = tid; i < BPC * 2 * RS; i += 128) {
     const int blk = i / (2 * RS), rem = i - blk * 2 * RS, row = rem / RS, x = rem - row * RS;
-    const size_t gb = min(first + blk, n_blocks - 1);
-    s_rows[blk * BS + row * RS + x] = __ldg(refs + gb * (size_t)(2 * GP) + row * GP + min(x, 2 * N));
+    if (PLANE) {
+      const int xx = min(x, 2 * N), X = s_X[blk], Y = s_Y[blk];
+      const int sx = row ? X - 1 : X - 1 + xx, sy = row ? Y - 1 + xx : Y - 1;
+      s_rows[blk * BS + row * RS + x] = __ldg(src.plane + (size_t)min(max(sy, 0), src.H - 1) * src.stride + min(max(sx, 0), src.W - 1));
+    } else {
+      const size_t gb = min(first + blk, n_blocks - 1);
+      s_rows[blk * BS + row * RS + x] = __ldg(refs + gb * (size_t)(2 * GP) + row * GP + min(x, 2 * N));
+    }
   }
   // original blocks, as they are and transposed
   for (int i = tid; i < BPC * N * N; i += 128) {
     const int blk = i / (N * N), p = i - blk * N * N, y = p / N, x = p - y * N;
-    const size_t gb = min(first + blk, n_blocks - 1);
-    const uint8_t v = __ldg(static_cast<const uint8_t *>(A.base) + A.offset(gb) + (size_t)y * A.stride + x);
+    uint8_t v;
+    if (PLANE) {
+      v = __ldg(src.plane + (size_t)min(s_Y[blk] + y, src.H - 1) * src.stride + min(s_X[blk] + x, src.W - 1));
+    } else {
+      const size_t gb = min(first + blk, n_blocks - 1);
+      v = __ldg(static_cast<const uint8_t *>(A.base) + A.offset(gb) + (size_t)y * A.stride + x);
+    }
     s_orig[blk * OP + p] = v;
     s_origT[blk * OP + x * N + y] = v;
   }
@@ -242,7 +211,7 @@ intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restr
           const int r = sy * 8 + rr;
           const uint2 o = *reinterpret_cast<const uint2 *>(orig + r * N);
           wo[rr][0] = o.x; wo[rr][1] = o.y;
-          angular_row8<N>(mp, mainr, side, ext0, r, sx, lim, wc[rr][0], wc[rr][1]);
+          angular_row8(mp, mainr, side, ext0, r, sx, lim, wc[rr][0], wc[rr][1]);
         }
         unsigned s1 = 0;
         satd += satd8_words_u8<true>(wo, wc, s1);
@@ -428,9 +397,26 @@ extern "C" int uvg_b200_intra_rough_dev(int bitdepth, int n, const uvg_b200_bloc
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint8_t *r = static_cast<const uint8_t *>(refs);
   auto grid = [&](int bpc) { return (unsigned)((n_blocks + bpc - 1) / bpc); };
-  if (n == 8) intra_rough_kernel<8><<<grid(RoughCfg<8>::BPC), 128, 0, st>>>(A, r, out, n_blocks, mt);
-  else if (n == 16) intra_rough_kernel<16><<<grid(RoughCfg<16>::BPC), 128, 0, st>>>(A, r, out, n_blocks, mt);
-  else intra_rough_kernel<32><<<grid(RoughCfg<32>::BPC), 128, 0, st>>>(A, r, out, n_blocks, mt);
+  const PlaneSrc none{};
+  if (n == 8) intra_rough_kernel<8, false><<<grid(RoughCfg<8>::BPC), 128, 0, st>>>(A, r, out, n_blocks, mt, none);
+  else if (n == 16) intra_rough_kernel<16, false><<<grid(RoughCfg<16>::BPC), 128, 0, st>>>(A, r, out, n_blocks, mt, none);
+  else intra_rough_kernel<32, false><<<grid(RoughCfg<32>::BPC), 128, 0, st>>>(A, r, out, n_blocks, mt, none);
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+int uvgb::launch_intra_rough_plane(int n, const PlaneSrc &src, const int8_t *modes, int k, uint32_t *out, size_t n_blocks,
+                                   cudaStream_t st)
+{
+  if (n != 8 && n != 16 && n != 32) { set_error("intra_rough: n must be 8, 16 or 32"); return 1; }
+  ModeTable mt;
+  if (fill_modes(mt, n, modes, k)) return 1;
+  if (n_blocks == 0) return 0;
+  const Blocks none{};
+  auto grid = [&](int bpc) { return (unsigned)((n_blocks + bpc - 1) / bpc); };
+  if (n == 8) intra_rough_kernel<8, true><<<grid(RoughCfg<8>::BPC), 128, 0, st>>>(none, nullptr, out, n_blocks, mt, src);
+  else if (n == 16) intra_rough_kernel<16, true><<<grid(RoughCfg<16>::BPC), 128, 0, st>>>(none, nullptr, out, n_blocks, mt, src);
+  else intra_rough_kernel<32, true><<<grid(RoughCfg<32>::BPC), 128, 0, st>>>(none, nullptr, out, n_blocks, mt, src);
   UVGB_LAUNCH_CHECK();
   return 0;
 }

@@ -152,4 +152,92 @@ __device__ __forceinline__ int pred_pixel(const ModeParam &mp, const RefRows<Pix
   return v;
 }
 
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
+{
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+
+// One row (8 pixels: work-row r, work-columns 8*sx..8*sx+7) of an angular prediction.
+__device__ __forceinline__ void angular_row8(const ModeParam &mp, const uint8_t *mainr, const uint8_t *side,
+                                             const uint8_t *ext0, int r, int sx, int lim, uint32_t &lo, uint32_t &hi)
+{
+  const int dpos = (r + 1) * mp.sample_disp, di = dpos >> 5, fr = dpos & 31;
+  int cw;
+  if (!mp.frac) cw = 64 << 8;                                              // integer slope: copy tap 1
+  else if (mp.cubic) cw = *reinterpret_cast<const int *>(c_cubic[fr]);
+  else { const int h = fr >> 1; cw = (16 - h) | ((32 - h) << 8) | ((16 + h) << 16) | (h << 24); }
+  const int i0 = di + 8 * sx, b0 = i0 & ~3, sh = (i0 & 3) * 8;
+  uint32_t W[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int b = b0 + 4 * j;
+    W[j] = *reinterpret_cast<const uint32_t *>((b >= 0 ? mainr : ext0) + b);
+  }
+  const uint32_t A0 = __funnelshift_r(W[0], W[1], sh), A1 = __funnelshift_r(W[1], W[2], sh),
+                 A2 = __funnelshift_r(W[2], W[3], sh);
+  int v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t a = c < 4 ? A0 : A1, b = c < 4 ? A1 : A2;
+    const uint32_t win = (c & 3) ? __funnelshift_r(a, b, 8 * (c & 3)) : a;
+    v[c] = min(max(dp4a_us(win, cw, 32) >> 6, 0), 255);
+  }
+  if (mp.pdpc) {
+    if (mp.sample_disp == 0) {                                            // :254-280
+      const int d = (int)side[1 + r] - (int)mainr[0];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int cc = 8 * sx + c;
+        if (cc < lim) v[c] = min(max(v[c] + (((32 >> ((2 * cc) >> mp.scale)) * d + 32) >> 6), 0), 255);
+      }
+    } else {                                                               // :234-251
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int cc = 8 * sx + c;
+        if (cc < lim) {
+          const int l = side[r + ((256 + (cc + 1) * mp.inv_angle) >> 9) + 1];
+          v[c] = (v[c] + (((32 >> ((2 * cc) >> mp.scale)) * (l - v[c]) + 32) >> 6)) & 255;
+        }
+      }
+    }
+  }
+  lo = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+  hi = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+}
+
+
+// One row (8 pixels: row Y, columns 8*sx..8*sx+7) of a planar (kind 0) or DC (kind 1) prediction incl. PDPC
+// (intra-generic.c:306-360, :414-437; intra.c:236-273), n >= 4.
+__device__ __forceinline__ void planar_dc_row8(const ModeParam &mp, const uint8_t *top, const uint8_t *left, int dc, int n,
+                                               int l2, int Y, int sx, uint32_t &lo, uint32_t &hi)
+{
+  const int tr = top[n + 1], bl = left[n + 1], lY = left[Y + 1];
+  const int wT = 32 >> min(31, (Y << 1) >> mp.scale);
+  uint32_t w2[2] = { 0, 0 };
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int X = 8 * sx + c, tX = top[X + 1];
+    int v = dc;
+    if (mp.kind == 0) {
+      const int hor = (lY << l2) + (X + 1) * (tr - lY), ver = (tX << l2) + (Y + 1) * (bl - tX);
+      v = ((hor << l2) + (ver << l2) + (1 << (2 * l2))) >> (1 + 2 * l2);
+    }
+    if (mp.pdpc) {
+      const int wL = 32 >> min(31, (X << 1) >> mp.scale);
+      v = (v + ((wL * (lY - v) + wT * (tX - v) + 32) >> 6)) & 255;
+    }
+    w2[c >> 2] |= (uint32_t)v << (8 * (c & 3));
+  }
+  lo = w2[0]; hi = w2[1];
+}
+
+// Fused rough search straight from a picture plane (frame.cu): blocks in CTU-major order, originals and reference
+// rows read from the plane with border replication instead of from gathered arrays.
+struct PlaneSrc { const uint8_t *plane; int stride, W, H, ctu_cols, ctu_begin; };
+int launch_intra_rough_plane(int n, const PlaneSrc &src, const int8_t *modes, int k, uint32_t *out, size_t n_blocks,
+                             cudaStream_t st);
+
 }  // namespace uvgb
