@@ -500,6 +500,8 @@ def gpu_arm(args):
     # inside the timed region); e2e_v1 = round 1's step (candidate predictions uploaded), kept for comparison ----
     e2e = e2e_frame(torch, U, L, rank, world, args, barrier, dist, dev)
     e2e["numa"] = numa
+    strong = strong_frame(torch, U, L, rank, world, args, barrier, dist, dev)
+    inter = inter_exchange(torch, U, L, rank, world, dist, dev, stream) if world > 1 else None
     e2e_v1 = None if args.no_e2e_v1 else e2e_bench(torch, U, L, rough, tus, cfg, n_ctu, world, args, barrier, dist, dev)
 
     cpu_baseline = None
@@ -534,7 +536,7 @@ def gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config_dict(n_ctu),
             "algorithmic_bytes_per_step": step_bytes,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_v1": e2e_v1,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_v1": e2e_v1, "strong": strong, "inter": inter,
             "gpu_launches": int(launches) * world,
             "clocks": clocks, "step_gbps": step_bytes * args.steps / (ms_max * 1e-3) / 1e9,
         }
@@ -710,6 +712,105 @@ def e2e_frame(torch, U, L, rank, world, args, barrier, dist, dev):
             "frames_in_flight": inflight, "latency_ms_one_frame": lat_ms, "device_ms_resident": float(np.median(dev_ms)),
             "launches_per_step": int(launches) // k, "pcie_probe": probe,
             "api": "uvg_b200_frame_submit + uvg_b200_frame_wait (pinned host source plane; results in host memory)"}
+
+
+def strong_frame(torch, U, L, rank, world, args, barrier, dist, dev):
+    """Strong scaling of the same end-to-end work: ONE 4K picture per step, split into `world` bands of CTU rows (the
+    partition of uvg_b200_band_rows), every rank pushing its own band through the frame pipeline from host memory
+    (H2D of the band's rows + halo, kernels, D2H of the band's results). No collective: all-intra. ms per picture =
+    max over ranks."""
+    H = CTU_ROWS * CTU
+    cfg = U.FrameCfg.make(FRAME_W, H, FRAME_LEVELS, TUS, FRAME_NBEST, U.QuantCfg.make(QP, 8, 1, 0, 0), COST_WEIGHTS)
+    f = L.uvg_b200_frame_create(C.byref(cfg))
+    if not f:
+        raise RuntimeError("uvg_b200_frame_create: " + L.uvg_b200_last_error().decode())
+    hp = torch.empty((H, FRAME_W), dtype=torch.uint8, pin_memory=True)
+    hp.copy_(torch.from_numpy(synth_plane_rows([(0, r) for r in range(CTU_ROWS)])))
+    lo, hi = C.c_int(), C.c_int()
+    L.uvg_b200_band_rows(rank, world, CTU_ROWS, C.byref(lo), C.byref(hi))
+    res = U.FrameResult()
+
+    def one():
+        U.check(L.uvg_b200_frame_submit(f, hp.data_ptr(), FRAME_W, lo.value, hi.value, 0))
+        U.check(L.uvg_b200_frame_wait(f, C.byref(res)))
+    for _ in range(3):
+        one()
+    k = max(3, min(args.steps, args.e2e_steps))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        one()
+        if world > 1:
+            dist.barrier()                    # a picture is done when its last band is
+    secs = time.perf_counter() - t0
+    t = torch.tensor([secs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    L.uvg_b200_frame_destroy(f)
+    return {"ms_per_picture": 1e3 * secs / k, "value": CTU_COLS * CTU_ROWS * k / secs, "unit": "CTU/s", "bands": world,
+            "ctu_rows_of_rank0": [lo.value, hi.value] if rank == 0 else None, "steps": k,
+            "what": "one 3840x2160 picture per step split into CTU-row bands across the GPUs, frame_pass end to end from host memory"}
+
+
+def inter_exchange(torch, U, L, rank, world, dist, dev, stream):
+    """The one collective of the path (inter pictures) through the C ABI: every rank searches its band
+    (full-search SAD r = 32 of every 64x64 CTU, uvg_b200_sad_search_dev), writes its band of the new reference picture,
+    then uvg_b200_refpic_exchange (one NCCL group of per-band broadcasts, in place). Checked: after the exchange every
+    rank holds the whole picture."""
+    Hpad = CTU_ROWS * CTU
+    uid = (C.c_uint8 * 128)()
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        U.check(L.uvg_b200_comm_unique_id(uid))
+        idt.copy_(torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    raw = bytes(idt.cpu().numpy().tobytes())
+    comm = L.uvg_b200_comm_create(raw, rank, world)
+    if not comm:
+        return {"unavailable": L.uvg_b200_last_error().decode()}
+    full = [torch.from_numpy(synth_plane_rows([(f_, r) for r in range(CTU_ROWS)])).to(dev) for f_ in range(2)]
+    lo, hi = C.c_int(), C.c_int()
+    L.uvg_b200_band_rows(rank, world, CTU_ROWS, C.byref(lo), C.byref(hi))
+    lo, hi = lo.value, hi.value
+    n, rng_ = 64, 32
+    ys, xs = np.meshgrid(np.arange(lo * 64, hi * 64, n), np.arange(0, FRAME_W, n), indexing="ij")
+    cx = torch.from_numpy(xs.ravel().astype(np.int32)).to(dev); cy = torch.from_numpy(ys.ravel().astype(np.int32)).to(dev)
+    zero = torch.zeros_like(cx)
+    nb, side = cx.numel(), 2 * rng_ + 1
+    out = torch.zeros(nb * side * side, dtype=torch.int32, device=dev)
+    ref = full[0].clone(); cur = full[1]
+
+    def search():
+        U.check(L.uvg_b200_sad_search_dev(8, n, n, cur.data_ptr(), ref.data_ptr(), FRAME_W, Hpad, FRAME_W, cx.data_ptr(), cy.data_ptr(),
+                                          zero.data_ptr(), zero.data_ptr(), rng_, out.data_ptr(), nb, stream))
+
+    def exchange():
+        U.check(L.uvg_b200_refpic_exchange(comm, ref.data_ptr(), FRAME_W, Hpad, stream))
+    # correctness: band of the new picture in place, exchange, compare with the whole new picture
+    ref.zero_()
+    ref[lo * 64: hi * 64] = cur[lo * 64: hi * 64]
+    exchange()
+    torch.cuda.synchronize()
+    ok = torch.tensor([int(torch.equal(ref, cur))], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    for _ in range(3):
+        search(); exchange()
+    torch.cuda.synchronize(); dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    K = 8
+    ts, te = 0.0, 0.0
+    for _ in range(K):
+        ev[0].record(); search(); ev[1].record(); exchange(); ev[2].record()
+        torch.cuda.synchronize()
+        ts += ev[0].elapsed_time(ev[1]); te += ev[1].elapsed_time(ev[2])
+    t = torch.tensor([ts / K, te / K], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    L.uvg_b200_comm_destroy(comm)
+    return {"search_ms": float(t[0].item()), "exchange_ms": float(t[1].item()), "bytes": FRAME_W * Hpad,
+            "picture_complete_on_every_rank": bool(ok.item()), "nccl_version": L.uvg_b200_comm_nccl_version(),
+            "what": "per inter picture: full-search SAD r=32 of the rank's band, then uvg_b200_refpic_exchange (one NCCL group "
+                    "of per-band broadcasts, in place, luma plane)"}
 
 
 def pcie_probe(torch, dev):
