@@ -269,6 +269,12 @@ UVG_B200_API int uvg_b200_bipred_average_dev(int bitdepth, int w, int h,
                                              int src0_is_im, const void *src1, int src1_is_im,
                                              size_t n_blocks, void *stream);
 
+/* pixel_var (strategies-picture.h:150, picture-generic.c:1334-1357): variance of `len` pixels in double, squared
+ * deviations accumulated in index order like the reference (bit-exact doubles). Array a = arrays + a * pitch pixels;
+ * out: DEVICE array of n_arrays doubles. One CTA per array (the encoder calls it per picture and per 64x64 CTU). */
+UVG_B200_API int uvg_b200_pixel_var_dev(int bitdepth, const void *arrays, size_t pitch, uint32_t len,
+                                        double *out, size_t n_arrays, void *stream);
+
 /* ---------------------------------------------------------------------------------- */
 /* (3) Batched host entry points (H2D + kernels + D2H inside the call, synchronous)    */
 /* ---------------------------------------------------------------------------------- */
@@ -528,6 +534,8 @@ UVG_B200_API void uvg_b200_fme_filter_16(int step, const uint16_t *src, int src_
                                                   int src1_is_im, int w, int h);
 UVG_B200_DECL_MISC(8, uint8_t)
 UVG_B200_DECL_MISC(16, uint16_t)
+UVG_B200_API double uvg_b200_pixel_var_8(const uint8_t *buf, uint32_t len);
+UVG_B200_API double uvg_b200_pixel_var_16(const uint16_t *buf, uint32_t len);
 
 /* strategies-dct.h:44 dct_func (the typedef's unsigned return is never used; void here) */
 UVG_B200_API void uvg_b200_dct_4x4(int8_t bitdepth, const int16_t *in, int16_t *out);

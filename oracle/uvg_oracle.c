@@ -1361,3 +1361,17 @@ void orc_fme_filter(int step, const orc_pixel *src, int src_stride, int w, int h
     orc_sample_quarterpel_luma(w, h, p, src_stride, out + (size_t)j * w * h, w, mvx, mvy);
   }
 }
+
+/* pixel_var_generic, picture-generic.c:1334-1357: mean, then squared deviations accumulated in index order. */
+double orc_pixel_var(const orc_pixel *arr, uint32_t len)
+{
+  double sum = 0, var = 0;
+  for (uint32_t i = 0; i < len; ++i) sum += arr[i];
+  const double mean = sum / (double)len;
+  for (uint32_t i = 0; i < len; ++i) {
+    volatile double tmp = (double)arr[i] - mean;      /* two roundings: the difference, then the product */
+    var += tmp * tmp;
+  }
+  var /= len;
+  return var;
+}

@@ -156,6 +156,7 @@ void orc_sample_octpel_chroma_hi(int w, int h, const orc_pixel *src, int src_str
 
 void orc_fme_filter(int step, const orc_pixel *src, int src_stride, int w, int h, int off_x, int off_y, orc_pixel *out);
 
+double orc_pixel_var(const orc_pixel *arr, uint32_t len);
 /* ---- picture table leftovers: IBC hash and bi-prediction average ---------------------------------- */
 uint32_t orc_crc32c_nxn(int n, const orc_pixel *buf, uint32_t stride);
 void orc_bipred_average(orc_pixel *dst, int dst_stride, const void *src0, int src0_is_im, const void *src1,

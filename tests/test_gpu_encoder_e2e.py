@@ -85,6 +85,9 @@ CASES = [
     # motion search patterns of BASELINE config 3 (TZ) and the exhaustive one
     ("ldp_tz", 8, 192, 128, 3, ["--preset=ultrafast", "--gop=lp-g4d3t1", "--me=tz"]),
     ("ldp_full8", 8, 128, 64, 2, ["--preset=ultrafast", "--gop=lp-g4d3t1", "--me=full8"]),
+    # variance-adaptive quantisation: pixel_var (doubles, index-order accumulation) on the picture and on every CTU
+    ("intra_vaq", 8, 128, 128, 2, ["--preset=ultrafast", "-p", "1", "--vaq=5"]),
+    ("intra_vaq_10bit", 10, 128, 64, 1, ["--preset=ultrafast", "-p", "1", "--vaq=5"]),
 ]
 
 # One encode per BASELINE.json config at a frame size that has all four frame edges, interior CTUs and partial

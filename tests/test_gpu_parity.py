@@ -83,6 +83,30 @@ def test_empty_blocks_cost_nothing():
     assert U.dropin("hor_sad", 8)(ptr(pic), ptr(ref), 16, 0, 64, 64, 4, 0) == 0
 
 
+@pytest.mark.parametrize("bd", BDS)
+def test_pixel_var_bit_exact_doubles(bd):
+    """pixel_var: the variance the reference computes in double with index-order accumulation, reproduced bit for
+    bit (drop-in on arrays up to picture size, batched entry point on 64x64 CTUs)."""
+    import torch
+    O = load_oracle(bd)
+    O.orc_pixel_var.argtypes = [vp, C.c_uint32]; O.orc_pixel_var.restype = C.c_double
+    L = U.lib()
+    f = getattr(L, "uvg_b200_pixel_var_%s" % U.suffix(bd))
+    rng = np.random.default_rng(1950 + bd)
+    for n in (1, 5, 64, 4095, 4096, 4097, 64 * 64, 832 * 480, 1920 * 1080 + 1):
+        a = rnd_pix(rng, bd, n, extreme=(n == 4097))
+        assert f(ptr(a), n) == O.orc_pixel_var(ptr(a), n), n
+    ctus = rnd_pix(rng, bd, 300 * 4096)
+    d = torch.from_numpy(ctus.view(np.uint8) if bd == 8 else ctus.view(np.int16)).cuda()
+    out = torch.zeros(300, dtype=torch.float64, device="cuda")
+    U.check(L.uvg_b200_pixel_var_dev(bd, d.data_ptr(), 4096, 4096, out.data_ptr(), 300, None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    for i in range(300):
+        blk = np.ascontiguousarray(ctus[i * 4096:(i + 1) * 4096])
+        assert got[i] == O.orc_pixel_var(ptr(blk), 4096), i
+
+
 def test_kat_coeff_abs_sum():
     data, expected = K.coeff_sum_case()
     assert U.lib().uvg_b200_coeff_abs_sum(ptr(data), data.size) == expected

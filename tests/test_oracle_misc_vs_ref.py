@@ -38,3 +38,17 @@ def test_crc32c_and_bipred(bd):
             O.orc_bipred_average(ptr(d1), 64, ptr(srcs[0]), i0, ptr(srcs[1]), i1, w, h)
             R.H.refh_bipred_average(ptr(d2), ptr(srcs[0]), i0, ptr(srcs[1]), i1, w, h)
             assert (d1[:, :w] == d2[:, :w]).all(), (bd, w, h, i0, i1)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_pixel_var(bd):
+    """pixel_var (picture-generic.c:1334-1357): bit-exact doubles, incl. a picture-sized array."""
+    O, R = load_oracle(bd), load_ref(bd)
+    O.orc_pixel_var.argtypes = [vp, C.c_uint32]; O.orc_pixel_var.restype = C.c_double
+    f = R.fn("pixel_var", C.c_double, [vp, C.c_uint32])
+    rng = np.random.default_rng(6700 + bd)
+    for n in (1, 7, 64, 4096, 1024 * 1024 + 3):
+        a = rng.integers(0, 1 << bd, n).astype(pix_dtype(bd))
+        assert O.orc_pixel_var(ptr(a), n) == f(ptr(a), n)
+        flat = np.full(n, (1 << bd) - 1, pix_dtype(bd))
+        assert O.orc_pixel_var(ptr(flat), n) == f(ptr(flat), n) == 0.0

@@ -178,6 +178,9 @@ def lib():
     L.uvg_b200_frame_wait.argtypes = [vp, C.POINTER(FrameResult)]
     L.uvg_b200_frame_device_buffers.argtypes = [vp, C.POINTER(FrameDevice)]
     L.uvg_b200_device_read.argtypes = [vp, vp, sz]
+    L.uvg_b200_pixel_var_dev.argtypes = [i, vp, sz, C.c_uint32, vp, sz, vp]
+    for suf in ("8", "16"):
+        f = getattr(L, "uvg_b200_pixel_var_" + suf); f.argtypes = [vp, C.c_uint32]; f.restype = C.c_double
     L.uvg_b200_set_lfnst_tables.argtypes = [vp, vp]
     L.uvg_b200_band_rows.argtypes = [i, i, i, vp, vp]; L.uvg_b200_band_rows.restype = None
     L.uvg_b200_comm_unique_id.argtypes = [vp]

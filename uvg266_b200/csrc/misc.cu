@@ -3,9 +3,14 @@
 //       polynomial 0x82F63B78) over the block's pixel bytes, row by row;
 //   bipred_average          (picture-generic.c:1133-1247): rounded average of two predictions, each
 //       either pixels or the 14-bit intermediates of the "_hi" interpolation (ipol.cu).
-// pixel_var (:1334-1357) accumulates squared deviations in double in index order; a parallel
-// reduction cannot reproduce its rounding, so it stays with the reference's implementation.
+//   pixel_var               (picture-generic.c:1334-1357): variance of a pixel array in double. The mean is a sum of
+//       integers (exact in any order); the squared deviations are accumulated in INDEX ORDER, one rounding per
+//       addition, which no parallel reduction reproduces - so one thread walks the array in order while its warp
+//       streams the pixels through shared memory, and (v - mean)^2 comes from a per-array table of the <= 2^bitdepth
+//       distinct values (computed with the same two roundings as the reference's `tmp = v - mean; tmp * tmp`).
 #include "common.cuh"
+#include <mutex>
+#include <string.h>
 
 namespace uvgb {
 
@@ -57,6 +62,41 @@ __global__ void bipred_kernel(Blocks D, int w, int h, const void *__restrict__ s
   const int c = im1 ? (int)static_cast<const int16_t *>(s1)[i] : (int)(int16_t)(static_cast<const Pix *>(s1)[i] << up);
   Pix *d = const_cast<Pix *>(static_cast<const Pix *>(D.base)) + D.offset(b) + (size_t)y * D.stride + x;
   *d = (Pix)min(max((a + c + (1 << (shift - 1))) >> shift, 0), (1 << bitdepth) - 1);
+}
+
+// One CTA per array. out[a] = pixel_var(arrays + a * pitch, len).
+template <typename Pix>
+__global__ void __launch_bounds__(256)
+pixel_var_kernel(const Pix *__restrict__ arrays, size_t pitch, uint32_t len, int n_values, double *__restrict__ out)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *s_sq = reinterpret_cast<double *>(smem_raw);                    // [n_values]
+  Pix *s_chunk = reinterpret_cast<Pix *>(s_sq + n_values);                // [2][CH]
+  constexpr int CH = 4096;
+  __shared__ unsigned long long s_sum;
+  const Pix *p = arrays + (size_t)blockIdx.x * pitch;
+  if (threadIdx.x == 0) s_sum = 0;
+  __syncthreads();
+  unsigned long long part = 0;
+  for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) part += p[i];
+  atomicAdd(&s_sum, part);
+  __syncthreads();
+  const double mean = __ddiv_rn((double)s_sum, (double)len);               // sum / (double)len, :1346
+  for (int v = threadIdx.x; v < n_values; v += blockDim.x) {
+    const double tmp = __dsub_rn((double)v, mean);                         // (double)arr[i] - arr_mean
+    s_sq[v] = __dmul_rn(tmp, tmp);
+  }
+  double var = 0.0;
+  for (uint32_t base = 0, buf = 0; base < len; base += CH, buf ^= 1) {
+    const uint32_t cnt = min((uint32_t)CH, len - base);
+    Pix *c = s_chunk + buf * CH;
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) c[i] = p[base + i];
+    __syncthreads();                                                       // also orders the table before its first use
+    if (threadIdx.x == 0)
+      for (uint32_t i = 0; i < cnt; ++i) var = __dadd_rn(var, s_sq[c[i]]);  // var += tmp * tmp, in index order
+    // double buffering: the other threads go on to stage the next chunk while thread 0 is still adding
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = __ddiv_rn(var, (double)len);      // var /= len, :1354
 }
 
 }  // namespace uvgb
@@ -145,3 +185,46 @@ void bipred_leaf(Pix *dst, int dst_stride, const void *s0, int im0, const void *
   { bipred_leaf<PIX>(dst, dst_stride, src0, src0_is_im, src1, src1_is_im, w, h); }
 UVGB_MISC_LEAVES(8, uint8_t)
 UVGB_MISC_LEAVES(16, uint16_t)
+
+// pixel_var of n_arrays arrays of `len` pixels, array a at arrays + a * pitch (pixels). One CTA per array.
+extern "C" int uvg_b200_pixel_var_dev(int bitdepth, const void *arrays, size_t pitch, uint32_t len, double *out,
+                                      size_t n_arrays, void *stream)
+{
+  if (ensure_init()) return 1;
+  if (bitdepth < 8 || bitdepth > 12) { set_error("pixel_var: bitdepth %d unsupported", bitdepth); return 1; }
+  if (n_arrays == 0) return 0;
+  if (len == 0) { set_error("pixel_var: empty array"); return 1; }
+  const int nv = 1 << bitdepth, pix = bitdepth == 8 ? 1 : 2;
+  const size_t smem = (size_t)nv * sizeof(double) + 2 * 4096 * pix;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bitdepth == 8) {
+    pixel_var_kernel<uint8_t><<<(unsigned)n_arrays, 256, smem, st>>>(static_cast<const uint8_t *>(arrays), pitch, len, nv, out);
+  } else {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] { err = cudaFuncSetAttribute(pixel_var_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); });
+    UVGB_TRY(err);
+    pixel_var_kernel<uint16_t><<<(unsigned)n_arrays, 256, smem, st>>>(static_cast<const uint16_t *>(arrays), pitch, len, nv, out);
+  }
+  UVGB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename Pix>
+static double dropin_pixel_var(const Pix *buf, uint32_t len)
+{
+  if (ensure_init()) die();
+  Staging &s = tls_staging();
+  const size_t bytes = ((size_t)len * sizeof(Pix) + 255) / 256 * 256;
+  if (s.ensure(16, bytes + 16)) die();
+  UVGB_MUST(cudaMemcpyAsync(s.d_buf, buf, (size_t)len * sizeof(Pix), cudaMemcpyHostToDevice, s.stream));
+  double *d_out = reinterpret_cast<double *>(s.d_buf + bytes);
+  if (uvg_b200_pixel_var_dev(dropin_bitdepth(sizeof(Pix)), s.d_buf, len, len, d_out, 1, s.stream)) die();
+  UVGB_MUST(cudaMemcpyAsync(s.h_pin, d_out, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  UVGB_MUST(cudaStreamSynchronize(s.stream));
+  double r;
+  memcpy(&r, s.h_pin, sizeof(r));
+  return r;
+}
+extern "C" double uvg_b200_pixel_var_8(const uint8_t *buf, uint32_t len) { return dropin_pixel_var<uint8_t>(buf, len); }
+extern "C" double uvg_b200_pixel_var_16(const uint16_t *buf, uint32_t len) { return dropin_pixel_var<uint16_t>(buf, len); }

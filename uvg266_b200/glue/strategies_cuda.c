@@ -138,6 +138,7 @@ static void bipred_average_cuda(lcu_t *const lcu, const yuv_t *const px_L0, cons
                          i1 ? (const void *)im_L1->v : (const void *)px_L1->v, i1, pu_w / 2, pu_h / 2);
   }
 }
+static double pixel_var_cuda(const uvg_pixel *buf, const uint32_t len) { return B200(pixel_var)(buf, len); }
 static uint32_t crc32c_4x4_cuda(const uvg_pixel *buf, uint32_t pic_stride) { return B200(crc32c_4x4)(buf, pic_stride); }
 static uint32_t crc32c_8x8_cuda(const uvg_pixel *buf, uint32_t pic_stride) { return B200(crc32c_8x8)(buf, pic_stride); }
 
@@ -357,8 +358,7 @@ int uvg_strategy_register_picture_cuda(void *opaque, uint8_t bitdepth)
   REG("generate_residual", generate_residual_func, generate_residual_cuda);
   REG("bipred_average", inter_recon_bipred_func, bipred_average_cuda);
   REG("crc32c_4x4", crc32c_4x4_func, crc32c_4x4_cuda); REG("crc32c_8x8", crc32c_8x8_func, crc32c_8x8_cuda);
-  /* pixel_var accumulates in double in index order: not reproducible by a parallel reduction, left to
-   * the reference's implementation */
+  REG("pixel_var", pixel_var_func, pixel_var_cuda);
   return ok;
 }
 
