@@ -28,8 +28,8 @@ def make_yuv(path, w, h, frames, bd=8, seed=1234):
             f.write(c.tobytes()); f.write(c[::-1].copy().tobytes())
 
 
-def encode(bd, yuv, w, h, frames, opts, cuda, threads=0, groups=None, extra_env=None):
-    d = os.path.join(ROOT, "oracle", "_ref", "bd%d" % bd)
+def encode(bd, yuv, w, h, frames, opts, cuda, threads=0, groups=None, extra_env=None, patched=False):
+    d = os.path.join(ROOT, "oracle", "_ref", "bd%d%s" % (bd, "p" if patched else ""))
     exe = os.path.join(d, "uvg266")
     glue = os.path.join(ROOT, "uvg266_b200", "lib", "libuvg266_b200_glue%d.so" % bd)
     if not (os.path.exists(exe) and os.path.exists(glue)):
@@ -138,6 +138,27 @@ def test_lfnst_blocks_stay_in_the_fused_kernel(tmp_path, bd):
     md5_host, launches_host, _ = encode(bd, yuv, 128, 64, 2, opts, cuda=True, extra_env={"UVG266_B200_LFNST": "host"})
     assert md5_dev == md5_gen and md5_host == md5_gen, err[-1500:]
     assert launches_dev and launches_host and launches_dev < 0.8 * launches_host, (launches_dev, launches_host)
+
+
+@pytest.mark.parametrize("groups,threads", [("hook", 0), ("hook", 4), ("picture,dct,quant,hook", 4)])
+def test_patched_call_site_is_bitstream_identical(tmp_path, groups, threads):
+    """Row 8(f)-4: the reference built with glue/patches/search_intra_rough.patch scores all 67 modes of every square
+    8 / 16 / 32 luma CU of search_intra_rough through ONE uvg_b200_intra_rough_host call; the bitstream must be the
+    one the unmodified encoder writes."""
+    yuv = str(tmp_path / "hook.yuv")
+    make_yuv(yuv, 320, 192, 2)
+    opts = ["--preset=ultrafast", "-p", "1"]
+    md5_gen, _, _ = encode(8, yuv, 320, 192, 2, opts, cuda=False)
+    md5_patched_off, _, _ = encode(8, yuv, 320, 192, 2, opts, cuda=False, patched=True)
+    md5_hook, launches, err = encode(8, yuv, 320, 192, 2, opts, cuda=True, threads=threads, groups=groups, patched=True)
+    assert md5_patched_off == md5_gen
+    assert launches and launches > 50, err[-1500:]
+    assert md5_hook == md5_gen, "bitstream differs with the batched call site (%s)" % groups
+    # a slower preset walks more CU sizes and the full rough-search refinement
+    opts = ["--preset=medium", "-p", "1"]
+    md5_gen, _, _ = encode(8, yuv, 320, 192, 1, opts, cuda=False)
+    md5_hook, launches, err = encode(8, yuv, 320, 192, 1, opts, cuda=True, threads=threads, groups=groups, patched=True)
+    assert launches and md5_hook == md5_gen, err[-1500:]
 
 
 def test_multithreaded_encode_is_identical(tmp_path):

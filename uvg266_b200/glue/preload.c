@@ -9,6 +9,8 @@
  *
  *   LD_PRELOAD=libuvg266_b200_glue8.so uvg266 -i in.yuv ...
  *   UVG266_B200_GROUPS=picture,dct,quant[,intra][,ipol]  (default picture,dct,quant)   UVG266_B200_DISABLE=1 (off)
+ *   UVG266_B200_GROUPS=hook : no leaf strategies at all, only the batched call site of a reference built with
+ *                             glue/patches/search_intra_rough.patch (one launch per rough-searched CU)
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -22,6 +24,7 @@ int uvg_strategy_register_dct_cuda(void *opaque, uint8_t bitdepth);
 int uvg_strategy_register_quant_cuda(void *opaque, uint8_t bitdepth);
 int uvg_strategy_register_intra_cuda(void *opaque, uint8_t bitdepth);
 int uvg_strategy_register_ipol_cuda(void *opaque, uint8_t bitdepth);
+int uvg_b200_install_rough_hook_only(uint8_t bitdepth);
 
 typedef int (*registrar_t)(void *, uint8_t);
 unsigned long long uvg_b200_launch_count(void);
@@ -48,6 +51,7 @@ static int forward(const char *sym, const char *group, registrar_t cuda, void *o
   if (!next) { fprintf(stderr, "uvg266_b200: %s not found in the host library\n", sym); return 0; }
   int ok = next(opaque, bitdepth);
   if (ok && group_enabled(group)) ok = cuda(opaque, bitdepth);
+  else if (ok && !strcmp(group, "picture") && group_enabled("hook")) ok = uvg_b200_install_rough_hook_only(bitdepth);
   return ok;
 }
 

@@ -312,6 +312,8 @@ FME_STEP(filter_hpel_blocks_diag_luma_cuda, 1)
 FME_STEP(filter_qpel_blocks_hor_ver_luma_cuda, 2)
 FME_STEP(filter_qpel_blocks_diag_luma_cuda, 3)
 
+static void install_rough_hook(void);
+
 /* ---- registration ---------------------------------------------------------------- */
 static int device_ready(uint8_t bitdepth)
 {
@@ -334,10 +336,18 @@ static int device_ready(uint8_t bitdepth)
   do { fntype *const typed_ = fn;                                                                \
        ok &= uvg_strategyselector_register(opaque, type, STRATEGY_NAME, CUDA_PRIORITY, (void *)typed_); } while (0)
 
+int uvg_b200_install_rough_hook_only(uint8_t bitdepth)
+{
+  if (!device_ready(bitdepth)) return 0;
+  install_rough_hook();
+  return 1;
+}
+
 int uvg_strategy_register_picture_cuda(void *opaque, uint8_t bitdepth)
 {
   if (!device_ready(bitdepth)) return 0;
   int ok = 1;
+  install_rough_hook();
   REG("reg_sad", reg_sad_func, reg_sad_cuda);
   REG("sad_4x4", cost_pixel_nxn_func, sad_4_cuda); REG("sad_8x8", cost_pixel_nxn_func, sad_8_cuda); REG("sad_16x16", cost_pixel_nxn_func, sad_16_cuda);
   REG("sad_32x32", cost_pixel_nxn_func, sad_32_cuda); REG("sad_64x64", cost_pixel_nxn_func, sad_64_cuda);
@@ -375,7 +385,47 @@ int uvg_strategy_register_dct_cuda(void *opaque, uint8_t bitdepth)
   return ok;
 }
 
-/* mip_predict and the unused intra_pred_filtered_dc stay with the reference's implementations */
+/* ---- batched call site (row 8(f)-4): search_intra_rough through ONE launch ------------------------------------------
+ * A reference built with glue/patches/search_intra_rough.patch exports the pointer uvg_b200_rough_hook; when it is
+ * there the picture registrar installs this function: all 67 modes of a square 8 / 16 / 32 luma block predicted and
+ * scored min(SATD, 2 SAD) (get_cost_dual, search_intra.c:133-160) by the fused rough-search kernel. Returns 0 for
+ * blocks it does not cover (the encoder then walks its own mode-by-mode path). */
+typedef int (*rough_hook_t)(const uvg_intra_references *refs, const uvg_pixel *orig_block, int width, int height,
+                            unsigned *costs_out);
+static int rough_hook_cuda(const uvg_intra_references *refs, const uvg_pixel *orig_block, int width, int height,
+                           unsigned *costs_out)
+{
+#if UVG_BIT_DEPTH == 8
+  static const int8_t all_modes[67] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25,
+    26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56,
+    57, 58, 59, 60, 61, 62, 63, 64, 65, 66 };
+  if (width != height || (width != 8 && width != 16 && width != 32)) return 0;
+  uvg_pixel rows[2 * (2 * 32 + 4)];
+  const int gp = 2 * width + 4;
+  memcpy(rows, refs->ref.top, (2 * width + 1) * sizeof(uvg_pixel));
+  memcpy(rows + gp, refs->ref.left, (2 * width + 1) * sizeof(uvg_pixel));
+  uvg_b200_blocks o;
+  o.base = orig_block; o.stride = (uint32_t)width; o.blocks_per_row = 1; o.col_pitch = 0; o.row_pitch = (uint64_t)width * height;
+  if (uvg_b200_intra_rough_host(8, width, &o, (size_t)width * height, rows, all_modes, 67, costs_out, 1) != 0) {
+    fprintf(stderr, "uvg266_b200: %s\n", uvg_b200_last_error());
+    abort();
+  }
+  return 1;
+#else
+  (void)refs; (void)orig_block; (void)width; (void)height; (void)costs_out;
+  return 0;
+#endif
+}
+
+static void install_rough_hook(void)
+{
+  rough_hook_t *slot = (rough_hook_t *)dlsym(RTLD_DEFAULT, "uvg_b200_rough_hook");
+  const char *off = getenv("UVG266_B200_ROUGH_HOOK");
+  if (slot && !(off && !strcmp(off, "0"))) *slot = rough_hook_cuda;
+}
+
+/* mip_predict (its trained matrices are file-static in mip_data_generic.h, not exported, so they cannot be handed to the
+ * device at run time) and the unused intra_pred_filtered_dc stay with the reference's implementations */
 int uvg_strategy_register_intra_cuda(void *opaque, uint8_t bitdepth)
 {
   if (!device_ready(bitdepth)) return 0;
