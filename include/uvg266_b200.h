@@ -57,6 +57,8 @@ UVG_B200_API int uvg_b200_sm_count(void);
 /* Kernel launches issued by this library since load (all threads). bench.py reads it to
  * report gpu_launches. */
 UVG_B200_API uint64_t uvg_b200_launch_count(void);
+/* Launches of the tcgen05 + tensor-map-TMA rough-cost kernel (rough_tma.cu) since load. */
+UVG_B200_API uint64_t uvg_b200_rough_tma_launches(void);
 
 /* ---------------------------------------------------------------------------------- */
 /* Block addressing for the batched entry points                                       */

@@ -685,7 +685,7 @@ def test_full_size_properties():
     assert torch.equal(out1.long(), (d * d).sum(1))
 
 
-@pytest.mark.parametrize("mode", ["staged", "mma", "umma", "tma"])
+@pytest.mark.parametrize("mode", ["staged", "mma", "umma", "tma", "tc5"])
 def test_rough_cost_kernel_variants(mode):
     """The interchangeable rough-cost kernels (packed ALU, mma.sync IMMA, tcgen05/TMEM, TMA-fed) are
     selected once per process by UVG266_B200_ROUGH: run the batched parity test under each."""

@@ -143,6 +143,7 @@ def lib():
     L.uvg_b200_last_error.restype = C.c_char_p
     L.uvg_b200_version.restype = C.c_char_p
     L.uvg_b200_launch_count.restype = C.c_uint64
+    L.uvg_b200_rough_tma_launches.restype = C.c_uint64
     L.uvg_b200_host_alloc.restype = vp
     L.uvg_b200_host_alloc.argtypes = [sz]
     L.uvg_b200_host_free.argtypes = [vp]

@@ -11,6 +11,7 @@
 namespace uvgb {
 
 int launch_rough_umma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_items, int k, int n, cudaStream_t st);
+int launch_rough_tma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_items, int k, int n, cudaStream_t st);
 int launch_rough_mma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_items, int k, int n, cudaStream_t st);
 int launch_rough_staged(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_items, int k, int n,
                         cudaStream_t st);
@@ -645,14 +646,21 @@ extern "C" int uvg_b200_rough_cost_dev(int bitdepth, int n, const uvg_b200_block
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n_items = n_blocks * (size_t)k;
   if (bitdepth == 8) {
-    // dense candidates, three interchangeable kernels (all bit-exact, all in the GPU tests):
-    //   default           packed-ALU shared-memory staged kernel (rough.cu)       8x8 0.075 ms  16x16 0.081 ms
-    //   ROUGH=umma        Hadamard as tcgen05.mma kind::i8 into TMEM (rough_umma.cu)   0.082 ms        0.107 ms
-    //   ROUGH=mma         Hadamard as mma.sync IMMA (rough_mma.cu)                     0.090 ms        0.072 ms
-    //   ROUGH=tma         the staged kernel fed by cp.async.bulk                       0.081 ms        0.083 ms
-    // (one 4K frame of the bench workload on a B200, CUDA events). The default is the fastest
-    // measured per size: staged for 8x8, mma.sync for 16x16 / 32x32.
+    // dense candidates, interchangeable kernels (all bit-exact, all in the GPU tests); one 4K frame of the bench
+    // workload on a B200, CUDA events:                                                     8x8 k=23   16x16 k=24
+    //   tc5 (default where it applies: dense originals too, n = 8 / 16, k >= 10)
+    //                     tcgen05.mma kind::i8 fed by tensor-map TMA, H O H^T from the same
+    //                     MMA, accumulators in TMEM (rough_tma.cu)                          0.068 ms   0.060 ms
+    //   ROUGH=staged      packed-ALU shared-memory staged kernel (rough.cu)                 0.072 ms   0.081 ms
+    //   ROUGH=mma         Hadamard as mma.sync IMMA (rough_mma.cu)                          0.090 ms   0.070 ms
+    //   ROUGH=umma        round 1's tcgen05 kernel fed by per-thread cp.async (rough_umma.cu) 0.082 ms 0.107 ms
+    //   ROUGH=tma         the staged kernel fed by cp.async.bulk                            0.081 ms   0.083 ms
+    // Without ROUGH the fastest measured kernel that accepts the layout runs: tc5, else staged (8x8) / mma (>= 16x16).
     static const char *mode = getenv("UVG266_B200_ROUGH");
+    if (!mode || !strcmp(mode, "tc5")) {
+      const int rt = launch_rough_tma(A, B, out, n_items, k, n, st);
+      if (rt >= 0) return rt;
+    }
     const bool want_umma = mode && !strcmp(mode, "umma");
     const bool want_mma = mode ? !strcmp(mode, "mma") : n >= 16;
     if (want_umma) {
