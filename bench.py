@@ -396,7 +396,7 @@ def gpu_arm(args):
                         O=U.Blocks.dense(rec.data_ptr(), n, n), bytes=nt * (5 * n * n + 9)))
     step_bytes = sum(x["bytes"] for x in rough) + sum(x["bytes"] for x in tus)
 
-    names = ["rough_cost 8x8 k=23 (rough_staged_kernel<8>)", "rough_cost 16x16 k=24 (rough_mma_kernel<16>)",
+    names = ["rough_cost 8x8 k=23 (rough_tma_kernel<8>: tcgen05 + tensor-map TMA)", "rough_cost 16x16 k=24 (rough_tma_kernel<16>: tcgen05 + tensor-map TMA)",
              "quantize_residual 4x4 (fused_small_kernel<4>)", "quantize_residual 8x8 (fused_imma8_kernel)",
              "quantize_residual 16x16 (fused_imma_kernel<16>)", "quantize_residual 32x32 (fused_imma_kernel<32>)"]
     kbytes = [x["bytes"] for x in rough] + [x["bytes"] for x in tus]
@@ -466,9 +466,12 @@ def gpu_arm(args):
     di = int(np.argmax(per_kernel_ms))
     traffic = None
     try:   # DRAM bytes per launch of the same kernel on the same inputs, from the committed ncu capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["bytes_per_launch"]
-        key = names[di].split("(")[1].rstrip(")").rstrip(">")          # e.g. "rough_staged_kernel<16"
-        traffic = next((v for k, v in tr.items() if key in k.replace("unsigned char, ", "")), None)
+        trf = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if not os.path.exists(trf):
+            trf = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tr = json.load(open(trf))["bytes_per_launch"]
+        key = names[di].split("(")[1].split(":")[0].rstrip(")").rstrip(">")          # e.g. "rough_tma_kernel<8"
+        traffic = next((v for k, v in tr.items() if key in k.replace("unsigned char, ", "").replace("(int)", "")), None)
     except (OSError, KeyError, IndexError):
         pass
     achieved = kbytes[di] / (per_kernel_ms[di] * 1e-3) / 1e9

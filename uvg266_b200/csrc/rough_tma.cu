@@ -21,7 +21,7 @@
 // Warp-specialised persistent CTA, mbarriers only in the steady state:
 //   warp 8, one lane : TMA producer - two cp.async.bulk.tensor.2d (UTMALDG) per tile: a 128 B x 112 row box of the
 //                      candidate matrix and a 128 B x 16 row box of the originals, both complete_tx on the stage's
-//                      full barrier; 3-stage ring. No thread touches global memory for operands.
+//                      full barrier; 4-stage ring. No thread touches global memory for operands.
 //   warp 9, one lane : MMA issuer - 4 x UTCIMMA into one of two 128-column TMEM accumulators, tcgen05.commit.
 //   warps 0-7        : two epilogue groups (alternate tiles), thread = tile row. Rows 112..127 publish H O H^T of
 //                      their blocks to shared memory (one named barrier per tile and group); every candidate row then
@@ -114,11 +114,11 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr)
 // K-major, N = 128 (N >> 3 << 17), M = 128 (M >> 4 << 24).
 constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
-constexpr int kRows = 128, kRowBytes = 128, kCandRows = 112, kOrigRows = 16, kTileBytes = kRows * kRowBytes,
-              kStages = 3, kAccCols = 128, kTmemCols = 256, kThreads = 320, kCtasPerSm = 2;
+constexpr int kRows = 128, kRowBytes = 128, kTileBytes = kRows * kRowBytes, kMaxOrigRows = 16,
+              kStages = 4, kAccCols = 128, kTmemCols = 256, kThreads = 320, kCtasPerSm = 2;
 constexpr int kSmemB = kRows * kRowBytes;                                  // 16 KB
 constexpr int kTOHalf = 68, kTOPitch = 2 * kTOHalf;                      // ints per 64-coefficient half / per table row;                                              // ints per table row (padded: rows of a warp's stores / loads spread over the banks)
-constexpr int kSmemTO = 2 * 2 * kOrigRows * kTOPitch * 4;                  // two groups x two buffers x 16 rows
+constexpr int kSmemTO = 2 * kMaxOrigRows * kTOPitch * 4;                   // two groups x (up to) 16 rows
 constexpr int kSmemTotal = kSmemB + kStages * kTileBytes + kSmemTO;
 
 __device__ __forceinline__ int sw128(int row, int chunk) { return row * kRowBytes + ((chunk ^ (row & 7)) << 4); }
@@ -132,11 +132,13 @@ __device__ __forceinline__ uint32_t fdivk(uint32_t x, const FastDivK &d)
 }  // namespace
 
 // n_cands: candidates in total (n_blocks * k). Candidate c of the launch belongs to block c / k.
-template <int N>
+// OR = rows of the tile given to the originals: 8 (k >= 20 candidates per block: 120 candidate rows per tile) or 16 (k >= 10).
+template <int N, int OR>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 rough_tma_kernel(const __grid_constant__ CUtensorMap map_cand, const __grid_constant__ CUtensorMap map_orig,
                  uint32_t *__restrict__ out, uint32_t n_cands, FastDivK kd)
 {
+  constexpr int kCandRows = kRows - OR;
   constexpr int CPR = N == 8 ? 2 : 1;             // candidates per tile row (N = 8) ...
   constexpr int RPC = N == 8 ? 1 : 2;             // ... or tile rows per candidate (N = 16)
   constexpr int CAND_PER_TILE = kCandRows * CPR / RPC;
@@ -145,7 +147,7 @@ rough_tma_kernel(const __grid_constant__ CUtensorMap map_cand, const __grid_cons
   extern __shared__ __align__(1024) uint8_t dyn[];
   uint8_t *const sB = dyn;
   uint8_t *const sA = dyn + kSmemB;
-  int *const sTO = reinterpret_cast<int *>(dyn + kSmemB + kStages * kTileBytes);     // [group][buffer][16][kTOPitch]
+  int *const sTO = reinterpret_cast<int *>(dyn + kSmemB + kStages * kTileBytes);     // [group][16][kTOPitch]
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -194,7 +196,9 @@ rough_tma_kernel(const __grid_constant__ CUtensorMap map_cand, const __grid_cons
     for (uint32_t i = grp; i < my_tiles; i += 2) {
       const uint32_t tile = tile0 + i * tstep, st = i % kStages;
       const uint8_t *tileA = sA + st * kTileBytes;
-      int *const myTO = sTO + (grp * 2 + ((i >> 1) & 1)) * (kOrigRows * kTOPitch);   // double-buffered: one barrier per tile
+      // One table per group and ONE barrier per tile: the table of tile i + 2 is written only after acc_full(i + 2), i.e.
+      // after every thread of the group has arrived on acc_empty(i) - which each does after its last table read of tile i.
+      int *const myTO = sTO + grp * (kMaxOrigRows * kTOPitch);
       const uint32_t c_first = tile * CAND_PER_TILE, b_first = fdivk(c_first, kd);
       // first row of the originals' box in units of original-matrix rows (the producer computes the same)
       const uint32_t orow0 = N == 8 ? (b_first >> 1) : 2 * b_first;
@@ -367,6 +371,7 @@ int launch_rough_tma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_i
 {
   if (n != 8 && n != 16) return -1;
   if (k < 10) return -1;                                   // 16 original rows per tile must cover the tile's blocks
+  const int orows = k >= 20 ? 8 : 16, crows = 128 - orows;
   if (B.stride != (uint32_t)n || B.bpr != 1 || B.row_pitch != (uint64_t)(n * n)) return -1;   // dense candidates
   if (A.stride != (uint32_t)n || A.bpr != 1 || A.row_pitch != (uint64_t)(n * n)) return -1;   // dense originals
   if ((reinterpret_cast<uintptr_t>(B.base) | reinterpret_cast<uintptr_t>(A.base)) & 127) return -1;
@@ -375,26 +380,36 @@ int launch_rough_tma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_i
   if (n == 8 && (n_blocks & 1)) return -1;                 // rows hold pairs of 8x8 blocks
   CUtensorMap mc, mo;
   const uint64_t cand_rows = n_items * (uint64_t)(n * n) / 128, orig_rows = n_blocks * (uint64_t)(n * n) / 128;
-  if (make_map(&mc, B.base, cand_rows, kCandRows) || make_map(&mo, A.base, orig_rows, kOrigRows)) return -1;
+  if (make_map(&mc, B.base, cand_rows, (uint32_t)crows) || make_map(&mo, A.base, orig_rows, (uint32_t)orows)) return -1;
   FastDivK kd;
   kd.k = (uint32_t)k;
   kd.magic = k > 1 ? (~0ull / (uint64_t)k) + 1 : 0;
-  const size_t per_tile = n == 8 ? 224 : 56;
+  const size_t per_tile = n == 8 ? 2 * crows : crows / 2;
   size_t grid = (n_items + per_tile - 1) / per_tile;
   const size_t cap = (size_t)sm_count() * kCtasPerSm;
   if (grid > cap) grid = cap;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rough_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(rough_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     // two CTAs (2 x ~99 KB) per SM need the full shared-memory carve-out
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(rough_tma_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(rough_tma_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    auto setup = [](const void *fn) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      return e;
+    };
+    attr_err = setup(reinterpret_cast<const void *>(rough_tma_kernel<8, 8>));
+    if (attr_err == cudaSuccess) attr_err = setup(reinterpret_cast<const void *>(rough_tma_kernel<8, 16>));
+    if (attr_err == cudaSuccess) attr_err = setup(reinterpret_cast<const void *>(rough_tma_kernel<16, 8>));
+    if (attr_err == cudaSuccess) attr_err = setup(reinterpret_cast<const void *>(rough_tma_kernel<16, 16>));
   });
   UVGB_TRY(attr_err);
-  if (n == 8) rough_tma_kernel<8><<<(unsigned)grid, kThreads, kSmemTotal, st>>>(mc, mo, out, (uint32_t)n_items, kd);
-  else rough_tma_kernel<16><<<(unsigned)grid, kThreads, kSmemTotal, st>>>(mc, mo, out, (uint32_t)n_items, kd);
+  if (n == 8) {
+    if (orows == 8) rough_tma_kernel<8, 8><<<(unsigned)grid, kThreads, kSmemTotal, st>>>(mc, mo, out, (uint32_t)n_items, kd);
+    else rough_tma_kernel<8, 16><<<(unsigned)grid, kThreads, kSmemTotal, st>>>(mc, mo, out, (uint32_t)n_items, kd);
+  } else {
+    if (orows == 8) rough_tma_kernel<16, 8><<<(unsigned)grid, kThreads, kSmemTotal, st>>>(mc, mo, out, (uint32_t)n_items, kd);
+    else rough_tma_kernel<16, 16><<<(unsigned)grid, kThreads, kSmemTotal, st>>>(mc, mo, out, (uint32_t)n_items, kd);
+  }
   UVGB_LAUNCH_CHECK();
   g_rough_tma_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
