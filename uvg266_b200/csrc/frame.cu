@@ -108,14 +108,16 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
     smem_raw[tu * per_tu + row * RS + (rem - row * RS)] = __ldg(plane + (size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1));
   }
   __syncthreads();
-  for (int i = tid; i < TPC * 2 * RS; i += 256) {            // intra_filter_reference, intra.c:190-225
-    const int tu = i / (2 * RS), rem = i - tu * 2 * RS, row = rem / RS, x = rem - row * RS;
-    const uint8_t *top = smem_raw + tu * per_tu, *left = top + RS, *src = row ? left : top;
-    int v;
-    if (x == 0) v = ((int)left[1] + 2 * (int)left[0] + (int)top[1] + 2) >> 2;
-    else if (x < 2 * n) v = ((int)src[x - 1] + 2 * (int)src[x] + (int)src[x + 1] + 2) >> 2;
-    else v = src[2 * n];
-    smem_raw[tu * per_tu + (2 + row) * RS + x] = (uint8_t)v;
+  if (N > 4) {                                               // no 4x4 mode uses the smoothed rows (intra.c:691-712: n*n > 32 / n != 4)
+    for (int i = tid; i < TPC * 2 * RS; i += 256) {          // intra_filter_reference, intra.c:190-225
+      const int tu = i / (2 * RS), rem = i - tu * 2 * RS, row = rem / RS, x = rem - row * RS;
+      const uint8_t *top = smem_raw + tu * per_tu, *left = top + RS, *src = row ? left : top;
+      int v;
+      if (x == 0) v = ((int)left[1] + 2 * (int)left[0] + (int)top[1] + 2) >> 2;
+      else if (x < 2 * n) v = ((int)src[x - 1] + 2 * (int)src[x] + (int)src[x + 1] + 2) >> 2;
+      else v = src[2 * n];
+      smem_raw[tu * per_tu + (2 + row) * RS + x] = (uint8_t)v;
+    }
   }
   if (tid < TPC) {                                           // intra_pred_dc, intra.c:236-273
     const uint8_t *top = smem_raw + tid * per_tu, *left = top + RS;
@@ -321,6 +323,8 @@ struct Frame {
   uvg_b200_frame_result res;
   int ctu_begin = 0, ctu_end = 0, flags = 0;
   bool in_flight = false;
+  struct PassGraph { bool used = false; int ctu_begin = 0, ctu_end = 0, flags = 0, seen = 0; uint64_t launches = 0; cudaGraphExec_t exec = nullptr; };
+  PassGraph graphs[4];
 };
 
 static void frame_release(Frame *f)
@@ -340,6 +344,7 @@ static void frame_release(Frame *f)
     if (f->ev_level[i]) cudaEventDestroy(f->ev_level[i]);
     if (f->ev_tu[i]) cudaEventDestroy(f->ev_tu[i]);
   }
+  for (Frame::PassGraph &g : f->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (cudaEvent_t e : { f->ev_pack, f->ev_total, f->ev_t0, f->ev_t1 }) if (e) cudaEventDestroy(e);
   if (f->s_main) cudaStreamDestroy(f->s_main);
   if (f->s_copy) cudaStreamDestroy(f->s_copy);
@@ -474,29 +479,17 @@ extern "C" void uvg_b200_frame_destroy(uvg_b200_frame *h)
   delete h;
 }
 
-extern "C" int uvg_b200_frame_submit(uvg_b200_frame *h, const void *src, size_t src_stride, int ctu_row_begin,
-                                     int ctu_row_end, int flags)
+// Everything of a pass between the H2D copy of the source rows and the last copy whose size is only known afterwards:
+// kernels on s_main, D2H copies on s_copy behind events, s_copy joined back into s_main at the end. Issued directly the
+// first time a (band, flags) configuration is seen (that run also performs every lazy one-time initialisation of the
+// kernels it calls), captured into a CUDA graph the second time and replayed from then on: ~20 launches and ~15 copies
+// become one cudaGraphLaunch (no launch gaps on the device, microseconds of host time per picture).
+static int enqueue_pass(Frame *f, int ctu_begin, int ctu_end, int flags)
 {
-  if (!h) { set_error("frame: NULL handle"); return 1; }
-  Frame *f = &h->f;
-  if (f->in_flight) { set_error("frame: submit while a pass is in flight (call uvg_b200_frame_wait first)"); return 1; }
-  if (ctu_row_end <= 0 || ctu_row_end > f->ctu_rows) ctu_row_end = f->ctu_rows;
-  if (ctu_row_begin < 0 || ctu_row_begin >= ctu_row_end) { set_error("frame: CTU row range [%d,%d) is empty", ctu_row_begin, ctu_row_end); return 1; }
   const uvg_b200_frame_cfg &c = f->cfg;
-  const int W = f->W, H = f->H;
-  const int ctu_begin = ctu_row_begin * f->ctu_cols, ctu_end = ctu_row_end * f->ctu_cols, band_ctus = ctu_end - ctu_begin;
-  f->ctu_begin = ctu_begin; f->ctu_end = ctu_end; f->flags = flags;
+  const int W = f->W, H = f->H, band_ctus = ctu_end - ctu_begin;
   cudaStream_t st = f->s_main, sc = f->s_copy;
   const bool d2h = !(flags & UVG_B200_FRAME_NO_D2H);
-  UVGB_TRY(cudaEventRecord(f->ev_t0, st));
-  if (!(flags & UVG_B200_FRAME_NO_H2D)) {
-    if (!src) { set_error("frame: NULL source plane"); return 1; }
-    // rows the band reads: one above, and below it what the left reference column of a 32x32 block at the band's
-    // last rows reaches (Y - 1 + 2n)
-    const int y0 = max(0, ctu_row_begin * kCtu - 1), y1 = min(H, ctu_row_end * kCtu + kCtu);
-    UVGB_TRY(cudaMemcpy2DAsync(f->d_plane + (size_t)y0 * f->pitch, f->pitch, static_cast<const uint8_t *>(src) + (size_t)y0 * src_stride,
-                               src_stride, W, y1 - y0, cudaMemcpyHostToDevice, st));
-  }
   Geo g{ W, H, f->ctu_cols, ctu_begin };
   const size_t cap = (size_t)sm_count() * 16;
   // ---- rough search --------------------------------------------------------------------------------------------
@@ -570,8 +563,62 @@ extern "C" int uvg_b200_frame_submit(uvg_b200_frame *h, const void *src, size_t 
       UVGB_TRY(cudaMemcpyAsync(f->h_off, f->d_off, (tu_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
     }
   }
+  if (d2h) {                                             // join: s_main's completion covers the copies
+    UVGB_TRY(cudaEventRecord(f->ev_total, sc));
+    UVGB_TRY(cudaStreamWaitEvent(st, f->ev_total, 0));
+  }
+  return 0;
+}
+
+extern "C" int uvg_b200_frame_submit(uvg_b200_frame *h, const void *src, size_t src_stride, int ctu_row_begin,
+                                     int ctu_row_end, int flags)
+{
+  if (!h) { set_error("frame: NULL handle"); return 1; }
+  Frame *f = &h->f;
+  if (f->in_flight) { set_error("frame: submit while a pass is in flight (call uvg_b200_frame_wait first)"); return 1; }
+  if (ctu_row_end <= 0 || ctu_row_end > f->ctu_rows) ctu_row_end = f->ctu_rows;
+  if (ctu_row_begin < 0 || ctu_row_begin >= ctu_row_end) { set_error("frame: CTU row range [%d,%d) is empty", ctu_row_begin, ctu_row_end); return 1; }
+  const int W = f->W, H = f->H;
+  const int ctu_begin = ctu_row_begin * f->ctu_cols, ctu_end = ctu_row_end * f->ctu_cols;
+  f->ctu_begin = ctu_begin; f->ctu_end = ctu_end; f->flags = flags;
+  cudaStream_t st = f->s_main;
+  UVGB_TRY(cudaEventRecord(f->ev_t0, st));
+  if (!(flags & UVG_B200_FRAME_NO_H2D)) {
+    if (!src) { set_error("frame: NULL source plane"); return 1; }
+    // rows the band reads: one above, and below it what the left reference column of a 32x32 block at the band's
+    // last rows reaches (Y - 1 + 2n)
+    const int y0 = max(0, ctu_row_begin * kCtu - 1), y1 = min(H, ctu_row_end * kCtu + kCtu);
+    UVGB_TRY(cudaMemcpy2DAsync(f->d_plane + (size_t)y0 * f->pitch, f->pitch, static_cast<const uint8_t *>(src) + (size_t)y0 * src_stride,
+                               src_stride, W, y1 - y0, cudaMemcpyHostToDevice, st));
+  }
+  const int key_flags = flags & ~UVG_B200_FRAME_NO_H2D;
+  Frame::PassGraph *pg = nullptr;
+  for (Frame::PassGraph &g : f->graphs)
+    if (g.used && g.ctu_begin == ctu_begin && g.ctu_end == ctu_end && g.flags == key_flags) pg = &g;
+  if (!pg)
+    for (Frame::PassGraph &g : f->graphs)
+      if (!g.used) { g.used = true; g.ctu_begin = ctu_begin; g.ctu_end = ctu_end; g.flags = key_flags; g.seen = 0; g.exec = nullptr; pg = &g; break; }
+  static const bool no_graph = getenv("UVG266_B200_FRAME_GRAPH") && !strcmp(getenv("UVG266_B200_FRAME_GRAPH"), "0");
+  if (pg && pg->exec) {
+    UVGB_TRY(cudaGraphLaunch(pg->exec, st));
+    g_launches.fetch_add(pg->launches, std::memory_order_relaxed);
+  } else if (pg && pg->seen >= 1 && !no_graph) {
+    const uint64_t l0 = g_launches.load();
+    cudaGraph_t graph = nullptr;
+    UVGB_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_pass(f, ctu_begin, ctu_end, flags);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("frame: graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return 1; }
+    pg->launches = g_launches.load() - l0;
+    const cudaError_t ie = cudaGraphInstantiate(&pg->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { pg->exec = nullptr; set_error("frame: graph instantiation failed: %s", cudaGetErrorString(ie)); return 1; }
+    UVGB_TRY(cudaGraphLaunch(pg->exec, st));
+  } else {
+    if (enqueue_pass(f, ctu_begin, ctu_end, flags)) return 1;
+    if (pg) pg->seen++;
+  }
   UVGB_TRY(cudaEventRecord(f->ev_t1, st));
-  if (d2h) UVGB_TRY(cudaEventRecord(f->ev_total, sc));
   f->in_flight = true;
   return 0;
 }
@@ -590,8 +637,8 @@ extern "C" int uvg_b200_frame_wait(uvg_b200_frame *h, uvg_b200_frame_result *out
   r.ctu_begin = f->ctu_begin; r.ctu_end = f->ctu_end;
   size_t tu_total = 0;
   for (int i = 0; i < c.n_tus; ++i) tu_total += (size_t)band_ctus * f->tu[i].per_ctu;
+  UVGB_TRY(cudaEventSynchronize(f->ev_t1));               // kernels and (joined) copies of the pass
   if (d2h) {
-    UVGB_TRY(cudaEventSynchronize(f->ev_total));
     if (c.n_tus) {
       // only now does the host know how many levels there are: one more copy of exactly that size
       const uint64_t total = f->h_off[tu_total];
