@@ -27,7 +27,7 @@ for obj in sorted(glob.glob(os.path.join(ROOT, "uvg266_b200", "build", "*.o"))):
                 rows.append((os.path.basename(obj), cur, total, counts))
             cur, counts, total = m.group(1), collections.Counter(), 0
             continue
-        if cur and re.search(r"/\*[0-9a-f]{4}\*/", line):
+        if cur and re.search(r"/\*[0-9a-f]{4,6}\*/", line):
             total += 1
             for name, pat in FAMILIES:
                 if re.search(pat, line):

@@ -86,6 +86,7 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
   constexpr int per_tu = 4 * RS + HEAD + nn;                 // all multiples of 4
   constexpr int l2 = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5;
   __shared__ int s_dc[TPC], s_mode[TPC], s_X[TPC], s_Y[TPC];
+  __shared__ unsigned char s_class[TPC], s_order[TPC];
   const int tid = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * TPC;
   if (tid < TPC) {
@@ -98,17 +99,29 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
     const int sb = kCtu / sel.src_n;
     const int lx = (X & (kCtu - 1)) / sel.src_n, ly = (Y & (kCtu - 1)) / sel.src_n;
     const size_t sblk = (size_t)(ctu - g.ctu_begin) * sel.src_per_ctu + ly * sb + lx;
-    s_mode[tid] = sel.best[sblk * sel.n_best + rank];
+    const int mode = sel.best[sblk * sel.n_best + rank];
+    s_mode[tid] = mode;
+    // code-path class of the mode: a warp's 8-pixel row items are handed out in class order (below), so that the lanes
+    // of a warp run the same branch of the predictor even though every TU has its own mode
+    const ModeParam mp = mt.m[mode];
+    s_class[tid] = (unsigned char)(mp.kind != 2 ? mp.kind : 2 + (mp.pdpc ? (mp.sample_disp == 0 ? 1 : 2) : 0) + (mp.vertical ? 0 : 3));
   }
   __syncthreads();
-  for (int i = tid; i < TPC * 2 * RS; i += 256) {            // reference rows from the plane, tail replicated
-    const int tu = i / (2 * RS), rem = i - tu * 2 * RS, row = rem / RS, x = min(rem - row * RS, 2 * n);
-    const int X = s_X[tu], Y = s_Y[tu];
-    const int sx = row ? X - 1 : X - 1 + x, sy = row ? Y - 1 + x : Y - 1;
-    smem_raw[tu * per_tu + row * RS + (rem - row * RS)] = __ldg(plane + (size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1));
+  if (tid < TPC) {                                           // stable counting sort of the CTA's TUs by class
+    const int c = s_class[tid];
+    int pos = 0;
+    for (int o = 0; o < TPC; ++o) pos += (s_class[o] < c) || (s_class[o] == c && o < tid);
+    s_order[pos] = (unsigned char)tid;
   }
-  __syncthreads();
-  if (N > 4) {                                               // no 4x4 mode uses the smoothed rows (intra.c:691-712: n*n > 32 / n != 4)
+  if (N >= 16) {
+    // large TUs: few TUs per CTA, long rows - one thread per reference sample
+    for (int i = tid; i < TPC * 2 * RS; i += 256) {
+      const int tu = i / (2 * RS), rem = i - tu * 2 * RS, row = rem / RS, x = min(rem - row * RS, 2 * n);
+      const int X = s_X[tu], Y = s_Y[tu];
+      const int sx = row ? X - 1 : X - 1 + x, sy = row ? Y - 1 + x : Y - 1;
+      smem_raw[tu * per_tu + row * RS + (rem - row * RS)] = __ldg(plane + (size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1));
+    }
+    __syncthreads();
     for (int i = tid; i < TPC * 2 * RS; i += 256) {          // intra_filter_reference, intra.c:190-225
       const int tu = i / (2 * RS), rem = i - tu * 2 * RS, row = rem / RS, x = rem - row * RS;
       const uint8_t *top = smem_raw + tu * per_tu, *left = top + RS, *src = row ? left : top;
@@ -117,6 +130,52 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
       else if (x < 2 * n) v = ((int)src[x - 1] + 2 * (int)src[x] + (int)src[x + 1] + 2) >> 2;
       else v = src[2 * n];
       smem_raw[tu * per_tu + (2 + row) * RS + x] = (uint8_t)v;
+    }
+  } else {
+    // Reference rows from the plane, tail replicated: one thread per (TU, row). The top row is contiguous in the plane:
+    // aligned word loads + funnel shifts when the TU is away from the picture borders; the left column is strided.
+    for (int i = tid; i < TPC * 2; i += 256) {
+      const int tu = i >> 1, row = i & 1;
+      const int X = s_X[tu], Y = s_Y[tu];
+      uint8_t *dst = smem_raw + tu * per_tu + row * RS;
+      if (row == 0 && Y >= 1 && X >= 4 && X + 2 * n + 4 <= g.W && Y - 1 < g.H) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(plane + (size_t)(Y - 1) * stride + (X - 4));   // X, stride: multiples of 4
+        constexpr int NW = (2 * n + 1 + 3) / 4;                                  // words that hold top[0 .. 2n]
+        uint32_t w = __ldg(src);
+  #pragma unroll
+        for (int j = 0; j < NW; ++j) {
+          const uint32_t wn = __ldg(src + j + 1);
+          uint32_t v = __funnelshift_r(w, wn, 24);                               // bytes X-1+4j .. X+2+4j
+          if (j == NW - 1) v = (v & 0xffu) * 0x01010101u;                        // 2n is a multiple of 4: the last word starts with the last sample top[2n]
+          *reinterpret_cast<uint32_t *>(dst + 4 * j) = v;
+          w = wn;
+        }
+        const uint32_t last = dst[2 * n] * 0x01010101u;
+  #pragma unroll
+        for (int j = NW; j < RS / 4; ++j) *reinterpret_cast<uint32_t *>(dst + 4 * j) = last;
+      } else {
+        for (int x = 0; x < RS; ++x) {
+          const int xx = min(x, 2 * n);
+          const int sx = row ? X - 1 : X - 1 + xx, sy = row ? Y - 1 + xx : Y - 1;
+          dst[x] = __ldg(plane + (size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1));
+        }
+      }
+    }
+    __syncthreads();
+    if (N > 4) {                                               // no 4x4 mode uses the smoothed rows (intra.c:691-712: n*n > 32 / n != 4)
+      for (int i = tid; i < TPC * 2; i += 256) {               // intra_filter_reference, intra.c:190-225: one thread per (TU, row)
+        const int tu = i >> 1, row = i & 1;
+        const uint8_t *top = smem_raw + tu * per_tu, *left = top + RS, *src = row ? left : top;
+        uint8_t *dst = smem_raw + tu * per_tu + (2 + row) * RS;
+        int a = src[0], bq = src[1];
+        dst[0] = (uint8_t)(((int)left[1] + 2 * (int)left[0] + (int)top[1] + 2) >> 2);
+        for (int x = 1; x < 2 * n; ++x) {
+          const int c = src[x + 1];
+          dst[x] = (uint8_t)((a + 2 * bq + c + 2) >> 2);
+          a = bq; bq = c;
+        }
+        for (int x = 2 * n; x < RS; ++x) dst[x] = src[2 * n];
+      }
     }
   }
   if (tid < TPC) {                                           // intra_pred_dc, intra.c:236-273
@@ -140,8 +199,9 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
   __syncthreads();
   constexpr int ns = n >= 8 ? n / 8 : 1, items_per_tu = n * ns;
   for (int e = tid; e < TPC * items_per_tu; e += 256) {
-    const int tu = e / items_per_tu, it = e - tu * items_per_tu, r = it / ns, sx = it - r * ns;
-    if (first + tu >= n_tus) break;
+    const int slot = e / items_per_tu, it = e - slot * items_per_tu, r = it / ns, sx = it - r * ns;
+    const int tu = s_order[slot];
+    if (first + tu >= n_tus) continue;
     const ModeParam mp = mt.m[s_mode[tu]];
     const uint8_t *base = smem_raw + tu * per_tu;
     const uint8_t *top = base + (mp.filtered ? 2 * RS : 0), *left = top + RS;

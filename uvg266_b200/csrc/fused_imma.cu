@@ -531,6 +531,9 @@ static const uint32_t *cached_tables8(int th, int tv)
   return d;
 }
 
+// DENSE: ref, pred and rec are dense arrays of 8x8 blocks (stride 8, 64 bytes per TU) - the layout of every batched
+// caller; block addresses are then tu * 64 and the descriptor arithmetic (and its bpr == 1 branches) disappears.
+template <bool DENSE>
 __global__ void __launch_bounds__(128)
 fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__restrict__ tab)
 {
@@ -542,7 +545,11 @@ fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__res
   const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
   const uint8_t *ref_b = static_cast<const uint8_t *>(a.ref.base), *pred_b = static_cast<const uint8_t *>(a.pred.base);
   uint8_t *rec_b = const_cast<uint8_t *>(static_cast<const uint8_t *>(a.rec.base));
-  const uint32_t ref_ln = g * a.ref.stride + 2 * t, pred_ln = g * a.pred.stride + 2 * t, rec_ln = g * a.rec.stride + 2 * t;
+  const uint32_t ref_ln = g * (DENSE ? 8u : a.ref.stride) + 2 * t, pred_ln = g * (DENSE ? 8u : a.pred.stride) + 2 * t,
+                 rec_ln = g * (DENSE ? 8u : a.rec.stride) + 2 * t;
+  auto off_ref = [&](uint32_t tu) -> uint64_t { return DENSE ? (uint64_t)tu * 64u : block_off32(a.ref, tu); };
+  auto off_pred = [&](uint32_t tu) -> uint64_t { return DENSE ? (uint64_t)tu * 64u : block_off32(a.pred, tu); };
+  auto off_rec = [&](uint32_t tu) -> uint64_t { return DENSE ? (uint64_t)tu * 64u : block_off32(a.rec, tu); };
   const bool do_recon = !a.early_skip;
 
   for (uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < n_units; unit += warps_total) {
@@ -550,10 +557,10 @@ fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__res
     const bool validB = tuA + 1 < n_tus;
     const uint32_t tuB = validB ? tuA + 1 : tuA;
     // ---- pixels (2t, 2t+1) of row g of both TUs -----------------------------------------------
-    const uint32_t rA = __ldg(reinterpret_cast<const uint16_t *>(ref_b + block_off32(a.ref, tuA) + ref_ln));
-    const uint32_t rB = __ldg(reinterpret_cast<const uint16_t *>(ref_b + block_off32(a.ref, tuB) + ref_ln));
-    const uint32_t pA = __ldg(reinterpret_cast<const uint16_t *>(pred_b + block_off32(a.pred, tuA) + pred_ln));
-    uint32_t pB = __ldg(reinterpret_cast<const uint16_t *>(pred_b + block_off32(a.pred, tuB) + pred_ln));
+    const uint32_t rA = __ldg(reinterpret_cast<const uint16_t *>(ref_b + off_ref(tuA) + ref_ln));
+    const uint32_t rB = __ldg(reinterpret_cast<const uint16_t *>(ref_b + off_ref(tuB) + ref_ln));
+    const uint32_t pA = __ldg(reinterpret_cast<const uint16_t *>(pred_b + off_pred(tuA) + pred_ln));
+    uint32_t pB = __ldg(reinterpret_cast<const uint16_t *>(pred_b + off_pred(tuB) + pred_ln));
     if (!validB) pB = rB;                                  // odd tail: the phantom TU has zero residual
     const uint32_t refw = rA | (rB << 16), predw = pA | (pB << 16);
 
@@ -627,9 +634,9 @@ fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__res
       outw = (reconA ? (w & 0xffffu) : (predw & 0xffffu)) | (reconB ? (w & 0xffff0000u) : (predw & 0xffff0000u));
     }
     if (reconA || !a.rec_is_pred)
-      *reinterpret_cast<uint16_t *>(rec_b + block_off32(a.rec, tuA) + rec_ln) = (uint16_t)outw;
+      *reinterpret_cast<uint16_t *>(rec_b + off_rec(tuA) + rec_ln) = (uint16_t)outw;
     if (validB && (reconB || !a.rec_is_pred))
-      *reinterpret_cast<uint16_t *>(rec_b + block_off32(a.rec, tuB) + rec_ln) = (uint16_t)(outw >> 16);
+      *reinterpret_cast<uint16_t *>(rec_b + off_rec(tuB) + rec_ln) = (uint16_t)(outw >> 16);
     if (a.ssd) {
       const uint32_t d4 = __vabsdiffu4(refw, outw);
       const unsigned ssdA = __reduce_add_sync(0xffffffffu, __dp4a(d4 & 0xffffu, d4, 0u));
@@ -657,7 +664,9 @@ static int launch_imma8(const FusedArgs &a, size_t n_tus, const QParams &q, int 
   size_t grid = (n_units + warps_per_block - 1) / warps_per_block;
   const size_t cap = (size_t)sm_count() * 16;
   if (grid > cap) grid = cap;
-  fused_imma8_kernel<<<(unsigned)grid, warps_per_block * 32, 0, st>>>(a, (uint32_t)n_tus, q, tab);
+  auto dense8 = [](const Blocks &b) { return b.bpr == 1 && b.stride == 8 && b.row_pitch == 64; };
+  if (dense8(a.ref) && dense8(a.pred) && dense8(a.rec)) fused_imma8_kernel<true><<<(unsigned)grid, warps_per_block * 32, 0, st>>>(a, (uint32_t)n_tus, q, tab);
+  else fused_imma8_kernel<false><<<(unsigned)grid, warps_per_block * 32, 0, st>>>(a, (uint32_t)n_tus, q, tab);
   UVGB_LAUNCH_CHECK();
   return 0;
 }
