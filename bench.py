@@ -647,8 +647,8 @@ def pair_bench(torch, U, L, dev, stream, hbm_peak):
 
 def e2e_frame(torch, U, L, rank, world, args, barrier, dist, dev):
     """End to end through the frame-pipeline C ABI: every step hands the library a source picture in pinned HOST
-    memory (uvg_b200_frame_submit: H2D of the plane, all kernels, D2H of costs / candidate lists / per-TU results /
-    compact coefficients) and waits for the results in host memory (uvg_b200_frame_wait). `inflight` frame objects
+    memory (uvg_b200_frame_submit: H2D of the plane, all kernels, D2H of the candidate lists with their costs - what
+    search_intra_rough returns - / per-TU results / compact coefficients) and waits for the results in host memory (uvg_b200_frame_wait). `inflight` frame objects
     alternate, like an encoder with --owf frames in flight, so one picture's D2H overlaps the next one's kernels.
     Weak scaling: every rank processes its own pictures."""
     H = CTU_ROWS * CTU
@@ -668,21 +668,28 @@ def e2e_frame(torch, U, L, rank, world, args, barrier, dist, dev):
     k = max(3, min(args.steps, args.e2e_steps))
     d2h = [0]
 
-    def run(steps):
-        pending = []
-        for s_ in range(steps):
-            i = s_ % inflight
-            if len(pending) == inflight:
-                U.check(L.uvg_b200_frame_wait(pending.pop(0), C.byref(res)))
+    import concurrent.futures
+    pool = concurrent.futures.ThreadPoolExecutor(inflight)
+
+    def worker(i, steps):
+        # one host thread per picture in flight, like the encoder's frame-level parallelism (--owf): a thread that sits in
+        # uvg_b200_frame_wait (the last, size-dependent copy of its picture) does not keep the other pictures from being
+        # submitted, so one picture's copies run under the other's kernels
+        r = U.FrameResult()
+        for _ in range(steps):
             U.check(L.uvg_b200_frame_submit(frames[i], planes[i].data_ptr(), FRAME_W, 0, 0, 0))
-            pending.append(frames[i])
-        while pending:
-            U.check(L.uvg_b200_frame_wait(pending.pop(0), C.byref(res)))
-    run(inflight + 1)
+            U.check(L.uvg_b200_frame_wait(frames[i], C.byref(r)))
+        return int(r.n_levels)
+
+    def run(steps):
+        """`steps` pictures in total, spread over the frame objects"""
+        per = [steps // inflight + (1 if i < steps % inflight else 0) for i in range(inflight)]
+        return list(pool.map(worker, range(inflight), per))
+    nnz_list = run(3 * inflight)
     # bytes that cross the link per picture: counted from what the result describes
-    fixed = sum(n_ctu * (CTU // n) ** 2 * (len(m) * 4 + FRAME_NBEST) for (n, m) in FRAME_LEVELS) + \
+    fixed = sum(n_ctu * (CTU // n) ** 2 * FRAME_NBEST * (1 + 4) for (n, m) in FRAME_LEVELS) + \
         sum(n_ctu * c * (1 + 1 + 4 + 4 + 4) + (n_ctu * c * n * n + 31) // 32 * 4 for (n, c) in TUS) + 4
-    nnz = int(res.n_levels)
+    nnz = max(nnz_list)
     d2h_bytes = fixed + nnz * 2
     launches0 = L.uvg_b200_launch_count()
     barrier()

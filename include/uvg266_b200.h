@@ -349,8 +349,9 @@ typedef struct uvg_b200_frame_cfg {
  * UVG_B200_FRAME_DENSE_COEFF. */
 typedef struct uvg_b200_frame_result {
   int32_t ctu_begin, ctu_end;
-  const uint32_t *rough_cost[UVG_B200_FRAME_MAX_LEVELS];   /* [blocks][k]                                */
-  const uint8_t *rough_best[UVG_B200_FRAME_MAX_LEVELS];    /* [blocks][n_best] mode values               */
+  const uint32_t *rough_cost[UVG_B200_FRAME_MAX_LEVELS];   /* [blocks][k]; only with UVG_B200_FRAME_ALL_COSTS */
+  const uint8_t *rough_best[UVG_B200_FRAME_MAX_LEVELS];    /* [blocks][n_best] mode values, best first   */
+  const uint32_t *rough_best_cost[UVG_B200_FRAME_MAX_LEVELS]; /* [blocks][n_best] their costs (what search_intra_rough returns: modes_out[i].cost) */
   const uint8_t *tu_mode[UVG_B200_FRAME_MAX_LEVELS];       /* [tus] the mode each TU was predicted with  */
   const uint8_t *tu_has_coeffs[UVG_B200_FRAME_MAX_LEVELS];
   const uint32_t *tu_ssd[UVG_B200_FRAME_MAX_LEVELS];
@@ -376,7 +377,9 @@ typedef struct uvg_b200_frame_device {
 enum {
   UVG_B200_FRAME_NO_H2D = 1,        /* the source rows are already on the device (previous submit)     */
   UVG_B200_FRAME_NO_D2H = 2,        /* leave the results on the device                                 */
-  UVG_B200_FRAME_DENSE_COEFF = 4    /* additionally return the dense coefficient arrays                */
+  UVG_B200_FRAME_DENSE_COEFF = 4,   /* additionally return the dense coefficient arrays                */
+  UVG_B200_FRAME_ALL_COSTS = 8      /* additionally return the cost of every (block, mode), not only   */
+                                    /* the n_best candidates' (the device-side copies always exist)    */
 };
 
 typedef struct uvg_b200_frame uvg_b200_frame;

@@ -36,7 +36,7 @@ def synth(w, h, seed):
     return np.clip(base + rng.normal(0, 6, base.shape), 0, 255).astype(np.uint8)
 
 
-def run_gpu(plane, levels, tus, n_best, qp, rows=None, flags=U.FRAME_DENSE_COEFF):
+def run_gpu(plane, levels, tus, n_best, qp, rows=None, flags=U.FRAME_DENSE_COEFF | U.FRAME_ALL_COSTS):
     L = U.lib()
     h, w = plane.shape
     cfg = U.FrameCfg.make(w, h, levels, tus, n_best, U.QuantCfg.make(qp, 8, 1, 0, 0), WEIGHTS)
@@ -53,6 +53,7 @@ def run_gpu(plane, levels, tus, n_best, qp, rows=None, flags=U.FRAME_DENSE_COEFF
             nb = n_ctu * (64 // n) ** 2
             out["cost%d" % i] = U.np_view(res.rough_cost[i], np.uint32, nb * len(modes)).copy()
             out["best%d" % i] = U.np_view(res.rough_best[i], np.uint8, nb * n_best).copy()
+            out["bestcost%d" % i] = U.np_view(res.rough_best_cost[i], np.uint32, nb * n_best).copy()
         levels_arr = U.np_view(res.levels, np.int16, int(res.n_levels)).copy()
         out["levels"] = levels_arr
         for i, (n, cnt) in enumerate(tus):
@@ -132,6 +133,11 @@ def compare(g, r, levels, tus):
     for i in range(len(levels)):
         assert (g["cost%d" % i] == r["cost%d" % i]).all(), "rough costs, level %d" % i
         assert (g["best%d" % i] == r["best%d" % i]).all(), "candidate lists, level %d" % i
+        # the costs that travel with the candidate lists = the full table at the listed modes
+        k = len(levels[i][1])
+        modes = np.array(levels[i][1]); full = r["cost%d" % i].reshape(-1, k); bm = r["best%d" % i].reshape(full.shape[0], -1)
+        idx = np.array([[int(np.where(modes == m)[0][0]) for m in row] for row in bm])
+        assert (g["bestcost%d" % i].reshape(bm.shape) == np.take_along_axis(full, idx, axis=1)).all(), "candidate costs, level %d" % i
     for i, (n, cnt) in enumerate(tus):
         for key in ("mode", "has", "ssd", "tcost", "coeff", "rec"):
             a, b = g["%s%d" % (key, i)], r["%s%d" % (key, i)]

@@ -60,7 +60,7 @@ class QuantCfg(C.Structure):
 
 
 FRAME_MAX_LEVELS = 4
-FRAME_NO_H2D, FRAME_NO_D2H, FRAME_DENSE_COEFF = 1, 2, 4
+FRAME_NO_H2D, FRAME_NO_D2H, FRAME_DENSE_COEFF, FRAME_ALL_COSTS = 1, 2, 4, 8
 
 
 class FrameLevel(C.Structure):
@@ -100,7 +100,7 @@ class FrameResult(C.Structure):
     """uvg_b200_frame_result: host pointers owned by the frame object"""
     _A = C.c_void_p * FRAME_MAX_LEVELS
     _fields_ = [("ctu_begin", C.c_int32), ("ctu_end", C.c_int32), ("rough_cost", _A), ("rough_best", _A),
-                ("tu_mode", _A), ("tu_has_coeffs", _A), ("tu_ssd", _A), ("tu_cost", _A), ("tu_sig", _A),
+                ("rough_best_cost", _A), ("tu_mode", _A), ("tu_has_coeffs", _A), ("tu_ssd", _A), ("tu_cost", _A), ("tu_sig", _A),
                 ("tu_level_off", _A), ("tu_coeff_dense", _A), ("levels", C.c_void_p), ("n_levels", C.c_uint64),
                 ("device_ms", C.c_float)]
 

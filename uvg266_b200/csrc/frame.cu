@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "intra.cuh"
 #include <cub/device/device_scan.cuh>
+#include <mutex>
 #include <new>
 #include <string.h>
 
@@ -29,6 +30,7 @@ namespace {
 
 constexpr int kCtu = 64;
 constexpr int kMaxLv = UVG_B200_FRAME_MAX_LEVELS;
+constexpr int kMaxStages = kMaxLv + 2;            // rough search | one per TU size | compaction
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
@@ -49,7 +51,7 @@ struct Geo {
 // of the cost list, like the insertion into the sorted mode list of search_intra.c:1064).
 __global__ void __launch_bounds__(256)
 frame_topk_kernel(const uint32_t *__restrict__ cost, size_t n_blocks, int k, int n_best,
-                  const int8_t *__restrict__ mode_values, uint8_t *__restrict__ best)
+                  const int8_t *__restrict__ mode_values, uint8_t *__restrict__ best, uint32_t *__restrict__ best_cost)
 {
   const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_blocks) return;
@@ -63,7 +65,11 @@ frame_topk_kernel(const uint32_t *__restrict__ cost, size_t n_blocks, int k, int
       if (s < n_best && c < bc[s]) { const uint32_t tc = bc[s]; const int ti = bi[s]; bc[s] = c; bi[s] = idx; c = tc; idx = ti; }
     }
   }
-  for (int s = 0; s < n_best; ++s) best[b * n_best + s] = (uint8_t)mode_values[bi[s < k ? s : k - 1]];
+  for (int s = 0; s < n_best; ++s) {
+    const int src = s < k ? s : k - 1;
+    best[b * n_best + s] = (uint8_t)mode_values[bi[src]];
+    best_cost[b * n_best + s] = bc[src];
+  }
 }
 
 // Residual-pass operands of one TU size: the original block and the intra prediction with the TU's mode, both
@@ -343,6 +349,20 @@ coeff_pack_kernel(const int16_t *__restrict__ coeff, size_t n_coeffs, const uint
   }
 }
 
+// The packed levels are the one result whose size the host only learns after the pass. The default is a second,
+// host-issued copy of exactly that size (uvg_b200_frame_wait); with UVG266_B200_FRAME_PUSH=1 a few CTAs store them
+// straight into the (UVA-mapped) pinned result buffer over PCIe instead, as 16-byte posted writes, 512 contiguous bytes
+// per warp instruction, the total read on the device: no host round trip, shorter latency for one picture at a time.
+__global__ void __launch_bounds__(256)
+levels_push_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ host_dst, const uint32_t *__restrict__ total_levels)
+{
+  const size_t n16 = ((size_t)*total_levels * sizeof(int16_t) + 15) / 16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldcs(src + i);
+    __stwt(host_dst + i, v);
+  }
+}
+
 struct Level {
   int n = 0, k = 0, ppc = 0;
   int8_t modes[68];
@@ -350,8 +370,8 @@ struct Level {
   size_t nb = 0;                                  // blocks of the whole picture
   uint8_t *d_orig = nullptr, *d_refs = nullptr, *d_best = nullptr;
   int8_t *d_modes = nullptr;
-  uint32_t *d_cost = nullptr;
-  uint32_t *h_cost = nullptr; uint8_t *h_best = nullptr;
+  uint32_t *d_cost = nullptr, *d_best_cost = nullptr;
+  uint32_t *h_cost = nullptr, *h_best_cost = nullptr; uint8_t *h_best = nullptr;
 };
 
 struct TuSize {
@@ -371,8 +391,8 @@ struct TuSize {
 struct Frame {
   uvg_b200_frame_cfg cfg;
   int W = 0, H = 0, pitch = 0, ctu_cols = 0, ctu_rows = 0, n_ctu = 0;
-  cudaStream_t s_main = nullptr, s_copy = nullptr;
-  cudaEvent_t ev_level[kMaxLv] = {}, ev_tu[kMaxLv] = {}, ev_pack = nullptr, ev_total = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaStream_t s_in = nullptr, s_copy = nullptr;         // source rows in, results out; the kernels go into the lane
+  cudaEvent_t ev_stage[kMaxStages] = {}, ev_in = nullptr, ev_done = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   uint8_t *d_plane = nullptr;
   Level lv[kMaxLv];
   TuSize tu[kMaxLv];
@@ -383,13 +403,19 @@ struct Frame {
   uvg_b200_frame_result res;
   int ctu_begin = 0, ctu_end = 0, flags = 0;
   bool in_flight = false;
-  struct PassGraph { bool used = false; int ctu_begin = 0, ctu_end = 0, flags = 0, seen = 0; uint64_t launches = 0; cudaGraphExec_t exec = nullptr; };
+  struct PassGraph {
+    bool used = false, ready = false;
+    int ctu_begin = 0, ctu_end = 0, flags = 0, seen = 0;
+    cudaGraphExec_t kernels[kMaxStages] = {}, copies[kMaxStages] = {};
+    uint64_t launches[kMaxStages] = {}, copy_launches[kMaxStages] = {};
+  };
   PassGraph graphs[4];
 };
 
 static void frame_release(Frame *f)
 {
-  if (f->s_main) cudaStreamSynchronize(f->s_main);
+  if (f->s_in) cudaStreamSynchronize(f->s_in);
+  if (f->ev_t1) cudaEventSynchronize(f->ev_t1);
   if (f->s_copy) cudaStreamSynchronize(f->s_copy);
   auto D = [](void *p) { if (p) cudaFree(p); };
   auto Hh = [](void *p) { if (p) cudaFreeHost(p); };
@@ -397,16 +423,16 @@ static void frame_release(Frame *f)
   Hh(f->h_off); Hh(f->h_levels);
   for (int i = 0; i < kMaxLv; ++i) {
     Level &l = f->lv[i];
-    D(l.d_orig); D(l.d_refs); D(l.d_best); D(l.d_cost); D(l.d_modes); Hh(l.h_cost); Hh(l.h_best);
+    D(l.d_orig); D(l.d_refs); D(l.d_best); D(l.d_cost); D(l.d_best_cost); D(l.d_modes); Hh(l.h_cost); Hh(l.h_best); Hh(l.h_best_cost);
     TuSize &t = f->tu[i];
     D(t.d_ref); D(t.d_pred); D(t.d_rec); D(t.d_mode); D(t.d_has); D(t.d_coeff); D(t.d_ssd); D(t.d_cost); D(t.d_sig);
     Hh(t.h_mode); Hh(t.h_has); Hh(t.h_ssd); Hh(t.h_cost); Hh(t.h_sig); Hh(t.h_coeff);
-    if (f->ev_level[i]) cudaEventDestroy(f->ev_level[i]);
-    if (f->ev_tu[i]) cudaEventDestroy(f->ev_tu[i]);
   }
-  for (Frame::PassGraph &g : f->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-  for (cudaEvent_t e : { f->ev_pack, f->ev_total, f->ev_t0, f->ev_t1 }) if (e) cudaEventDestroy(e);
-  if (f->s_main) cudaStreamDestroy(f->s_main);
+  for (Frame::PassGraph &g : f->graphs)
+    for (int s = 0; s < kMaxStages; ++s) { if (g.kernels[s]) cudaGraphExecDestroy(g.kernels[s]); if (g.copies[s]) cudaGraphExecDestroy(g.copies[s]); }
+  for (cudaEvent_t e : f->ev_stage) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : { f->ev_in, f->ev_done, f->ev_t0, f->ev_t1 }) if (e) cudaEventDestroy(e);
+  if (f->s_in) cudaStreamDestroy(f->s_in);
   if (f->s_copy) cudaStreamDestroy(f->s_copy);
   cudaGetLastError();
 }
@@ -420,14 +446,11 @@ static int frame_build(Frame *f, const uvg_b200_frame_cfg *c)
   f->W = c->width; f->H = c->height;
   f->ctu_cols = (c->width + kCtu - 1) / kCtu; f->ctu_rows = (c->height + kCtu - 1) / kCtu;
   f->n_ctu = f->ctu_cols * f->ctu_rows;
-  UVGB_TRY(cudaStreamCreateWithFlags(&f->s_main, cudaStreamNonBlocking));
+  UVGB_TRY(cudaStreamCreateWithFlags(&f->s_in, cudaStreamNonBlocking));
   UVGB_TRY(cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking));
-  for (int i = 0; i < kMaxLv; ++i) {
-    UVGB_TRY(cudaEventCreateWithFlags(&f->ev_level[i], cudaEventDisableTiming));
-    UVGB_TRY(cudaEventCreateWithFlags(&f->ev_tu[i], cudaEventDisableTiming));
-  }
-  UVGB_TRY(cudaEventCreateWithFlags(&f->ev_pack, cudaEventDisableTiming));
-  UVGB_TRY(cudaEventCreateWithFlags(&f->ev_total, cudaEventDisableTiming));
+  for (cudaEvent_t &e : f->ev_stage) UVGB_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  UVGB_TRY(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
+  UVGB_TRY(cudaEventCreateWithFlags(&f->ev_done, cudaEventDisableTiming));
   UVGB_TRY(cudaEventCreate(&f->ev_t0));
   UVGB_TRY(cudaEventCreate(&f->ev_t1));
   f->pitch = (f->W + 15) & ~15;                                  // rows start 16-byte aligned: word loads of block rows
@@ -440,8 +463,8 @@ static int frame_build(Frame *f, const uvg_b200_frame_cfg *c)
     for (int m = 0; m < l.k; ++m) l.mt.m[m] = make_mode(l.n, l.modes[m]);
     l.nb = (size_t)f->n_ctu * l.ppc;
     if (dalloc(l.d_cost, l.nb * l.k) ||
-        dalloc(l.d_best, l.nb * c->n_best) || dalloc(l.d_modes, (size_t)68) || halloc(l.h_cost, l.nb * l.k) ||
-        halloc(l.h_best, l.nb * c->n_best)) return 1;
+        dalloc(l.d_best, l.nb * c->n_best) || dalloc(l.d_best_cost, l.nb * c->n_best) || dalloc(l.d_modes, (size_t)68) ||
+        halloc(l.h_cost, l.nb * l.k) || halloc(l.h_best, l.nb * c->n_best) || halloc(l.h_best_cost, l.nb * c->n_best)) return 1;
     UVGB_TRY(cudaMemcpy(l.d_modes, l.modes, 68, cudaMemcpyHostToDevice));
   }
   for (int i = 0; i < c->n_tus; ++i) {
@@ -463,8 +486,8 @@ static int frame_build(Frame *f, const uvg_b200_frame_cfg *c)
     f->total_tus += t.nt; f->total_coeffs += px;
   }
   if (dalloc(f->d_cnt, f->total_tus + 1) || dalloc(f->d_off, f->total_tus + 1) || halloc(f->h_off, f->total_tus + 1) ||
-      dalloc(f->d_levels, f->total_coeffs) || halloc(f->h_levels, f->total_coeffs)) return 1;
-  UVGB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, f->scan_tmp_bytes, f->d_cnt, f->d_off, (int)(f->total_tus + 1), f->s_main));
+      dalloc(f->d_levels, f->total_coeffs + 8) || halloc(f->h_levels, f->total_coeffs + 8)) return 1;
+  UVGB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, f->scan_tmp_bytes, f->d_cnt, f->d_off, (int)(f->total_tus + 1), f->s_in));
   UVGB_TRY(cudaMalloc(&f->d_scan_tmp, f->scan_tmp_bytes + 64));
   return 0;
 }
@@ -539,39 +562,65 @@ extern "C" void uvg_b200_frame_destroy(uvg_b200_frame *h)
   delete h;
 }
 
-// Everything of a pass between the H2D copy of the source rows and the last copy whose size is only known afterwards:
-// kernels on s_main, D2H copies on s_copy behind events, s_copy joined back into s_main at the end. Issued directly the
-// first time a (band, flags) configuration is seen (that run also performs every lazy one-time initialisation of the
-// kernels it calls), captured into a CUDA graph the second time and replayed from then on: ~20 launches and ~15 copies
-// become one cudaGraphLaunch (no launch gaps on the device, microseconds of host time per picture).
-static int enqueue_pass(Frame *f, int ctu_begin, int ctu_end, int flags)
+// ---- how a pass is scheduled -----------------------------------------------------------------------------------------
+// Every frame object's KERNELS go into one process-wide compute stream, in submission order (the lane). Two pictures'
+// kernels never share the SMs: with a stream per picture the older picture's chain of short dependent kernels queues
+// behind the younger one's long rough-search waves, both finish together, and the copies at either end of a pass (source
+// rows in, results out: ~0.45 ms per 4K picture) find no kernels to hide under. In the lane picture B's kernels start
+// the moment A's end, B's source rows arrive (s_in) while A computes, and A's results leave (s_copy) while B computes.
+// A pass is cut into stages - rough search | one per TU size | compaction - and after each stage an event releases that
+// stage's D2H copies on the picture's own s_copy. Kernels and copies of a stage are each captured into a CUDA graph the
+// second time a (band, flags) configuration is seen (the first run performs the lazy one-time initialisation of the
+// kernels it calls) and replayed from then on.
+struct ComputeLane { cudaStream_t st = nullptr; std::mutex mu; };
+static ComputeLane *lane()
+{
+  static ComputeLane l;
+  static std::once_flag once;
+  std::call_once(once, [] { if (cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking) != cudaSuccess) l.st = nullptr; });
+  return l.st ? &l : nullptr;
+}
+
+constexpr int kPushCtas = 64;
+static bool levels_pushed()
+{
+  // opt-in: measured on the B200 with two pictures in flight the push kernel's CTAs, resident beside the next picture's
+  // kernels for the ~0.3 ms the PCIe writes take, slow those by ~20 % (1.15 ms per 4K picture against 0.98 with the
+  // host-issued copy, which costs the picture one round trip of latency but leaves the SMs alone)
+  static const bool on = getenv("UVG266_B200_FRAME_PUSH") && !strcmp(getenv("UVG266_B200_FRAME_PUSH"), "1");
+  return on;
+}
+
+static int n_stages(const Frame *f) { return 1 + f->cfg.n_tus + (f->cfg.n_tus ? 1 : 0); }
+
+static size_t tus_before(const Frame *f, int band_ctus, int i)
+{
+  size_t b = 0;
+  for (int j = 0; j < i; ++j) b += (size_t)band_ctus * f->tu[j].per_ctu;
+  return b;
+}
+
+// kernels of stage s, into `st`
+static int stage_kernels(Frame *f, int s, int ctu_begin, int ctu_end, cudaStream_t st)
 {
   const uvg_b200_frame_cfg &c = f->cfg;
   const int W = f->W, H = f->H, band_ctus = ctu_end - ctu_begin;
-  cudaStream_t st = f->s_main, sc = f->s_copy;
-  const bool d2h = !(flags & UVG_B200_FRAME_NO_D2H);
-  Geo g{ W, H, f->ctu_cols, ctu_begin };
-  const size_t cap = (size_t)sm_count() * 16;
-  // ---- rough search --------------------------------------------------------------------------------------------
-  for (int i = 0; i < c.n_levels; ++i) {
-    Level &l = f->lv[i];
-    const size_t nb = (size_t)band_ctus * l.ppc;
-    const PlaneSrc ps{ f->d_plane, f->pitch, W, H, f->ctu_cols, ctu_begin };
-    if (launch_intra_rough_plane(l.n, ps, l.modes, l.k, l.d_cost, nb, st)) return 1;
-    frame_topk_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(l.d_cost, nb, l.k, c.n_best, l.d_modes, l.d_best);
-    UVGB_LAUNCH_CHECK();
-    if (d2h) {
-      UVGB_TRY(cudaEventRecord(f->ev_level[i], st));
-      UVGB_TRY(cudaStreamWaitEvent(sc, f->ev_level[i], 0));
-      UVGB_TRY(cudaMemcpyAsync(l.h_cost, l.d_cost, nb * l.k * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
-      UVGB_TRY(cudaMemcpyAsync(l.h_best, l.d_best, nb * c.n_best, cudaMemcpyDeviceToHost, sc));
+  if (s == 0) {                                            // ---- rough search, every level
+    for (int i = 0; i < c.n_levels; ++i) {
+      Level &l = f->lv[i];
+      const size_t nb = (size_t)band_ctus * l.ppc;
+      const PlaneSrc ps{ f->d_plane, f->pitch, W, H, f->ctu_cols, ctu_begin };
+      if (launch_intra_rough_plane(l.n, ps, l.modes, l.k, l.d_cost, nb, st)) return 1;
+      frame_topk_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(l.d_cost, nb, l.k, c.n_best, l.d_modes, l.d_best, l.d_best_cost);
+      UVGB_LAUNCH_CHECK();
     }
+    return 0;
   }
-  // ---- residual pass -----------------------------------------------------------------------------------------------
-  size_t tu_base = 0;
-  for (int i = 0; i < c.n_tus; ++i) {
+  if (s <= c.n_tus) {                                      // ---- residual pass of one TU size
+    const int i = s - 1;
     TuSize &t = f->tu[i];
     const Level &sl = f->lv[t.src];
+    const Geo g{ W, H, f->ctu_cols, ctu_begin };
     const size_t nt = (size_t)band_ctus * t.per_ctu;
     // TUs per CTA chosen so that the 8-pixel row items of a CTA's TUs fill its 256 threads
     const int nn = t.n * t.n, tpc = t.n == 4 ? 64 : t.n == 8 ? 32 : t.n == 16 ? 8 : 2;
@@ -588,45 +637,82 @@ static int enqueue_pass(Frame *f, int ctu_begin, int ctu_end, int flags)
     for (uvg_b200_blocks *b : { &R, &P, &O }) { b->stride = (uint32_t)t.n; b->blocks_per_row = 1; b->col_pitch = 0; b->row_pitch = (uint64_t)nn; }
     if (uvg_b200_quantize_residual_dev(&c.quant, 1 /* CU_INTRA */, 0, t.n, t.n, 0, 0, 0, &R, &P, &O, t.d_coeff, t.d_has, t.d_ssd,
                                        t.d_cost, c.cost_weights, nt, st)) return 1;
-    if (count_pack(false, t.n, t.d_coeff, nt * (size_t)nn, t.d_sig, f->d_cnt + tu_base, nullptr, nullptr, st)) return 1;
-    if (d2h) {
-      UVGB_TRY(cudaEventRecord(f->ev_tu[i], st));
-      UVGB_TRY(cudaStreamWaitEvent(sc, f->ev_tu[i], 0));
-      UVGB_TRY(cudaMemcpyAsync(t.h_mode, t.d_mode, nt, cudaMemcpyDeviceToHost, sc));
-      UVGB_TRY(cudaMemcpyAsync(t.h_has, t.d_has, nt, cudaMemcpyDeviceToHost, sc));
-      UVGB_TRY(cudaMemcpyAsync(t.h_ssd, t.d_ssd, nt * 4, cudaMemcpyDeviceToHost, sc));
-      UVGB_TRY(cudaMemcpyAsync(t.h_cost, t.d_cost, nt * 4, cudaMemcpyDeviceToHost, sc));
-      UVGB_TRY(cudaMemcpyAsync(t.h_sig, t.d_sig, (nt * (size_t)nn + 31) / 32 * 4, cudaMemcpyDeviceToHost, sc));
-      if (flags & UVG_B200_FRAME_DENSE_COEFF) {
-        if (!t.h_coeff && halloc(t.h_coeff, t.nt * (size_t)nn)) return 1;
-        UVGB_TRY(cudaMemcpyAsync(t.h_coeff, t.d_coeff, nt * (size_t)nn * 2, cudaMemcpyDeviceToHost, sc));
-      }
-    }
-    tu_base += nt;
+    return count_pack(false, t.n, t.d_coeff, nt * (size_t)nn, t.d_sig, f->d_cnt + tus_before(f, band_ctus, i), nullptr, nullptr, st);
   }
-  // ---- compact coefficients: offsets = exclusive scan of the counts, then the packed levels -----------------------------
-  if (c.n_tus) {
-    UVGB_TRY(cudaMemsetAsync(f->d_cnt + tu_base, 0, sizeof(uint32_t), st));
-    size_t tmp = f->scan_tmp_bytes;
-    UVGB_TRY(cub::DeviceScan::ExclusiveSum(f->d_scan_tmp, tmp, f->d_cnt, f->d_off, (int)(tu_base + 1), st));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    size_t b2 = 0;
-    for (int i = 0; i < c.n_tus; ++i) {
-      TuSize &t = f->tu[i];
-      const size_t nt = (size_t)band_ctus * t.per_ctu;
-      if (count_pack(true, t.n, t.d_coeff, nt * (size_t)(t.n * t.n), nullptr, nullptr, f->d_off + b2, f->d_levels, st)) return 1;
-      b2 += nt;
-    }
-    if (d2h) {
-      UVGB_TRY(cudaEventRecord(f->ev_pack, st));
-      UVGB_TRY(cudaStreamWaitEvent(sc, f->ev_pack, 0));
-      UVGB_TRY(cudaMemcpyAsync(f->h_off, f->d_off, (tu_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
-    }
+  // ---- compact coefficients: offsets = exclusive scan of the counts, then the packed levels
+  const size_t tu_total = tus_before(f, band_ctus, c.n_tus);
+  UVGB_TRY(cudaMemsetAsync(f->d_cnt + tu_total, 0, sizeof(uint32_t), st));
+  size_t tmp = f->scan_tmp_bytes;
+  UVGB_TRY(cub::DeviceScan::ExclusiveSum(f->d_scan_tmp, tmp, f->d_cnt, f->d_off, (int)(tu_total + 1), st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  for (int i = 0; i < c.n_tus; ++i) {
+    TuSize &t = f->tu[i];
+    const size_t nt = (size_t)band_ctus * t.per_ctu;
+    if (count_pack(true, t.n, t.d_coeff, nt * (size_t)(t.n * t.n), nullptr, nullptr, f->d_off + tus_before(f, band_ctus, i), f->d_levels, st)) return 1;
   }
-  if (d2h) {                                             // join: s_main's completion covers the copies
-    UVGB_TRY(cudaEventRecord(f->ev_total, sc));
-    UVGB_TRY(cudaStreamWaitEvent(st, f->ev_total, 0));
+  return 0;
+}
+
+// D2H copies that stage s releases, into `sc`; *any tells whether there were any
+static int stage_copies(Frame *f, int s, int ctu_begin, int ctu_end, int flags, cudaStream_t sc, bool *any)
+{
+  const uvg_b200_frame_cfg &c = f->cfg;
+  const int band_ctus = ctu_end - ctu_begin;
+  *any = false;
+  if (flags & UVG_B200_FRAME_NO_D2H) return 0;
+  *any = true;
+  if (s == 0) {
+    for (int i = 0; i < c.n_levels; ++i) {
+      Level &l = f->lv[i];
+      const size_t nb = (size_t)band_ctus * l.ppc;
+      // what search_intra_rough hands back is the list of best candidates with their costs (search_intra.c:1215-1223);
+      // the cost of every (block, mode) only crosses PCIe on request
+      if (flags & UVG_B200_FRAME_ALL_COSTS) UVGB_TRY(cudaMemcpyAsync(l.h_cost, l.d_cost, nb * l.k * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+      UVGB_TRY(cudaMemcpyAsync(l.h_best, l.d_best, nb * c.n_best, cudaMemcpyDeviceToHost, sc));
+      UVGB_TRY(cudaMemcpyAsync(l.h_best_cost, l.d_best_cost, nb * c.n_best * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+    }
+    return 0;
   }
+  if (s <= c.n_tus) {
+    TuSize &t = f->tu[s - 1];
+    const size_t nt = (size_t)band_ctus * t.per_ctu, nn = (size_t)t.n * t.n;
+    UVGB_TRY(cudaMemcpyAsync(t.h_mode, t.d_mode, nt, cudaMemcpyDeviceToHost, sc));
+    UVGB_TRY(cudaMemcpyAsync(t.h_has, t.d_has, nt, cudaMemcpyDeviceToHost, sc));
+    UVGB_TRY(cudaMemcpyAsync(t.h_ssd, t.d_ssd, nt * 4, cudaMemcpyDeviceToHost, sc));
+    UVGB_TRY(cudaMemcpyAsync(t.h_cost, t.d_cost, nt * 4, cudaMemcpyDeviceToHost, sc));
+    UVGB_TRY(cudaMemcpyAsync(t.h_sig, t.d_sig, (nt * nn + 31) / 32 * 4, cudaMemcpyDeviceToHost, sc));
+    if (flags & UVG_B200_FRAME_DENSE_COEFF) UVGB_TRY(cudaMemcpyAsync(t.h_coeff, t.d_coeff, nt * nn * 2, cudaMemcpyDeviceToHost, sc));
+    return 0;
+  }
+  const size_t tu_total = tus_before(f, band_ctus, c.n_tus);
+  UVGB_TRY(cudaMemcpyAsync(f->h_off, f->d_off, (tu_total + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+  if (levels_pushed()) {
+    levels_push_kernel<<<kPushCtas, 256, 0, sc>>>(reinterpret_cast<const uint4 *>(f->d_levels), reinterpret_cast<uint4 *>(f->h_levels),
+                                                  f->d_off + tu_total);
+    UVGB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// run `body` into `st`: directly, or (capture = true) captured into *exec and launched
+template <typename Body>
+static int run_or_capture(cudaStream_t st, bool capture, cudaGraphExec_t *exec, Body body)
+{
+  if (!capture) return body();
+  cudaGraph_t graph = nullptr;
+  UVGB_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = body();
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    if (!rc) set_error("frame: graph capture failed: %s", cudaGetErrorString(ce));
+    cudaGetLastError();
+    return 1;
+  }
+  const cudaError_t ie = cudaGraphInstantiate(exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { *exec = nullptr; set_error("frame: graph instantiation failed: %s", cudaGetErrorString(ie)); return 1; }
+  UVGB_TRY(cudaGraphLaunch(*exec, st));
   return 0;
 }
 
@@ -634,51 +720,72 @@ extern "C" int uvg_b200_frame_submit(uvg_b200_frame *h, const void *src, size_t 
                                      int ctu_row_end, int flags)
 {
   if (!h) { set_error("frame: NULL handle"); return 1; }
+  if (ensure_init()) return 1;                           // also selects the library's device for a new calling thread
   Frame *f = &h->f;
+  ComputeLane *ln = lane();
+  if (!ln) { set_error("frame: no compute stream"); return 1; }
   if (f->in_flight) { set_error("frame: submit while a pass is in flight (call uvg_b200_frame_wait first)"); return 1; }
   if (ctu_row_end <= 0 || ctu_row_end > f->ctu_rows) ctu_row_end = f->ctu_rows;
   if (ctu_row_begin < 0 || ctu_row_begin >= ctu_row_end) { set_error("frame: CTU row range [%d,%d) is empty", ctu_row_begin, ctu_row_end); return 1; }
   const int W = f->W, H = f->H;
   const int ctu_begin = ctu_row_begin * f->ctu_cols, ctu_end = ctu_row_end * f->ctu_cols;
   f->ctu_begin = ctu_begin; f->ctu_end = ctu_end; f->flags = flags;
-  cudaStream_t st = f->s_main;
-  UVGB_TRY(cudaEventRecord(f->ev_t0, st));
+  if ((flags & UVG_B200_FRAME_DENSE_COEFF) && !(flags & UVG_B200_FRAME_NO_D2H))
+    for (int i = 0; i < f->cfg.n_tus; ++i) {
+      TuSize &t = f->tu[i];
+      if (!t.h_coeff && halloc(t.h_coeff, t.nt * (size_t)t.n * t.n)) return 1;
+    }
   if (!(flags & UVG_B200_FRAME_NO_H2D)) {
     if (!src) { set_error("frame: NULL source plane"); return 1; }
     // rows the band reads: one above, and below it what the left reference column of a 32x32 block at the band's
     // last rows reaches (Y - 1 + 2n)
     const int y0 = max(0, ctu_row_begin * kCtu - 1), y1 = min(H, ctu_row_end * kCtu + kCtu);
     UVGB_TRY(cudaMemcpy2DAsync(f->d_plane + (size_t)y0 * f->pitch, f->pitch, static_cast<const uint8_t *>(src) + (size_t)y0 * src_stride,
-                               src_stride, W, y1 - y0, cudaMemcpyHostToDevice, st));
+                               src_stride, W, y1 - y0, cudaMemcpyHostToDevice, f->s_in));
   }
+  UVGB_TRY(cudaEventRecord(f->ev_in, f->s_in));
   const int key_flags = flags & ~UVG_B200_FRAME_NO_H2D;
   Frame::PassGraph *pg = nullptr;
   for (Frame::PassGraph &g : f->graphs)
     if (g.used && g.ctu_begin == ctu_begin && g.ctu_end == ctu_end && g.flags == key_flags) pg = &g;
   if (!pg)
     for (Frame::PassGraph &g : f->graphs)
-      if (!g.used) { g.used = true; g.ctu_begin = ctu_begin; g.ctu_end = ctu_end; g.flags = key_flags; g.seen = 0; g.exec = nullptr; pg = &g; break; }
+      if (!g.used) { g = Frame::PassGraph(); g.used = true; g.ctu_begin = ctu_begin; g.ctu_end = ctu_end; g.flags = key_flags; pg = &g; break; }
   static const bool no_graph = getenv("UVG266_B200_FRAME_GRAPH") && !strcmp(getenv("UVG266_B200_FRAME_GRAPH"), "0");
-  if (pg && pg->exec) {
-    UVGB_TRY(cudaGraphLaunch(pg->exec, st));
-    g_launches.fetch_add(pg->launches, std::memory_order_relaxed);
-  } else if (pg && pg->seen >= 1 && !no_graph) {
-    const uint64_t l0 = g_launches.load();
-    cudaGraph_t graph = nullptr;
-    UVGB_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_pass(f, ctu_begin, ctu_end, flags);
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rc || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("frame: graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return 1; }
-    pg->launches = g_launches.load() - l0;
-    const cudaError_t ie = cudaGraphInstantiate(&pg->exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) { pg->exec = nullptr; set_error("frame: graph instantiation failed: %s", cudaGetErrorString(ie)); return 1; }
-    UVGB_TRY(cudaGraphLaunch(pg->exec, st));
-  } else {
-    if (enqueue_pass(f, ctu_begin, ctu_end, flags)) return 1;
-    if (pg) pg->seen++;
+  const bool replay = pg && pg->ready, capture = pg && !pg->ready && pg->seen >= 1 && !no_graph;
+  const int ns = n_stages(f);
+  {
+    std::lock_guard<std::mutex> lock(ln->mu);              // one picture's kernels at a time, in submission order
+    UVGB_TRY(cudaStreamWaitEvent(ln->st, f->ev_in, 0));
+    UVGB_TRY(cudaEventRecord(f->ev_t0, ln->st));
+    for (int s = 0; s < ns; ++s) {
+      if (replay) {
+        UVGB_TRY(cudaGraphLaunch(pg->kernels[s], ln->st));
+        g_launches.fetch_add(pg->launches[s], std::memory_order_relaxed);
+      } else {
+        const uint64_t l0 = g_launches.load();
+        if (run_or_capture(ln->st, capture, capture ? &pg->kernels[s] : nullptr, [&] { return stage_kernels(f, s, ctu_begin, ctu_end, ln->st); })) return 1;
+        if (capture) pg->launches[s] = g_launches.load() - l0;
+      }
+      UVGB_TRY(cudaEventRecord(f->ev_stage[s], ln->st));
+    }
+    UVGB_TRY(cudaEventRecord(f->ev_t1, ln->st));
   }
-  UVGB_TRY(cudaEventRecord(f->ev_t1, st));
+  for (int s = 0; s < ns; ++s) {
+    UVGB_TRY(cudaStreamWaitEvent(f->s_copy, f->ev_stage[s], 0));
+    if (replay) {
+      if (pg->copies[s]) { UVGB_TRY(cudaGraphLaunch(pg->copies[s], f->s_copy)); g_launches.fetch_add(pg->copy_launches[s], std::memory_order_relaxed); }
+    } else {
+      bool any = false;
+      const uint64_t l0 = g_launches.load();
+      // (a stage without copies is not captured: probe first)
+      if (flags & UVG_B200_FRAME_NO_D2H) continue;
+      if (run_or_capture(f->s_copy, capture, capture ? &pg->copies[s] : nullptr, [&] { return stage_copies(f, s, ctu_begin, ctu_end, flags, f->s_copy, &any); })) return 1;
+      if (capture) pg->copy_launches[s] = g_launches.load() - l0;
+    }
+  }
+  UVGB_TRY(cudaEventRecord(f->ev_done, f->s_copy));
+  if (pg) { if (capture) pg->ready = true; else if (!replay) pg->seen++; }
   f->in_flight = true;
   return 0;
 }
@@ -686,6 +793,7 @@ extern "C" int uvg_b200_frame_submit(uvg_b200_frame *h, const void *src, size_t 
 extern "C" int uvg_b200_frame_wait(uvg_b200_frame *h, uvg_b200_frame_result *out)
 {
   if (!h) { set_error("frame: NULL handle"); return 1; }
+  if (ensure_init()) return 1;
   Frame *f = &h->f;
   if (!f->in_flight) { set_error("frame: wait without submit"); return 1; }
   f->in_flight = false;
@@ -695,25 +803,27 @@ extern "C" int uvg_b200_frame_wait(uvg_b200_frame *h, uvg_b200_frame_result *out
   uvg_b200_frame_result &r = f->res;
   memset(&r, 0, sizeof(r));
   r.ctu_begin = f->ctu_begin; r.ctu_end = f->ctu_end;
-  size_t tu_total = 0;
-  for (int i = 0; i < c.n_tus; ++i) tu_total += (size_t)band_ctus * f->tu[i].per_ctu;
-  UVGB_TRY(cudaEventSynchronize(f->ev_t1));               // kernels and (joined) copies of the pass
-  if (d2h) {
-    if (c.n_tus) {
-      // only now does the host know how many levels there are: one more copy of exactly that size
-      const uint64_t total = f->h_off[tu_total];
-      r.n_levels = total;
+  const size_t tu_total = tus_before(f, band_ctus, c.n_tus);
+  UVGB_TRY(cudaEventSynchronize(f->ev_done));             // kernels of the pass and the copies they released
+  if (d2h && c.n_tus) {
+    const uint64_t total = f->h_off[tu_total];
+    r.n_levels = total;
+    if (!levels_pushed()) {
+      // without the push kernel the host, which only now knows how many levels there are, issues one more copy of
+      // exactly that size
       if (total) UVGB_TRY(cudaMemcpyAsync(f->h_levels, f->d_levels, total * sizeof(int16_t), cudaMemcpyDeviceToHost, f->s_copy));
       UVGB_TRY(cudaStreamSynchronize(f->s_copy));
     }
   }
-  UVGB_TRY(cudaStreamSynchronize(f->s_main));
   float ms = 0.f;
-  UVGB_TRY(cudaEventElapsedTime(&ms, f->ev_t0, f->ev_t1));
+  UVGB_TRY(cudaEventElapsedTime(&ms, f->ev_t0, f->ev_t1));  // the pass's kernels, first to last
   r.device_ms = ms;
   if (d2h) {
     size_t base = 0;
-    for (int i = 0; i < c.n_levels; ++i) { r.rough_cost[i] = f->lv[i].h_cost; r.rough_best[i] = f->lv[i].h_best; }
+    for (int i = 0; i < c.n_levels; ++i) {
+      r.rough_cost[i] = (f->flags & UVG_B200_FRAME_ALL_COSTS) ? f->lv[i].h_cost : nullptr;
+      r.rough_best[i] = f->lv[i].h_best; r.rough_best_cost[i] = f->lv[i].h_best_cost;
+    }
     for (int i = 0; i < c.n_tus; ++i) {
       TuSize &t = f->tu[i];
       r.tu_mode[i] = t.h_mode; r.tu_has_coeffs[i] = t.h_has; r.tu_ssd[i] = t.h_ssd; r.tu_cost[i] = t.h_cost; r.tu_sig[i] = t.h_sig;
@@ -737,7 +847,7 @@ extern "C" int uvg_b200_frame_device_buffers(uvg_b200_frame *h, uvg_b200_frame_d
   for (int i = 0; i < f->cfg.n_tus; ++i) {
     out->tu_pred[i] = f->tu[i].d_pred; out->tu_rec[i] = f->tu[i].d_rec; out->tu_coeff[i] = f->tu[i].d_coeff;
   }
-  out->stream = f->s_main;
+  out->stream = lane() ? lane()->st : nullptr;           // the stream every pass's kernels run in
   return 0;
 }
 
