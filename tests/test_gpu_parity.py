@@ -698,6 +698,47 @@ def test_rough_cost_kernel_variants(mode):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_transform_kernel_variants():
+    """Square 16x16 / 32x32 transforms run on the INT8 tensor cores (transform_imma.cu); UVG266_B200_TRANSFORM=fast
+    selects the packed-ALU kernel every other shape uses: the same parity tests under it."""
+    import os, subprocess, sys
+    env = dict(os.environ, UVG266_B200_TRANSFORM="fast")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-x", "-q",
+                        "-k", "test_dropin_transforms or test_batched_quantize_residual_and_transform or test_transform_full_range"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("bd", BDS)
+@pytest.mark.parametrize("n", [16, 32])
+def test_transform_full_range_all_type_pairs(bd, n):
+    """The tensor-core transform kernels split 16-bit values into byte planes: full-range int16 input (every
+    accumulator at its bound), the type pairs of explicit MTS with the zero-out of 32-point DST7 / DCT8, both directions, against
+    the oracle's matrix formulation on every TU."""
+    O = load_oracle(bd)
+    L = U.lib()
+    rng = np.random.default_rng(5100 + bd + n)
+    nt = 37
+    x = rng.integers(-32768, 32768, nt * n * n).astype(np.int16)
+    x[: n * n] = 32767; x[n * n: 2 * n * n] = -32768
+    x[2 * n * n: 3 * n * n] = np.where(rng.integers(0, 2, n * n) == 1, 32767, -32768)
+    # tr_idx -> (type_hor, type_ver) of explicit MTS (dct-generic.c:2501-2557); DCT8 = 1, DST7 = 2
+    for tr_idx, (th, tv) in {0: (0, 0), 2: (2, 2), 3: (1, 2), 4: (2, 1), 5: (1, 1)}.items():
+        sk = 16 if (n == 32 and th != 0) else 0
+        skv = 16 if (n == 32 and tv != 0) else 0
+        y = np.zeros_like(x); z = np.zeros_like(x)
+        U.check(L.uvg_b200_transform_host(0, bd, n, n, th, tv, sk, skv, ptr(x), ptr(y), nt))
+        U.check(L.uvg_b200_transform_host(1, bd, n, n, th, tv, sk, skv, ptr(x), ptr(z), nt))
+        for t in range(nt):
+            sl = slice(t * n * n, (t + 1) * n * n)
+            xx = np.ascontiguousarray(x[sl]); o = np.zeros(n * n, np.int16)
+            O.orc_mts_dct(bd, 0, 1, tr_idx, 0, 0, 0, n, n, ptr(xx), ptr(o), 3)
+            assert (y[sl] == o).all(), ("fwd", n, th, tv, t)
+            O.orc_mts_idct(bd, 0, 1, tr_idx, 0, 0, 0, n, n, ptr(xx), ptr(o), 3)
+            assert (z[sl] == o).all(), ("inv", n, th, tv, t)
+
+
 @pytest.mark.parametrize("bd", BDS)
 def test_crc32c_and_bipred_average(bd):
     """The non-distortion leftovers of the picture table: IBC block hash and bi-prediction average,

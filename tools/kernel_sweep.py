@@ -5,7 +5,8 @@ size and both bit depths, algorithmic GB/s against the measured HBM peak.
   transform  : forward and inverse DCT-2, n = 4..32, 2^20 TUs (4*n*n bytes per TU)
   quant      : quant and dequant, n = 4..32, 2^20 TUs, QP 22 / 27 / 32 / 37 (timing is QP independent: one row)
 
-  python tools/kernel_sweep.py > profiles/r1_kernel_sweep.json
+  python tools/kernel_sweep.py [--only transform] > profiles/r2_kernel_sweep.json
+  UVG266_B200_TRANSFORM=fast python tools/kernel_sweep.py --only transform      # the packed-ALU transform kernel
 """
 import ctypes as C
 import json
@@ -41,9 +42,10 @@ def timed(fn, iters=10, warm=3):
     return a.elapsed_time(b) / iters
 
 
-res = {"hbm_peak_gbs": PEAK, "distortion": [], "transform": [], "quant": []}
+ONLY = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""      # e.g. --only transform
+res = {"hbm_peak_gbs": PEAK, "distortion": [], "transform": [], "quant": [], "transform_kernel": os.environ.get("UVG266_B200_TRANSFORM", "imma (16x16, 32x32) / fast")}
 g = torch.Generator(device=dev); g.manual_seed(1234)
-for bd in (8, 10):
+for bd in (() if ONLY and ONLY != "distortion" else (8, 10)):
     s = 1 if bd == 8 else 2
     total = 1 << 29                      # bytes per operand: 512 MiB (1 GiB read per launch)
     a = torch.randint(0, 1 << bd, (total // s,), dtype=torch.int16 if bd != 8 else torch.uint8, device=dev, generator=g)
@@ -60,7 +62,7 @@ for bd in (8, 10):
     del a, b
 NT = 1 << 20
 cfg = U.QuantCfg.make(27, 8, 1, 0, 0)
-for n in (4, 8, 16, 32):
+for n in (() if ONLY and ONLY not in ("transform", "quant") else (4, 8, 16, 32)):
     src = torch.randint(-255, 256, (NT * n * n,), dtype=torch.int16, device=dev, generator=g)
     dst = torch.zeros_like(src)
     for inv in (0, 1):

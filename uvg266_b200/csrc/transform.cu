@@ -102,7 +102,7 @@ int make_fwd_plan(TrPlan &p, int bd, int w, int h, int th, int tv, int skip_w, i
   // only the 8/16/32-point DST7/DCT8 forward kernels honour skip_line2 (:1574-2343)
   const int cut_w = (th == UVG_B200_DCT2 || w < 8) ? w : w - skip_w;
   const int cut_h = (tv == UVG_B200_DCT2 || h < 8) ? h : h - skip_h;
-  p.w = w; p.h = h;
+  p.w = w; p.h = h; p.th = th; p.tv = tv;
   if (h == 1) {            // :2608
     p.n1 = w; p.line1 = 1; p.reduced1 = 1; p.cutoff1 = cut_w; p.shift1 = l2w - 1 + bd - 8;
     p.t1 = tr_matrix_dev(th, w); p.n2 = 0; p.t2 = nullptr;
@@ -125,7 +125,7 @@ int make_inv_plan(TrPlan &p, int bd, int w, int h, int th, int tv, int skip_w, i
   const int cut_w = (th != UVG_B200_DCT2 && w == 8) ? w - skip_w : w;
   const int cut_h = (tv != UVG_B200_DCT2 && h == 8) ? h - skip_h : h;
   const int shift2 = 20 - bd;
-  p.w = w; p.h = h;
+  p.w = w; p.h = h; p.th = th; p.tv = tv;
   if (h == 1) {            // :2669
     p.n1 = w; p.line1 = 1; p.reduced1 = 1; p.cutoff1 = cut_w; p.shift1 = shift2 + 1;
     p.t1 = tr_matrix_dev(th, w); p.n2 = 0; p.t2 = nullptr;
@@ -336,6 +336,10 @@ transform_fast_kernel(const int16_t *__restrict__ in, int16_t *__restrict__ out,
 int launch_transform(bool inverse, const TrPlan &p, const int16_t *in, int16_t *out, size_t n_tus,
                      cudaStream_t st)
 {
+  {
+    const int rc = launch_transform_imma(inverse, p, in, out, n_tus, st);
+    if (rc >= 0) return rc;
+  }
   const int area = p.w * p.h;
   const int cl1 = inverse ? p.cutoff1 : p.n1, cl2 = inverse ? p.cutoff2 : p.n2;     // contraction lengths
   if (p.n2 && !(p.n1 & 3) && !(p.n2 & 3) && !(cl1 & 3) && !(cl2 & 3) && area >= 64 &&

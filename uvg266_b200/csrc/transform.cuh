@@ -18,6 +18,7 @@ struct TrPlan {
   int n2, line2, reduced2, cutoff2, shift2;   // second pass (n2 == 0: single-pass 1-D case)
   const int8_t *t1;                           // device matrices, row-major T[k*n+i]
   const int8_t *t2;
+  int th, tv;                                 // transform types (UVG_B200_DCT2 / DST7 / DCT8) of the two directions
 };
 
 // Forward kernel contract of the reference, e.g. fastForwardDCT2_B8 (dct-generic.c:1159),
@@ -118,6 +119,8 @@ int make_fwd_plan(TrPlan &p, int bitdepth, int w, int h, int type_hor, int type_
                   int skip_h);
 int make_inv_plan(TrPlan &p, int bitdepth, int w, int h, int type_hor, int type_ver, int skip_w,
                   int skip_h);
+// square 16x16 / 32x32 on the INT8 tensor cores (transform_imma.cu). 0: launched; -1: not covered; 1: error
+int launch_transform_imma(bool inverse, const TrPlan &p, const int16_t *in, int16_t *out, size_t n_tus, cudaStream_t st);
 // uvg_get_tr_type + the zero-out rules of mts_dct_generic (dct-generic.c:2501-2600).
 void derive_tr(int w, int h, int color, int cu_type, int tr_idx, int lfnst_idx, int cr_lfnst_idx,
                int isp_mode, int mts_type, int *type_hor, int *type_ver, int *skip_w, int *skip_h);
