@@ -77,6 +77,14 @@ frame_topk_kernel(const uint32_t *__restrict__ cost, size_t n_blocks, int k, int
 // block's candidate list.
 struct TuSel { int src_n, src_per_ctu, n_best; const uint8_t *best; };
 
+// shared-memory bytes of one TU of frame_tu_predict_kernel: an ODD number of 32-bit words, so that lanes working at the
+// same offset of different TUs hit different banks (192 bytes for 8x8 = 48 words made it a 16-way conflict)
+__host__ __device__ constexpr int tu_smem_bytes(int n)
+{
+  const int b = 4 * (2 * n + 12) + (n + 8) + kExtMirror + n * n;
+  return ((b / 4) & 1) ? b : b + 4;
+}
+
 template <int N, int TPC>
 __global__ void __launch_bounds__(256)
 frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, int per_ctu, size_t n_tus, TuSel sel,
@@ -89,7 +97,8 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
   // orientation and leave as 32-bit words.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int n = N, RS = 2 * n + 12, HEAD = n + 8, nn = n * n;
-  constexpr int per_tu = 4 * RS + HEAD + nn;                 // all multiples of 4
+  constexpr int TILE = 4 * RS + HEAD + kExtMirror;           // offset of a TU's prediction tile
+  constexpr int per_tu = tu_smem_bytes(N);                   // [4 reference rows | HEAD | mirror | tile], odd word count
   constexpr int l2 = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5;
   __shared__ int s_dc[TPC], s_mode[TPC], s_X[TPC], s_Y[TPC];
   __shared__ unsigned char s_class[TPC], s_order[TPC];
@@ -138,13 +147,16 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
       smem_raw[tu * per_tu + (2 + row) * RS + x] = (uint8_t)v;
     }
   } else {
-    // Reference rows from the plane, tail replicated: one thread per (TU, row). The top row is contiguous in the plane:
-    // aligned word loads + funnel shifts when the TU is away from the picture borders; the left column is strided.
-    for (int i = tid; i < TPC * 2; i += 256) {
-      const int tu = i >> 1, row = i & 1;
+    // Reference rows from the plane, tail replicated. 1 + LP work items per TU (one pass of the CTA's 256 threads): the
+    // top row (contiguous in the plane: aligned word loads + funnel shifts when the TU is away from the picture
+    // borders) and LP pieces of the strided left column.
+    constexpr int LP = N == 4 ? 2 : 4, Q = RS / LP;            // pieces of the left column, samples per piece
+    static_assert(RS % LP == 0 && TPC * (1 + LP) <= 256, "staging items");
+    for (int i = tid; i < TPC * (1 + LP); i += 256) {
+      const int tu = i / (1 + LP), part = i - tu * (1 + LP);
       const int X = s_X[tu], Y = s_Y[tu];
-      uint8_t *dst = smem_raw + tu * per_tu + row * RS;
-      if (row == 0 && Y >= 1 && X >= 4 && X + 2 * n + 4 <= g.W && Y - 1 < g.H) {
+      uint8_t *dst = smem_raw + tu * per_tu + (part ? RS : 0);
+      if (part == 0 && Y >= 1 && X >= 4 && X + 2 * n + 4 <= g.W && Y - 1 < g.H) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(plane + (size_t)(Y - 1) * stride + (X - 4));   // X, stride: multiples of 4
         constexpr int NW = (2 * n + 1 + 3) / 4;                                  // words that hold top[0 .. 2n]
         uint32_t w = __ldg(src);
@@ -159,11 +171,18 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
         const uint32_t last = dst[2 * n] * 0x01010101u;
   #pragma unroll
         for (int j = NW; j < RS / 4; ++j) *reinterpret_cast<uint32_t *>(dst + 4 * j) = last;
+      } else if (part == 0) {
+        for (int x = 0; x < RS; ++x)
+          dst[x] = __ldg(plane + (size_t)clampi(Y - 1, 0, g.H - 1) * stride + clampi(X - 1 + min(x, 2 * n), 0, g.W - 1));
       } else {
-        for (int x = 0; x < RS; ++x) {
-          const int xx = min(x, 2 * n);
-          const int sx = row ? X - 1 : X - 1 + xx, sy = row ? Y - 1 + xx : Y - 1;
-          dst[x] = __ldg(plane + (size_t)clampi(sy, 0, g.H - 1) * stride + clampi(sx, 0, g.W - 1));
+        const int x0 = (part - 1) * Q;
+        const uint8_t *col = plane + clampi(X - 1, 0, g.W - 1);
+        if (Y >= 1 && Y - 1 + 2 * n < g.H) {                   // no clamp along the column
+          const uint8_t *ps = col + (size_t)(Y - 1 + min(x0, 2 * n)) * stride;
+  #pragma unroll
+          for (int x = 0; x < Q; ++x) { dst[x0 + x] = __ldg(ps); if (x0 + x < 2 * n) ps += stride; }
+        } else {
+          for (int x = x0; x < x0 + Q; ++x) dst[x] = __ldg(col + (size_t)clampi(Y - 1 + min(x, 2 * n), 0, g.H - 1) * stride);
         }
       }
     }
@@ -200,6 +219,8 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
       const uint8_t *top = smem_raw + tu * per_tu + (mp.filtered ? 2 * RS : 0), *left = top + RS;
       const uint8_t *side = mp.vertical ? left : top;
       smem_raw[tu * per_tu + 4 * RS + HEAD - j] = side[min((j * mp.inv_angle + 256) >> 9, n)];
+      // angular_row8 reads the four words of a row from one base: the scratch continues with a copy of main[0 .. 12)
+      if (j <= kExtMirror) smem_raw[tu * per_tu + 4 * RS + HEAD + j - 1] = (mp.vertical ? top : left)[j - 1];
     }
   }
   __syncthreads();
@@ -211,7 +232,7 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
     const ModeParam mp = mt.m[s_mode[tu]];
     const uint8_t *base = smem_raw + tu * per_tu;
     const uint8_t *top = base + (mp.filtered ? 2 * RS : 0), *left = top + RS;
-    uint8_t *tile = smem_raw + tu * per_tu + 4 * RS + HEAD;
+    uint8_t *tile = smem_raw + tu * per_tu + TILE;
     uint32_t lo, hi;
     bool transposed = false;
     if (mp.kind == 2) {
@@ -235,7 +256,7 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
     const int tu = e / wpt, wi = e - tu * wpt, y = (4 * wi) >> l2, x = (4 * wi) & (n - 1);
     const size_t t = first + tu;
     if (t >= n_tus) break;
-    const uint8_t *tile = smem_raw + tu * per_tu + 4 * RS + HEAD;
+    const uint8_t *tile = smem_raw + tu * per_tu + TILE;
     reinterpret_cast<uint32_t *>(pred_out + t * (size_t)nn)[wi] = *reinterpret_cast<const uint32_t *>(tile + 4 * wi);
     const int X = s_X[tu] + x, Y = s_Y[tu] + y;
     uint32_t ow;
@@ -624,7 +645,7 @@ static int stage_kernels(Frame *f, int s, int ctu_begin, int ctu_end, cudaStream
     const size_t nt = (size_t)band_ctus * t.per_ctu;
     // TUs per CTA chosen so that the 8-pixel row items of a CTA's TUs fill its 256 threads
     const int nn = t.n * t.n, tpc = t.n == 4 ? 64 : t.n == 8 ? 32 : t.n == 16 ? 8 : 2;
-    const size_t smem = (size_t)tpc * (4 * (2 * t.n + 12) + t.n + 8 + nn);
+    const size_t smem = (size_t)tpc * tu_smem_bytes(t.n);
     const TuSel sel{ sl.n, sl.ppc, c.n_best, sl.d_best };
     const unsigned grid = (unsigned)((nt + tpc - 1) / tpc);
     if (t.n == 4) frame_tu_predict_kernel<4, 64><<<grid, 256, smem, st>>>(f->d_plane, f->pitch, g, t.per_ctu, nt, sel, t.mt, t.d_ref, t.d_pred, t.d_mode);
@@ -816,6 +837,7 @@ extern "C" int uvg_b200_frame_wait(uvg_b200_frame *h, uvg_b200_frame_result *out
     }
   }
   float ms = 0.f;
+  UVGB_TRY(cudaEventSynchronize(f->ev_t1));               // (recorded just after the last stage's event)
   UVGB_TRY(cudaEventElapsedTime(&ms, f->ev_t0, f->ev_t1));  // the pass's kernels, first to last
   r.device_ms = ms;
   if (d2h) {

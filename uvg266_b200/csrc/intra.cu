@@ -102,21 +102,22 @@ struct RoughCfg {
   static constexpr int RS = 2 * N + 12;              // shared-memory pitch of one reference row
   static constexpr int BS = 4 * RS + 4;              // per-block stride of the 4 rows: odd word count
   static constexpr int HEAD = N + 8;                 // scratch for main-reference indices -HEAD..-1
+  static constexpr int RP = N == 8 ? 32 : N == 16 ? 64 : 128;   // RS rounded up to a power of two (index math of the prologue)
   static constexpr int OP = N * N + 8 * NS;          // per-block stride of the original (bank spread)
 };
 
 // PLANE: block gb is CTU-major block (gb % per_ctu) of CTU ctu_begin + gb / per_ctu of the picture `src` (frame.cu);
 // original and reference rows come from the plane with border replication, `A` / `refs` are unused.
 template <int N, bool PLANE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, N == 16 ? 6 : 1)
 intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restrict__ out, size_t n_blocks, ModeTable mt,
                    PlaneSrc src)
 {
   using Cfg = RoughCfg<N>;
-  constexpr int NS = Cfg::NS, BPC = Cfg::BPC, RS = Cfg::RS, BS = Cfg::BS, HEAD = Cfg::HEAD, OP = Cfg::OP;
+  constexpr int NS = Cfg::NS, BPC = Cfg::BPC, RS = Cfg::RS, BS = Cfg::BS, HEAD = Cfg::HEAD, OP = Cfg::OP, RP = Cfg::RP;
   constexpr int GP = 2 * N + 4, L2 = N == 8 ? 3 : N == 16 ? 4 : 5;
   __shared__ __align__(16) uint8_t s_rows[BPC * BS];
-  __shared__ __align__(16) uint8_t s_ext[4][BPC][HEAD];
+  __shared__ __align__(16) uint8_t s_ext[4][BPC][HEAD + kExtMirror + 4];   // [.. HEAD) projected side samples, then a copy of main[0..12)
   __shared__ __align__(16) uint8_t s_orig[BPC * OP], s_origT[BPC * OP];
   __shared__ int s_dc[BPC];
   __shared__ int s_X[BPC], s_Y[BPC];
@@ -133,8 +134,9 @@ intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restr
     __syncthreads();
   }
   // reference rows (tail replicated)
-  for (int i = tid; i < BPC * 2 * RS; i += 128) {
-    const int blk = i / (2 * RS), rem = i - blk * 2 * RS, row = rem / RS, x = rem - row * RS;
+  for (int i = tid; i < BPC * 2 * RP; i += 128) {                        // (power-of-two index space: shifts, no divisions)
+    const int blk = i / (2 * RP), row = (i / RP) & 1, x = i & (RP - 1);
+    if (x >= RS) continue;
     if (PLANE) {
       const int xx = min(x, 2 * N), X = s_X[blk], Y = s_Y[blk];
       const int sx = row ? X - 1 : X - 1 + xx, sy = row ? Y - 1 + xx : Y - 1;
@@ -158,8 +160,9 @@ intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restr
     s_origT[blk * OP + x * N + y] = v;
   }
   __syncthreads();
-  for (int i = tid; i < BPC * 2 * RS; i += 128) {                         // intra_filter_reference :190-225
-    const int blk = i / (2 * RS), rem = i - blk * 2 * RS, row = rem / RS, x = rem - row * RS;
+  for (int i = tid; i < BPC * 2 * RP; i += 128) {                         // intra_filter_reference :190-225
+    const int blk = i / (2 * RP), row = (i / RP) & 1, x = i & (RP - 1);
+    if (x >= RS) continue;
     const uint8_t *top = s_rows + blk * BS, *left = top + RS, *src = row ? left : top;
     int v;
     if (x == 0) v = ((int)left[1] + 2 * (int)left[0] + (int)top[1] + 2) >> 2;
@@ -200,6 +203,10 @@ intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restr
           e[h] = w;
         }
         *reinterpret_cast<uint2 *>(ext0 - 8 * sx - 8) = make_uint2(e[0], e[1]);
+        if (sx == 0) {                                                    // angular_row8 reads a row's words from one base
+#pragma unroll
+          for (int q = 0; q < kExtMirror / 4; ++q) reinterpret_cast<uint32_t *>(ext0)[q] = reinterpret_cast<const uint32_t *>(mainr)[q];
+        }
         __syncwarp();
       }
       const int lim = min(3 << mp.scale, N);

@@ -160,6 +160,21 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
 }
 
 
+// four values -> four bytes, each saturated to 0..255 (two I2IP: clip and pack in one)
+__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3)
+{
+  uint32_t d;
+  asm("{ .reg .b32 t;\n\t"
+      "cvt.pack.sat.u8.s32.b32 t, %4, %3, 0;\n\t"
+      "cvt.pack.sat.u8.s32.b32 %0, %2, %1, t; }"
+      : "=r"(d) : "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+  return d;
+}
+
+// Bytes the scratch behind `ext0` must mirror from the main reference row (ext0[0 .. kExtMirror) = mainr[0 .. kExtMirror)):
+// a window that starts left of index 0 ends at most 11 bytes right of it, so a row's four words come from ONE base.
+constexpr int kExtMirror = 12;
+
 // One row (8 pixels: work-row r, work-columns 8*sx..8*sx+7) of an angular prediction.
 __device__ __forceinline__ void angular_row8(const ModeParam &mp, const uint8_t *mainr, const uint8_t *side,
                                              const uint8_t *ext0, int r, int sx, int lim, uint32_t &lo, uint32_t &hi)
@@ -170,37 +185,39 @@ __device__ __forceinline__ void angular_row8(const ModeParam &mp, const uint8_t 
   else if (mp.cubic) cw = *reinterpret_cast<const int *>(c_cubic[fr]);
   else { const int h = fr >> 1; cw = (16 - h) | ((32 - h) << 8) | ((16 + h) << 16) | (h << 24); }
   const int i0 = di + 8 * sx, b0 = i0 & ~3, sh = (i0 & 3) * 8;
-  uint32_t W[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int b = b0 + 4 * j;
-    W[j] = *reinterpret_cast<const uint32_t *>((b >= 0 ? mainr : ext0) + b);
-  }
-  const uint32_t A0 = __funnelshift_r(W[0], W[1], sh), A1 = __funnelshift_r(W[1], W[2], sh),
-                 A2 = __funnelshift_r(W[2], W[3], sh);
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>((b0 < 0 ? ext0 : mainr) + b0);
+  const uint32_t W0 = wp[0], W1 = wp[1], W2 = wp[2], W3 = wp[3];
+  const uint32_t A0 = __funnelshift_r(W0, W1, sh), A1 = __funnelshift_r(W1, W2, sh), A2 = __funnelshift_r(W2, W3, sh);
   int v[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const uint32_t a = c < 4 ? A0 : A1, b = c < 4 ? A1 : A2;
     const uint32_t win = (c & 3) ? __funnelshift_r(a, b, 8 * (c & 3)) : a;
-    v[c] = min(max(dp4a_us(win, cw, 32) >> 6, 0), 255);
+    v[c] = dp4a_us(win, cw, 32) >> 6;                                     // only the cubic taps can leave 0..255
   }
-  if (mp.pdpc) {
-    if (mp.sample_disp == 0) {                                            // :254-280
-      const int d = (int)side[1 + r] - (int)mainr[0];
+  if (!mp.pdpc) {
+    lo = pack4_sat_u8(v[0], v[1], v[2], v[3]);
+    hi = pack4_sat_u8(v[4], v[5], v[6], v[7]);
+    return;
+  }
+  if (mp.cubic) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int cc = 8 * sx + c;
-        if (cc < lim) v[c] = min(max(v[c] + (((32 >> ((2 * cc) >> mp.scale)) * d + 32) >> 6), 0), 255);
-      }
-    } else {                                                               // :234-251
+    for (int c = 0; c < 8; ++c) v[c] = min(max(v[c], 0), 255);
+  }
+  if (mp.sample_disp == 0) {                                              // :254-280
+    const int d = (int)side[1 + r] - (int)mainr[0];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int cc = 8 * sx + c;
-        if (cc < lim) {
-          const int l = side[r + ((256 + (cc + 1) * mp.inv_angle) >> 9) + 1];
-          v[c] = (v[c] + (((32 >> ((2 * cc) >> mp.scale)) * (l - v[c]) + 32) >> 6)) & 255;
-        }
+    for (int c = 0; c < 8; ++c) {
+      const int cc = 8 * sx + c;
+      if (cc < lim) v[c] = min(max(v[c] + (((32 >> ((2 * cc) >> mp.scale)) * d + 32) >> 6), 0), 255);
+    }
+  } else {                                                                 // :234-251
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int cc = 8 * sx + c;
+      if (cc < lim) {
+        const int l = side[r + ((256 + (cc + 1) * mp.inv_angle) >> 9) + 1];
+        v[c] = (v[c] + (((32 >> ((2 * cc) >> mp.scale)) * (l - v[c]) + 32) >> 6)) & 255;
       }
     }
   }
