@@ -287,6 +287,11 @@ class CpuArm:
         H.refh_frame_pass.argtypes = [C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + \
                                      [C.c_void_p] * 6 + [C.c_uint64]
 
+    def frame_strategy(self, name):
+        """'generic' (the parity oracle) or 'avx2' (the reference's own SIMD strategies; context only)."""
+        self.R.H.refh_frame_strategy.argtypes = [C.c_char_p]
+        return self.R.H.refh_frame_strategy(name.encode())
+
     def frame_run(self, threads):
         """Seconds for one frame pass over self.f_nctu CTUs with the unmodified reference's functions."""
         a = self.f_args
@@ -319,6 +324,16 @@ def reference_arm(args):
     fsteps = max(3, min(args.steps, 10))
     ft = [arm.frame_run(cores) for _ in range(fsteps)]
     fv = arm.f_nctu * fsteps / sum(ft)
+    # context: the same frame pass with the reference's AVX2 strategies (what the unmodified encoder selects on this CPU);
+    # the headline stays on the generic-C functions, which are what the parity oracle and the GPU kernels are pinned to
+    avx2 = None
+    try:
+        if arm.frame_strategy("avx2") > 0:
+            arm.frame_run(cores)
+            fa = [arm.frame_run(cores) for _ in range(fsteps)]
+            avx2 = {"value": arm.f_nctu * fsteps / sum(fa), "unit": "CTU/s", "strategies": "avx2 where the reference has them"}
+    finally:
+        arm.frame_strategy("generic")
     line = {
         "metric": METRIC, "value": v, "unit": "CTU/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
@@ -332,7 +347,7 @@ def reference_arm(args):
         "e2e": {"value": fv, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "workload": "frame_pass", "sample": "%d CTUs (%d CTU rows of the 4K picture) x %d passes, %d pthreads, "
                 "uvg_intra_predict + satd/sad duals + quantize_residual + ssd + fast_coeff_cost of the unmodified reference"
-                % (arm.f_nctu, frows, fsteps, cores), "ms_per_pass": 1e3 * sum(ft) / fsteps},
+                % (arm.f_nctu, frows, fsteps, cores), "ms_per_pass": 1e3 * sum(ft) / fsteps, "avx2_context": avx2},
         "gpu_launches": 0,
     }
     emit(line)
@@ -528,6 +543,15 @@ def gpu_arm(args):
             fr = [arm.frame_run(cores) for _ in range(3)]
             cpu_baseline["frame_pass"] = {"value": arm.f_nctu * len(fr) / sum(fr), "unit": "CTU/s", "cores": cores,
                                           "sample": "%d CTUs x %d passes" % (arm.f_nctu, len(fr))}
+            # context: the same frame pass with the reference's AVX2 strategies where it has them
+            # (intra prediction, SATD/SAD, DCT, quant, SSD, coefficient cost); bit-exact with generic by the
+            # reference's own tests, not the parity oracle
+            if arm.frame_strategy("avx2") > 0:
+                arm.frame_run(cores)
+                fa = [arm.frame_run(cores) for _ in range(3)]
+                cpu_baseline["frame_pass_avx2"] = {"value": arm.f_nctu * len(fa) / sum(fa), "unit": "CTU/s", "cores": cores,
+                                                   "sample": "%d CTUs x %d passes, reference AVX2 strategies" % (arm.f_nctu, len(fa))}
+            arm.frame_strategy("generic")
         except Exception as exc:  # reported, never silently replaced
             cpu_baseline = {"value": None, "unit": "CTU/s", "cores": host_cores(), "kind": "reference",
                             "sample": "unavailable: %s" % exc}

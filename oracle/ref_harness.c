@@ -587,6 +587,9 @@ static void frame_block(const frame_job_t *f, int X, int Y, int n, uvg_pixel *ds
       dst[y * n + x] = f->plane[(size_t)MIN(Y + y, f->H - 1) * f->stride + MIN(X + x, f->W - 1)];
 }
 
+static char g_frame_strategy_buf[32];
+static const char *g_frame_strategy = "generic";   /* refh_frame_strategy() */
+
 static void frame_ctu(const frame_job_t *f, int ctu)
 {
   const int cx = (ctu % f->ctu_cols) * LCU_WIDTH, cy = (ctu / f->ctu_cols) * LCU_WIDTH;
@@ -635,9 +638,12 @@ static void frame_ctu(const frame_job_t *f, int ctu)
       for (int s2 = 0; s2 < f->n_best; ++s2) best[s2] = (uint8_t)f->levels[l].modes[bi[s2 < k ? s2 : k - 1]];
     }
   }
-  quant_residual_func *qr = refh_get("quantize_residual", "generic");
-  pixels_calc_ssd_func *ssd = refh_get("pixels_calc_ssd", "generic");
-  fast_coeff_cost_func *fcc = refh_get("fast_coeff_cost", "generic");
+  quant_residual_func *qr = refh_get("quantize_residual", g_frame_strategy);
+  pixels_calc_ssd_func *ssd = refh_get("pixels_calc_ssd", g_frame_strategy);
+  fast_coeff_cost_func *fcc = refh_get("fast_coeff_cost", g_frame_strategy);
+  if (!qr) qr = refh_get("quantize_residual", "generic");
+  if (!ssd) ssd = refh_get("pixels_calc_ssd", "generic");
+  if (!fcc) fcc = refh_get("fast_coeff_cost", "generic");
   cu_info_t cu;
   fill_cu(&cu, CU_INTRA, 0, 0, 0, 0);
   for (int i = 0; i < f->n_tus; ++i) {
@@ -815,6 +821,22 @@ static double run_pool_job(refh_job_t *j, int threads)
   pthread_mutex_unlock(&g_pool.mu);
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* Which registered implementations the frame pass calls: "generic" (the parity oracle, default) or "avx2" (the
+ * reference's own SIMD strategies, for context; names without an avx2 entry stay generic). Also repoints the globals
+ * uvg_intra_predict / uvg_pixels_get_* dispatch through. Returns how many globals now point at `strategy`. */
+int refh_frame_strategy(const char *strategy)
+{
+  refh_use("generic");
+  g_frame_strategy = "generic";
+  if (strategy && strcmp(strategy, "generic")) {
+    const int n = refh_use(strategy);
+    snprintf(g_frame_strategy_buf, sizeof g_frame_strategy_buf, "%s", strategy);
+    g_frame_strategy = g_frame_strategy_buf;
+    return n;
+  }
+  return 0;
 }
 
 /* Runs the frame pass over CTUs [ctu_begin, ctu_end) on `threads` pool workers; returns seconds. */

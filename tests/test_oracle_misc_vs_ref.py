@@ -52,3 +52,27 @@ def test_pixel_var(bd):
         assert O.orc_pixel_var(ptr(a), n) == f(ptr(a), n)
         flat = np.full(n, (1 << bd) - 1, pix_dtype(bd))
         assert O.orc_pixel_var(ptr(flat), n) == f(ptr(flat), n) == 0.0
+
+
+def test_frame_pass_with_the_references_avx2_strategies_equals_generic():
+    """bench.py reports the CPU frame pass with the reference's AVX2 strategies as context next to the generic-C
+    baseline: same outputs on the same picture rows (the harness only repoints the strategy table)."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    try:
+        arm = bench.CpuArm(60)
+    except Exception as exc:
+        pytest.skip("oracle/_ref not built: %s" % exc)
+    arm.frame_setup(1)
+    arm.frame_run(2)
+    keep = {k: [x.copy() for x in v] for k, v in arm.f_arrays.items()}
+    try:
+        if arm.frame_strategy("avx2") <= 0:
+            pytest.skip("no AVX2 strategies registered on this CPU")
+        arm.frame_run(2)
+        for k, v in arm.f_arrays.items():
+            for a, b in zip(v, keep[k]):
+                assert (a == b).all(), k
+    finally:
+        arm.frame_strategy("generic")
