@@ -10,7 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 for src, dst in (("r2_bench.json", "r2_bench.json"), ("r2_bench_reference_arm.json", "r2_bench_reference_arm.json"),
                  ("r2_pytest_gpu.txt", "r2_pytest_gpu.txt"), ("r2_launches.csv", "r2_launches.csv"),
-                 ("bench_r2_n2.json", "r2_bench_2gpu.json"), ("r2_frame_device_ms.txt", "r2_frame_device_ms.txt")):
+                 ("bench_r2_n2.json", "r2_bench_2gpu.json"), ("r2_frame_device_ms.txt", "r2_frame_device_ms.txt"),
+                 ("r2_frame_kernel_times.txt", "r2_frame_kernel_times.txt"), ("r2_kernel_sweep_transform.json", "r2_kernel_sweep_transform.json"),
+                 ("r2_kernel_sweep_transform_fast.json", "r2_kernel_sweep_transform_fast.json"), ("r2_e2e_timeline.txt", "r2_e2e_timeline.txt")):
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 py = sys.executable
