@@ -103,13 +103,17 @@ struct RoughCfg {
   static constexpr int BS = 4 * RS + 4;              // per-block stride of the 4 rows: odd word count
   static constexpr int HEAD = N + 8;                 // scratch for main-reference indices -HEAD..-1
   static constexpr int RP = N == 8 ? 32 : N == 16 ? 64 : 128;   // RS rounded up to a power of two (index math of the prologue)
+  // bytes of one (warp, block) extension scratch: HEAD + mirror, rounded to an ODD multiple of 8 bytes (8-byte stores stay
+  // aligned, lanes of different blocks spread over the banks: 32 bytes for 8x8 was an 8-way conflict)
+  static constexpr int EXT8 = (HEAD + kExtMirror + 7) / 8;
+  static constexpr int EXTROW = 8 * (EXT8 | 1);
   static constexpr int OP = N * N + 8 * NS;          // per-block stride of the original (bank spread)
 };
 
 // PLANE: block gb is CTU-major block (gb % per_ctu) of CTU ctu_begin + gb / per_ctu of the picture `src` (frame.cu);
 // original and reference rows come from the plane with border replication, `A` / `refs` are unused.
 template <int N, bool PLANE>
-__global__ void __launch_bounds__(128, N == 16 ? 6 : 1)
+__global__ void __launch_bounds__(128, N == 8 ? 8 : N == 16 ? 6 : 5)    // 64 / 80 / 96 registers
 intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restrict__ out, size_t n_blocks, ModeTable mt,
                    PlaneSrc src)
 {
@@ -117,7 +121,7 @@ intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restr
   constexpr int NS = Cfg::NS, BPC = Cfg::BPC, RS = Cfg::RS, BS = Cfg::BS, HEAD = Cfg::HEAD, OP = Cfg::OP, RP = Cfg::RP;
   constexpr int GP = 2 * N + 4, L2 = N == 8 ? 3 : N == 16 ? 4 : 5;
   __shared__ __align__(16) uint8_t s_rows[BPC * BS];
-  __shared__ __align__(16) uint8_t s_ext[4][BPC][HEAD + kExtMirror + 4];   // [.. HEAD) projected side samples, then a copy of main[0..12)
+  __shared__ __align__(16) uint8_t s_ext[4][BPC][Cfg::EXTROW];   // [.. HEAD) projected side samples, then a copy of main[0..12)
   __shared__ __align__(16) uint8_t s_orig[BPC * OP], s_origT[BPC * OP];
   __shared__ int s_dc[BPC];
   __shared__ int s_X[BPC], s_Y[BPC];
