@@ -38,7 +38,9 @@ for obj in sorted(glob.glob(os.path.join(ROOT, "uvg266_b200", "build", "*.o"))):
 
 def demangle(n):
     try:
-        return subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip().split("(")[0]
+        d = subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
+        d = d.replace("(anonymous namespace)::", "").replace("uvgb::", "")
+        return d.split("(")[0]
     except OSError:
         return n
 
