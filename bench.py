@@ -689,7 +689,9 @@ def e2e_frame(torch, U, L, rank, world, args, barrier, dist, dev):
         hp.copy_(torch.from_numpy(synth_plane_rows([(rank * inflight + i, r) for r in range(CTU_ROWS)])))
         planes.append(hp)
     res = U.FrameResult()
-    k = max(3, min(args.steps, args.e2e_steps))
+    # pictures in the timed region: a picture is ~1 ms, so the frame-pipeline leg takes more of them than the PCIe-bound
+    # e2e_v1 leg (10 steps of 10 ms) to keep thread start-up and scheduling noise of the host out of the number
+    k = max(3, min(2 * args.steps, args.e2e_frame_steps))
     d2h = [0]
 
     import concurrent.futures
@@ -966,6 +968,7 @@ def main():
     ap.add_argument("--ref-frame-rows", type=int, default=CTU_ROWS, help="CTU rows per pass of the reference frame pass")
     ap.add_argument("--e2e-inflight", type=int, default=2, help="frame objects in flight in the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-frame-steps", type=int, default=60, help="pictures in the timed region of the frame-pipeline e2e (at most 2 x --steps)")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the *_host calls")
     ap.add_argument("--e2e-order", default="interleaved", choices=["interleaved", "sequential"],
                     help="order of the independent *_host calls inside a host thread")

@@ -121,12 +121,18 @@ static const uint32_t *cached_tables(int N, int th, int tv)
   return d;
 }
 
-template <int N>
+// PLAIN: no forward zero-out (cut1 == cut2 == N: every DCT-2 pair and every 8 / 16-point MTS pair), so the per-value
+// frequency compares disappear. The kernel only ever runs on 8-bit video, so the four rounding shifts are literals and
+// their offsets ride in as the initial value of the (low-plane) accumulators.
+template <int N, bool PLAIN>
 __global__ void __launch_bounds__(128, N == 32 ? 4 : 1)
 fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 {
   using S = ImmaShape<N>;
   constexpr int MT = S::MT, NT = S::NT, KT = S::KT;
+  constexpr int L2N = N == 8 ? 3 : N == 16 ? 4 : 5;
+  constexpr int SF1 = L2N - 1, SF2 = L2N + 6, SI1 = 7, SI2 = 12;             // dct-generic.c:2613-2615, :2673-2674 at 8 bits
+  constexpr int RF1 = SF1 > 0 ? 1 << (SF1 - 1) : 0, RF2 = 1 << (SF2 - 1), RI1 = 1 << (SI1 - 1), RI2 = 1 << (SI2 - 1);
   // constant operand fragments, [tile][reg][lane]
   __shared__ uint32_t sAH[MT * KT * 2 * 32];     // F1  A =  Th        (natural contraction order: pixel columns)
   __shared__ uint32_t sANH[MT * KT * 2 * 32];    // F1  A = -Th
@@ -149,8 +155,6 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
-  const int add_f1 = p.shift_f1 > 0 ? 1 << (p.shift_f1 - 1) : 0;
-  const int add_f2 = 1 << (p.shift_f2 - 1), add_i1 = 1 << (p.shift_i1 - 1), add_i2 = 1 << (p.shift_i2 - 1);
   const size_t n_units = (n_tus + S::TUS - 1) / S::TUS;
 
   for (size_t unit = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < n_units; unit += warps_total) {
@@ -190,7 +194,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        int acc[4] = { 0, 0, 0, 0 };
+        int acc[4] = { RF1, RF1, RF1, RF1 };
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) {
           const int fi = ((mt * KT + kt) * 2) * 32 + lane;
@@ -200,8 +204,8 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int k = N >= 16 ? mt * 16 + g + 8 * (c >> 1) : g;
-          const int s = (int)(short)((acc[c] + add_f1) >> p.shift_f1);
-          v[mt][nt][c] = k < p.cut1 ? s : 0;
+          const int s = (int)(short)(acc[c] >> SF1);
+          v[mt][nt][c] = (PLAIN || k < p.cut1) ? s : 0;
         }
       }
 
@@ -214,7 +218,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { accL[nt][c] = 0; accH[nt][c] = 0; }
+          for (int c = 0; c < 4; ++c) { accL[nt][c] = RF2; accH[nt][c] = 0; }
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) {
           uint32_t lo0, hi0, lo1, hi1;
@@ -237,8 +241,8 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int kv = nt * 8 + 2 * t + (c & 1);
-            const int s = (int)(short)((accH[nt][c] * 256 + accL[nt][c] + add_f2) >> p.shift_f2);
-            y[mt][nt][c] = kv < p.cut2 ? s : 0;
+            const int s = (int)(short)((accH[nt][c] * 256 + accL[nt][c]) >> SF2);
+            y[mt][nt][c] = (PLAIN || kv < p.cut2) ? s : 0;
           }
       }
 #pragma unroll
@@ -304,7 +308,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { accL[mt][c] = 0; accH[mt][c] = 0; }
+          for (int c = 0; c < 4; ++c) { accL[mt][c] = RI1; accH[mt][c] = 0; }
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) {
           uint32_t lo, hi;
@@ -325,7 +329,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            u[mt][nt][c] = clip3(-32768, 32767, (accH[mt][c] * 256 + accL[mt][c] + add_i1) >> p.shift_i1);
+            u[mt][nt][c] = clip3(-32768, 32767, (accH[mt][c] * 256 + accL[mt][c]) >> SI1);
       }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -333,7 +337,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { accL[nt][c] = 0; accH[nt][c] = 0; }
+          for (int c = 0; c < 4; ++c) { accL[nt][c] = RI2; accH[nt][c] = 0; }
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) {
           uint32_t lo0, hi0, lo1, hi1;
@@ -355,7 +359,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            rr[mt][nt][c] = clip3(-32768, 32767, (accH[nt][c] * 256 + accL[nt][c] + add_i2) >> p.shift_i2);
+            rr[mt][nt][c] = clip3(-32768, 32767, (accH[nt][c] * 256 + accL[nt][c]) >> SI2);
       }
     }
 
@@ -649,7 +653,8 @@ static int launch_imma(const FusedArgs &a, size_t n_tus, const QParams &q, const
   static const int cap_mult = getenv("UVG266_B200_IMMA_CAP") ? atoi(getenv("UVG266_B200_IMMA_CAP")) : 16;
   const size_t cap = (size_t)sm_count() * (size_t)(cap_mult > 0 ? cap_mult : 16);
   if (grid > cap) grid = cap;
-  fused_imma_kernel<N><<<(unsigned)grid, warps_per_block * 32, 0, st>>>(a, n_tus, q, p);
+  if (p.cut1 == N && p.cut2 == N) fused_imma_kernel<N, true><<<(unsigned)grid, warps_per_block * 32, 0, st>>>(a, n_tus, q, p);
+  else fused_imma_kernel<N, false><<<(unsigned)grid, warps_per_block * 32, 0, st>>>(a, n_tus, q, p);
   UVGB_LAUNCH_CHECK();
   return 0;
 }
