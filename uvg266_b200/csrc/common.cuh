@@ -107,6 +107,26 @@ __device__ __forceinline__ unsigned group_sum(unsigned v)
   return v;
 }
 
+// four values -> four bytes, each saturated to 0..255 (two I2IP: clip and pack in one)
+__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3)
+{
+  uint32_t d;
+  asm("{ .reg .b32 t;\n\t"
+      "cvt.pack.sat.u8.s32.b32 t, %4, %3, 0;\n\t"
+      "cvt.pack.sat.u8.s32.b32 %0, %2, %1, t; }"
+      : "=r"(d) : "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+  return d;
+}
+
+// two values -> two int16 halves (lo in bits 0-15), each saturated to -32768..32767: clip3(-32768, 32767, .) of both and
+// the pair packing of a byte-plane split in ONE instruction
+__device__ __forceinline__ uint32_t pack2_sat_s16(int lo, int hi)
+{
+  uint32_t d;
+  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+  return d;
+}
+
 __device__ __forceinline__ int clip3(int lo, int hi, int v) { return min(max(v, lo), hi); }
 
 static inline int ilog2_host(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }

@@ -280,7 +280,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
             if (tuc < n_tus) a.coeff_out[tuc * (size_t)(N * N) + kv * N + g] = (int16_t)level;
             if (c >> 1) { nzB |= ulevel; costB += wgt; } else { nzA |= ulevel; costA += wgt; }
           }
-          v[mt][nt][c] = clip3(-32768, 32767, (level * q.dq_scale + q.dq_add) >> q.dq_shift);   // dequant
+          v[mt][nt][c] = (level * q.dq_scale + q.dq_add) >> q.dq_shift;   // dequant; its clip to int16 happens in split4_sat
         }
     const bool hasA = __any_sync(0xffffffffu, nzA != 0);
     const bool hasB = N >= 16 ? false : __any_sync(0xffffffffu, nzB != 0);
@@ -314,9 +314,9 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
           uint32_t lo, hi;
           if (N >= 16) {
             const int h2 = 2 * (nt & 1);
-            split4(v[nt >> 1][2 * kt][h2], v[nt >> 1][2 * kt][h2 + 1], v[nt >> 1][2 * kt + 1][h2], v[nt >> 1][2 * kt + 1][h2 + 1], lo, hi);
+            split4_sat(v[nt >> 1][2 * kt][h2], v[nt >> 1][2 * kt][h2 + 1], v[nt >> 1][2 * kt + 1][h2], v[nt >> 1][2 * kt + 1][h2 + 1], lo, hi);
           } else {
-            split4(v[0][0][0], v[0][0][1], v[0][0][2], v[0][0][3], lo, hi);
+            split4_sat(v[0][0][0], v[0][0][1], v[0][0][2], v[0][0][3], lo, hi);
           }
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -329,7 +329,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            u[mt][nt][c] = clip3(-32768, 32767, (accH[mt][c] * 256 + accL[mt][c]) >> SI1);
+            u[mt][nt][c] = (accH[mt][c] * 256 + accL[mt][c]) >> SI1;       // clipped to int16 by split4_sat below
       }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -342,11 +342,11 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
         for (int kt = 0; kt < KT; ++kt) {
           uint32_t lo0, hi0, lo1, hi1;
           if (N >= 16) {
-            split4(u[mt][2 * kt][0], u[mt][2 * kt][1], u[mt][2 * kt + 1][0], u[mt][2 * kt + 1][1], lo0, hi0);
-            split4(u[mt][2 * kt][2], u[mt][2 * kt][3], u[mt][2 * kt + 1][2], u[mt][2 * kt + 1][3], lo1, hi1);
+            split4_sat(u[mt][2 * kt][0], u[mt][2 * kt][1], u[mt][2 * kt + 1][0], u[mt][2 * kt + 1][1], lo0, hi0);
+            split4_sat(u[mt][2 * kt][2], u[mt][2 * kt][3], u[mt][2 * kt + 1][2], u[mt][2 * kt + 1][3], lo1, hi1);
           } else {
-            split4(u[0][0][0], u[0][0][1], 0, 0, lo0, hi0);
-            split4(u[0][0][2], u[0][0][3], 0, 0, lo1, hi1);
+            split4_sat(u[0][0][0], u[0][0][1], 0, 0, lo0, hi0);
+            split4_sat(u[0][0][2], u[0][0][3], 0, 0, lo1, hi1);
           }
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
@@ -359,7 +359,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            rr[mt][nt][c] = clip3(-32768, 32767, (accH[nt][c] * 256 + accL[nt][c]) >> SI2);
+            rr[mt][nt][c] = min((accH[nt][c] * 256 + accL[nt][c]) >> SI2, 32767);   // (the lower int16 bound cannot matter: below)
       }
     }
 
@@ -374,13 +374,16 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
           const int mt = nt >> 1, hh = nt & 1;
           uint32_t outw = predw[nt][qs];
           if (recon) {
+            // reference: clip(0, 255, (int16)(clip16(r) + pred)). r <= 32767 is applied above; r < -32768 gives a negative
+            // sum with or without its clip, which the saturating pack turns into 0 either way; the int16 wrap of the sum
+            // (r close to 32767) is kept
             int px[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int r = rr[mt][2 * qs + (e >> 1)][2 * hh + (e & 1)];
-              px[e] = clip3(0, q.pixel_max, (int)(short)(r + (int)((predw[nt][qs] >> (8 * e)) & 0xffu)));
+              px[e] = (int)(short)(max(r, -32768) + (int)((predw[nt][qs] >> (8 * e)) & 0xffu));
             }
-            outw = pack4(px[0], px[1], px[2], px[3]);
+            outw = pack4_sat_u8(px[0], px[1], px[2], px[3]);
           }
           if (recon || !a.rec_is_pred)
             *reinterpret_cast<uint32_t *>(prec + (size_t)(nt * 8 + g) * a.rec.stride + qs * 16 + 4 * t) = outw;
@@ -406,8 +409,8 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
         const uint32_t pw = ((tb ? pB : pA) >> sh) & 0xffffu, rw = ((tb ? rB : rA) >> sh) & 0xffffu;
         uint32_t ow = pw;
         if (recon) {
-          const int x0 = clip3(0, q.pixel_max, (int)(short)(rr[0][0][2 * tb] + (int)(pw & 0xffu)));
-          const int x1 = clip3(0, q.pixel_max, (int)(short)(rr[0][0][2 * tb + 1] + (int)(pw >> 8)));
+          const int x0 = clip3(0, q.pixel_max, (int)(short)(max(rr[0][0][2 * tb], -32768) + (int)(pw & 0xffu)));
+          const int x1 = clip3(0, q.pixel_max, (int)(short)(max(rr[0][0][2 * tb + 1], -32768) + (int)(pw >> 8)));
           ow = (uint32_t)x0 | ((uint32_t)x1 << 8);
         }
         const size_t tuc = tu0 + tb;
@@ -562,7 +565,7 @@ fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__res
       ul[c] = ((unsigned)abs(v[c]) * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits;
       lv[c] = v[c] < 0 ? -(int)ul[c] : (int)ul[c];
       wg[c] = __byte_perm(wlo, whi, min(ul[c], 3u) * 0x22u + 0x10u) & 0xffffu;
-      v[c] = clip3(-32768, 32767, (lv[c] * q.dq_scale + q.dq_add) >> q.dq_shift);
+      v[c] = (lv[c] * q.dq_scale + q.dq_add) >> q.dq_shift;     // clipped to int16 by split4_sat below
     }
     {
       int16_t *co = a.coeff_out + (size_t)tuA * 64 + 16 * t + g;           // [kv][kh]
@@ -589,21 +592,23 @@ fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__res
     uint32_t outw = predw;
     if (reconA || reconB) {
       uint32_t lo, hi;
-      split4(v[0], v[1], v[2], v[3], lo, hi);
-      int accL[4], accH[4], u[4];
+      split4_sat(v[0], v[1], v[2], v[3], lo, hi);
+      int accL[4], accH[4];
       imma_c<false, true>(accL, avt0, avt1, lo, 64);
       imma_c<false, false>(accH, avt0, avt1, hi, 0);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) u[c] = clip3(-32768, 32767, (accH[c] * 256 + accL[c]) >> 7);
-      imma_c<true, false>(accL, __byte_perm(u[0], u[1], 0x0040), __byte_perm(u[2], u[3], 0x0040), bh, 2048);
-      imma_c<false, false>(accH, __byte_perm(u[0], u[1], 0x0051), __byte_perm(u[2], u[3], 0x0051), bh, 0);
+      // U clipped to int16 and packed in pairs by one saturating pack each; byte planes (u0.b0, u1.b0, 0, 0) / (.b1 ..)
+      const uint32_t u01 = pack2_sat_s16((accH[0] * 256 + accL[0]) >> 7, (accH[1] * 256 + accL[1]) >> 7);
+      const uint32_t u23 = pack2_sat_s16((accH[2] * 256 + accL[2]) >> 7, (accH[3] * 256 + accL[3]) >> 7);
+      imma_c<true, false>(accL, __byte_perm(u01, 0, 0x4420), __byte_perm(u23, 0, 0x4420), bh, 2048);
+      imma_c<false, false>(accH, __byte_perm(u01, 0, 0x4431), __byte_perm(u23, 0, 0x4431), bh, 0);
+      // reference: clip(0, 255, (int16)(clip16(r) + pred)): see fused_imma_kernel
       int px[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int r = clip3(-32768, 32767, (accH[c] * 256 + accL[c]) >> 12);
-        px[c] = clip3(0, q.pixel_max, (int)(short)(r + (int)((predw >> (8 * c)) & 0xffu)));
+        const int r = min(max((accH[c] * 256 + accL[c]) >> 12, -32768), 32767);
+        px[c] = (int)(short)(r + (int)((predw >> (8 * c)) & 0xffu));
       }
-      const uint32_t w = pack4(px[0], px[1], px[2], px[3]);
+      const uint32_t w = pack4_sat_u8(px[0], px[1], px[2], px[3]);
       outw = (reconA ? (w & 0xffffu) : (predw & 0xffffu)) | (reconB ? (w & 0xffff0000u) : (predw & 0xffff0000u));
     }
     if (reconA || !a.rec_is_pred)

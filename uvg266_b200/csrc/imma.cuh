@@ -30,6 +30,15 @@ __device__ __forceinline__ void split4(int v0, int v1, int v2, int v3, uint32_t 
   hi = __byte_perm(p01, p23, 0x7531);
 }
 
+// the same for values that still need their clip to int16 (inverse-transform stages, dequantised coefficients): the
+// saturating pair pack does the clip
+__device__ __forceinline__ void split4_sat(int v0, int v1, int v2, int v3, uint32_t &lo, uint32_t &hi)
+{
+  const uint32_t p01 = pack2_sat_s16(v0, v1), p23 = pack2_sat_s16(v2, v3);
+  lo = __byte_perm(p01, p23, 0x6420);
+  hi = __byte_perm(p01, p23, 0x7531);
+}
+
 __host__ __device__ __forceinline__ uint32_t pack4(int b0, int b1, int b2, int b3)
 {
   return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);

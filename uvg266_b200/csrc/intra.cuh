@@ -160,17 +160,6 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
 }
 
 
-// four values -> four bytes, each saturated to 0..255 (two I2IP: clip and pack in one)
-__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3)
-{
-  uint32_t d;
-  asm("{ .reg .b32 t;\n\t"
-      "cvt.pack.sat.u8.s32.b32 t, %4, %3, 0;\n\t"
-      "cvt.pack.sat.u8.s32.b32 %0, %2, %1, t; }"
-      : "=r"(d) : "r"(v0), "r"(v1), "r"(v2), "r"(v3));
-  return d;
-}
-
 // Bytes the scratch behind `ext0` must mirror from the main reference row (ext0[0 .. kExtMirror) = mainr[0 .. kExtMirror)):
 // a window that starts left of index 0 ends at most 11 bytes right of it, so a row's four words come from ONE base.
 constexpr int kExtMirror = 12;
