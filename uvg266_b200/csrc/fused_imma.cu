@@ -204,7 +204,7 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int k = N >= 16 ? mt * 16 + g + 8 * (c >> 1) : g;
-          const int s = (int)(short)(acc[c] >> SF1);
+          const int s = acc[c] >> SF1;                     // its int16 wrap = split4 taking the low half below
           v[mt][nt][c] = (PLAIN || k < p.cut1) ? s : 0;
         }
       }
@@ -270,7 +270,8 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
           const int level = cf < 0 ? -(int)ulevel : (int)ulevel;
           const int kv = nt * 8 + 2 * t + (c & 1);
           // fast_coeff_cost weight of min(|level|, 3): one PRMT on the packed Q8.8 table, no branch
-          const unsigned wgt = __byte_perm(wlo, whi, min(ulevel, 3u) * 0x22u + 0x10u) & 0xffffu;
+          // (bytes 2, 3 of the PRMT result are copies of byte 0 of the table: a constant, taken off after the reduction)
+          const unsigned wgt = __byte_perm(wlo, whi, min(ulevel, 3u) * 0x22u + 0x10u);
           if (N >= 16) {
             const int kh = mt * 16 + g + 8 * (c >> 1);
             a.coeff_out[tu0 * (size_t)(N * N) + kv * N + kh] = (int16_t)level;
@@ -285,8 +286,10 @@ fused_imma_kernel(FusedArgs a, size_t n_tus, QParams q, ImmaParams p)
     const bool hasA = __any_sync(0xffffffffu, nzA != 0);
     const bool hasB = N >= 16 ? false : __any_sync(0xffffffffu, nzB != 0);
     if (a.cost) {
-      costA = __reduce_add_sync(0xffffffffu, costA);
-      if (N < 16) costB = __reduce_add_sync(0xffffffffu, costB);
+      // every lane added (N * N / 32) [two 8x8 TUs: 2 each] weights per TU, each carrying the constant junk halves
+      const unsigned junk = ((wlo & 0xffu) * 0x01010000u) * (N >= 16 ? (unsigned)(N * N) : 64u);
+      costA = __reduce_add_sync(0xffffffffu, costA) - junk;
+      if (N < 16) costB = __reduce_add_sync(0xffffffffu, costB) - junk;
       if (lane == 0) {
         a.cost[tu0] = (costA + 128u) >> 8;
         if (N < 16 && tu0 + 1 < n_tus) a.cost[tu0 + 1] = (costB + 128u) >> 8;
@@ -547,7 +550,7 @@ fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__res
       imma_c<false, true>(d, ah0, ah1, refw, 2);
       imma<false, true>(d, anh0, anh1, predw);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[c] = (int)(short)(d[c] >> 2);
+      for (int c = 0; c < 4; ++c) v[c] = d[c] >> 2;            // (int16 wrap = the byte picks of the next operands)
     }
     // ---- F2: Y^T = D' Tv^T (rows kh, columns kv = 2t, 2t+1); bytes 2,3 of the A words meet zeros --
     {
@@ -564,7 +567,7 @@ fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__res
     for (int c = 0; c < 4; ++c) {
       ul[c] = ((unsigned)abs(v[c]) * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits;
       lv[c] = v[c] < 0 ? -(int)ul[c] : (int)ul[c];
-      wg[c] = __byte_perm(wlo, whi, min(ul[c], 3u) * 0x22u + 0x10u) & 0xffffu;
+      wg[c] = __byte_perm(wlo, whi, min(ul[c], 3u) * 0x22u + 0x10u);        // + constant junk in bytes 2, 3: removed below
       v[c] = (lv[c] * q.dq_scale + q.dq_add) >> q.dq_shift;     // clipped to int16 by split4_sat below
     }
     {
@@ -575,8 +578,9 @@ fused_imma8_kernel(FusedArgs a, uint32_t n_tus, QParams q, const uint32_t *__res
     const bool hasA = __any_sync(0xffffffffu, (ul[0] | ul[1]) != 0);
     const bool hasB = __any_sync(0xffffffffu, (ul[2] | ul[3]) != 0);
     if (a.cost) {
-      const unsigned costA = __reduce_add_sync(0xffffffffu, wg[0] + wg[1]);
-      const unsigned costB = __reduce_add_sync(0xffffffffu, wg[2] + wg[3]);
+      const unsigned junk = ((wlo & 0xffu) * 0x01010000u) * 64u;           // 64 weights per TU, each with the junk halves
+      const unsigned costA = __reduce_add_sync(0xffffffffu, wg[0] + wg[1]) - junk;
+      const unsigned costB = __reduce_add_sync(0xffffffffu, wg[2] + wg[3]) - junk;
       if (lane == 0) {
         a.cost[tuA] = (costA + 128u) >> 8;
         if (validB) a.cost[tuA + 1] = (costB + 128u) >> 8;
