@@ -101,9 +101,12 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
   constexpr int per_tu = tu_smem_bytes(N);                   // [4 reference rows | HEAD | mirror | tile], odd word count
   constexpr int l2 = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5;
   __shared__ int s_dc[TPC], s_mode[TPC], s_X[TPC], s_Y[TPC];
-  __shared__ unsigned char s_class[TPC], s_order[TPC];
+  constexpr int kClasses = 8;                                // planar, DC, 2 + {no PDPC, PDPC at 0 displacement, PDPC} + 3 * horizontal
+  __shared__ unsigned char s_class[TPC], s_order[TPC], s_rank[TPC];
+  __shared__ int s_hist[kClasses];
   const int tid = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * TPC;
+  if (tid >= 256 - kClasses) s_hist[255 - tid] = 0;          // (threads that have nothing to do in the next block)
   if (tid < TPC) {
     const size_t t = min(first + tid, n_tus - 1);
     int X, Y, ctu, j;
@@ -122,11 +125,16 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
     s_class[tid] = (unsigned char)(mp.kind != 2 ? mp.kind : 2 + (mp.pdpc ? (mp.sample_disp == 0 ? 1 : 2) : 0) + (mp.vertical ? 0 : 3));
   }
   __syncthreads();
-  if (tid < TPC) {                                           // stable counting sort of the CTA's TUs by class
+  // counting sort of the CTA's TUs by class (order inside a class does not matter): a shared-memory histogram hands out
+  // the ranks, the running sums over the eight classes give the bases
+  if (tid < TPC) s_rank[tid] = (unsigned char)atomicAdd(&s_hist[s_class[tid]], 1);
+  __syncthreads();
+  if (tid < TPC) {
     const int c = s_class[tid];
-    int pos = 0;
-    for (int o = 0; o < TPC; ++o) pos += (s_class[o] < c) || (s_class[o] == c && o < tid);
-    s_order[pos] = (unsigned char)tid;
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < kClasses; ++k) base += k < c ? s_hist[k] : 0;
+    s_order[base + s_rank[tid]] = (unsigned char)tid;
   }
   if (N >= 16) {
     // large TUs: few TUs per CTA, long rows - one thread per reference sample
