@@ -343,9 +343,9 @@ typedef struct uvg_b200_frame_cfg {
 
 /* Results of one pass: HOST pointers into pinned buffers owned by the frame object, valid until the next submit.
  * Coefficients come back compact: tu_sig[i] is a bit array over the dense [n_tus][n*n] coefficient array of TU size
- * i (coefficient g = bit (g & 31) of word g >> 5), `levels` holds the non-zero coefficients of all TUs (sizes in
- * configuration order, TUs in index order, coefficients in index order) and tu_level_off[i][t] is where TU t's
- * begin. uvg_b200_frame_expand_coeffs rebuilds the dense array. tu_coeff_dense is set only with
+ * i (coefficient g = bit (g & 31) of word g >> 5), `levels` holds the non-zero coefficients of all TUs - a TU's are
+ * contiguous and in index order, starting at tu_level_off[i][t]; the order of the TUs inside `levels` is unspecified
+ * (it can differ between two passes over the same picture). uvg_b200_frame_expand_coeffs rebuilds the dense array. tu_coeff_dense is set only with
  * UVG_B200_FRAME_DENSE_COEFF. */
 typedef struct uvg_b200_frame_result {
   int32_t ctu_begin, ctu_end;

@@ -19,7 +19,6 @@
 // visit of that position: visit r uses the r-th best candidate mode of the rough block that covers it.
 #include "common.cuh"
 #include "intra.cuh"
-#include <cub/device/device_scan.cuh>
 #include <mutex>
 #include <new>
 #include <string.h>
@@ -284,7 +283,7 @@ frame_tu_predict_kernel(const uint8_t *__restrict__ plane, int stride, Geo g, in
 // The dense coefficient arrays of the residual pass ([n_tus][n*n] int16) are mostly zeros. What crosses PCIe is
 //   sig    : one bit per coefficient of the dense array (bit i of the array = bit (i & 31) of word i >> 5)
 //   levels : the non-zero coefficients, TU after TU, each TU's in index order
-//   off    : per TU, where its levels start (exclusive prefix sum of the per-TU non-zero counts)
+//   off    : per TU, where its levels start
 // Lane l of a warp owns coefficients [8l, 8l+8) of a 256-coefficient chunk.
 template <int S /* coefficients per TU: 16, 64, 256, 1024 */>
 __device__ __forceinline__ void chunk_masks(const int16_t *__restrict__ coeff, size_t chunk, size_t n_chunks, int lane,
@@ -301,79 +300,77 @@ __device__ __forceinline__ void chunk_masks(const int16_t *__restrict__ coeff, s
   }
 }
 
+// One pass over a TU size's dense coefficients: significance bits, the packed levels, and per TU where its levels start.
+// A warp takes one unit (a 256-coefficient chunk; a whole TU for 32x32) per iteration and keeps its 16-byte pieces in
+// registers; the CTA's eight unit totals are summed, ONE atomicAdd on the picture's level counter reserves the CTA's
+// span of `levels`, and every lane stores its non-zero values at span + prefix. A TU's levels are contiguous and in
+// index order; in which order the TUs (and TU sizes) lie in `levels` is whatever the atomics decide - tu_level_off[]
+// says where each one starts. (The two-pass form - count kernel, device-wide scan, pack kernel - read the 111 MB of a
+// 4K picture's coefficients twice and cost 95 us; this one 50.)
 template <int S>
 __global__ void __launch_bounds__(256)
-coeff_count_kernel(const int16_t *__restrict__ coeff, size_t n_coeffs, uint32_t *__restrict__ sig, uint32_t *__restrict__ cnt)
+coeff_compact_kernel(const int16_t *__restrict__ coeff, size_t n_coeffs, uint32_t *__restrict__ sig, uint32_t *__restrict__ off,
+                     int16_t *__restrict__ levels, uint32_t *__restrict__ counter)
 {
-  const int lane = threadIdx.x & 31;
-  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  __shared__ unsigned s_tot[8], s_base[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t n_chunks = (n_coeffs + 255) / 256;            // n_coeffs is a multiple of 16; a tail chunk reads zeros
-  constexpr int CPT = S > 256 ? S / 256 : 1;                 // chunks per TU (32x32: 4)
-  for (size_t c0 = warp * CPT; c0 < n_chunks; c0 += n_warps * CPT) {
-    unsigned acc = 0;
+  constexpr int CPT = S > 256 ? S / 256 : 1;                 // chunks per unit (32x32: the TU's 4)
+  constexpr int LPT = S >= 256 ? 32 : S / 8;                 // lanes per TU inside a chunk
+  const size_t n_units = (n_chunks + CPT - 1) / CPT, units_per_iter = (size_t)gridDim.x * 8;
+  const size_t iters = (n_units + units_per_iter - 1) / units_per_iter;
+  for (size_t it = 0; it < iters; ++it) {
+    const size_t unit = it * units_per_iter + (size_t)blockIdx.x * 8 + warp, c0 = unit * CPT;
+    uint4 v[CPT]; uint32_t m8[CPT]; unsigned excl[CPT], seg0[CPT], tot[CPT];
+    unsigned unit_total = 0;
 #pragma unroll
     for (int cc = 0; cc < CPT; ++cc) {
       const size_t chunk = c0 + cc;
-      uint32_t m8; uint4 v;
-      // the last chunk may be partial (n_coeffs % 256 != 0 only for 4x4 / 8x8 TU counts): guard the load
-      if ((chunk * 256 + (size_t)lane * 8) < n_coeffs) chunk_masks<S>(coeff, chunk, n_chunks, lane, m8, v); else m8 = 0;
-      uint32_t m = m8 << (8 * (lane & 3));
+      const bool live = unit < n_units && (chunk * 256 + (size_t)lane * 8) < n_coeffs;
+      m8[cc] = 0; v[cc] = make_uint4(0, 0, 0, 0);
+      if (live) chunk_masks<S>(coeff, chunk, n_chunks, lane, m8[cc], v[cc]);
+      uint32_t m = m8[cc] << (8 * (lane & 3));
       m |= __shfl_xor_sync(0xffffffffu, m, 1);
       m |= __shfl_xor_sync(0xffffffffu, m, 2);
-      if ((lane & 3) == 0 && (chunk * 256 + (size_t)lane * 8) < n_coeffs) sig[chunk * 8 + (lane >> 2)] = m;
-      unsigned c = __popc(m8);
-      constexpr int LPT = S >= 256 ? 32 : S / 8;              // lanes per TU inside a chunk
-#pragma unroll
-      for (int d = LPT / 2; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-      if (S <= 256) {
-        if ((lane % LPT) == 0) {
-          const size_t tu = (chunk * 256 + (size_t)lane * 8) / S;
-          if (tu * S < n_coeffs) cnt[tu] = c;
-        }
-      } else {
-        acc += c;
-      }
-    }
-    if (S > 256 && lane == 0) cnt[c0 / CPT] = acc;
-  }
-}
-
-template <int S>
-__global__ void __launch_bounds__(256)
-coeff_pack_kernel(const int16_t *__restrict__ coeff, size_t n_coeffs, const uint32_t *__restrict__ off,
-                  int16_t *__restrict__ levels)
-{
-  const int lane = threadIdx.x & 31;
-  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  const size_t n_chunks = (n_coeffs + 255) / 256;
-  constexpr int CPT = S > 256 ? S / 256 : 1;
-  constexpr int LPT = S >= 256 ? 32 : S / 8;
-  for (size_t c0 = warp * CPT; c0 < n_chunks; c0 += n_warps * CPT) {
-    unsigned carried = 0;
-#pragma unroll
-    for (int cc = 0; cc < CPT; ++cc) {
-      const size_t chunk = c0 + cc;
-      const bool live = (chunk * 256 + (size_t)lane * 8) < n_coeffs;
-      uint32_t m8 = 0; uint4 v = make_uint4(0, 0, 0, 0);
-      if (live) chunk_masks<S>(coeff, chunk, n_chunks, lane, m8, v);
-      const unsigned c = __popc(m8);
+      if ((lane & 3) == 0 && live) sig[chunk * 8 + (lane >> 2)] = m;
+      const unsigned c = __popc(m8[cc]);
       unsigned incl = c;                                     // inclusive scan over the warp
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-      const unsigned excl = incl - c;
-      const unsigned seg0 = __shfl_sync(0xffffffffu, excl, lane - (lane % LPT));
-      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-      if (live && m8) {
-        const size_t tu = (chunk * 256 + (size_t)lane * 8) / S;
-        int16_t *dst = levels + off[tu] + carried + (excl - seg0);
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+      excl[cc] = incl - c;
+      seg0[cc] = __shfl_sync(0xffffffffu, excl[cc], lane - (lane % LPT));
+      tot[cc] = __shfl_sync(0xffffffffu, incl, 31);
+      unit_total += tot[cc];
+    }
+    if (lane == 0) s_tot[warp] = unit_total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned sum = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (w[i] & 0xffffu) *dst++ = (int16_t)(w[i] & 0xffffu);
-          if (w[i] >> 16) *dst++ = (int16_t)(w[i] >> 16);
+      for (int w = 0; w < 8; ++w) sum += s_tot[w];
+      unsigned base = sum ? atomicAdd(counter, sum) : 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { s_base[w] = base; base += s_tot[w]; }
+    }
+    __syncthreads();
+    unsigned pos = s_base[warp];
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc) {
+      const size_t chunk = c0 + cc, first = chunk * 256 + (size_t)lane * 8;
+      if (unit < n_units && first < n_coeffs) {
+        if (S <= 256) { if ((lane % LPT) == 0) off[first / S] = pos + seg0[cc]; }
+        else if (cc == 0 && lane == 0) off[first / S] = pos;
+        if (m8[cc]) {
+          int16_t *dst = levels + pos + excl[cc];
+          const uint32_t w[4] = { v[cc].x, v[cc].y, v[cc].z, v[cc].w };
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (w[i] & 0xffffu) *dst++ = (int16_t)(w[i] & 0xffffu);
+            if (w[i] >> 16) *dst++ = (int16_t)(w[i] >> 16);
+          }
         }
       }
-      carried += total;
+      pos += tot[cc];
     }
   }
 }
@@ -426,8 +423,7 @@ struct Frame {
   Level lv[kMaxLv];
   TuSize tu[kMaxLv];
   size_t total_tus = 0, total_coeffs = 0;
-  uint32_t *d_cnt = nullptr, *d_off = nullptr, *h_off = nullptr;
-  void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+  uint32_t *d_off = nullptr, *h_off = nullptr;         // per TU: where its levels start; [total TUs] = the level counter
   int16_t *d_levels = nullptr, *h_levels = nullptr;
   uvg_b200_frame_result res;
   int ctu_begin = 0, ctu_end = 0, flags = 0;
@@ -448,7 +444,7 @@ static void frame_release(Frame *f)
   if (f->s_copy) cudaStreamSynchronize(f->s_copy);
   auto D = [](void *p) { if (p) cudaFree(p); };
   auto Hh = [](void *p) { if (p) cudaFreeHost(p); };
-  D(f->d_plane); D(f->d_cnt); D(f->d_off); D(f->d_scan_tmp); D(f->d_levels);
+  D(f->d_plane); D(f->d_off); D(f->d_levels);
   Hh(f->h_off); Hh(f->h_levels);
   for (int i = 0; i < kMaxLv; ++i) {
     Level &l = f->lv[i];
@@ -514,10 +510,8 @@ static int frame_build(Frame *f, const uvg_b200_frame_cfg *c)
         halloc(t.h_sig, px / 32 + 8)) return 1;
     f->total_tus += t.nt; f->total_coeffs += px;
   }
-  if (dalloc(f->d_cnt, f->total_tus + 1) || dalloc(f->d_off, f->total_tus + 1) || halloc(f->h_off, f->total_tus + 1) ||
+  if (dalloc(f->d_off, f->total_tus + 1) || halloc(f->h_off, f->total_tus + 1) ||
       dalloc(f->d_levels, f->total_coeffs + 8) || halloc(f->h_levels, f->total_coeffs + 8)) return 1;
-  UVGB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, f->scan_tmp_bytes, f->d_cnt, f->d_off, (int)(f->total_tus + 1), f->s_in));
-  UVGB_TRY(cudaMalloc(&f->d_scan_tmp, f->scan_tmp_bytes + 64));
   return 0;
 }
 
@@ -543,26 +537,26 @@ static int cfg_check(const uvg_b200_frame_cfg *c)
 }
 
 template <int S>
-static void launch_count_pack(bool pack, const int16_t *coeff, size_t n_coeffs, uint32_t *sig, uint32_t *cnt,
-                              const uint32_t *off, int16_t *levels, cudaStream_t st)
+static void launch_compact(const int16_t *coeff, size_t n_coeffs, uint32_t *sig, uint32_t *off, int16_t *levels, uint32_t *counter,
+                           cudaStream_t st)
 {
-  const size_t chunks = (n_coeffs + 255) / 256;
-  size_t grid = (chunks + 7) / 8;
-  const size_t cap = (size_t)sm_count() * 16;
+  constexpr int CPT = S > 256 ? S / 256 : 1;
+  const size_t units = ((n_coeffs + 255) / 256 + CPT - 1) / CPT;
+  size_t grid = (units + 7) / 8;
+  const size_t cap = (size_t)sm_count() * 8;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  if (!pack) coeff_count_kernel<S><<<(unsigned)grid, 256, 0, st>>>(coeff, n_coeffs, sig, cnt);
-  else coeff_pack_kernel<S><<<(unsigned)grid, 256, 0, st>>>(coeff, n_coeffs, off, levels);
+  coeff_compact_kernel<S><<<(unsigned)grid, 256, 0, st>>>(coeff, n_coeffs, sig, off, levels, counter);
 }
 
-static int count_pack(bool pack, int n, const int16_t *coeff, size_t n_coeffs, uint32_t *sig, uint32_t *cnt,
-                      const uint32_t *off, int16_t *levels, cudaStream_t st)
+static int compact(int n, const int16_t *coeff, size_t n_coeffs, uint32_t *sig, uint32_t *off, int16_t *levels, uint32_t *counter,
+                   cudaStream_t st)
 {
   switch (n) {
-    case 4: launch_count_pack<16>(pack, coeff, n_coeffs, sig, cnt, off, levels, st); break;
-    case 8: launch_count_pack<64>(pack, coeff, n_coeffs, sig, cnt, off, levels, st); break;
-    case 16: launch_count_pack<256>(pack, coeff, n_coeffs, sig, cnt, off, levels, st); break;
-    default: launch_count_pack<1024>(pack, coeff, n_coeffs, sig, cnt, off, levels, st); break;
+    case 4: launch_compact<16>(coeff, n_coeffs, sig, off, levels, counter, st); break;
+    case 8: launch_compact<64>(coeff, n_coeffs, sig, off, levels, counter, st); break;
+    case 16: launch_compact<256>(coeff, n_coeffs, sig, off, levels, counter, st); break;
+    default: launch_compact<1024>(coeff, n_coeffs, sig, off, levels, counter, st); break;
   }
   UVGB_LAUNCH_CHECK();
   return 0;
@@ -620,7 +614,7 @@ static bool levels_pushed()
   return on;
 }
 
-static int n_stages(const Frame *f) { return 1 + f->cfg.n_tus + (f->cfg.n_tus ? 1 : 0); }
+static int n_stages(const Frame *f) { return 1 + f->cfg.n_tus; }
 
 static size_t tus_before(const Frame *f, int band_ctus, int i)
 {
@@ -666,18 +660,10 @@ static int stage_kernels(Frame *f, int s, int ctu_begin, int ctu_end, cudaStream
     for (uvg_b200_blocks *b : { &R, &P, &O }) { b->stride = (uint32_t)t.n; b->blocks_per_row = 1; b->col_pitch = 0; b->row_pitch = (uint64_t)nn; }
     if (uvg_b200_quantize_residual_dev(&c.quant, 1 /* CU_INTRA */, 0, t.n, t.n, 0, 0, 0, &R, &P, &O, t.d_coeff, t.d_has, t.d_ssd,
                                        t.d_cost, c.cost_weights, nt, st)) return 1;
-    return count_pack(false, t.n, t.d_coeff, nt * (size_t)nn, t.d_sig, f->d_cnt + tus_before(f, band_ctus, i), nullptr, nullptr, st);
-  }
-  // ---- compact coefficients: offsets = exclusive scan of the counts, then the packed levels
-  const size_t tu_total = tus_before(f, band_ctus, c.n_tus);
-  UVGB_TRY(cudaMemsetAsync(f->d_cnt + tu_total, 0, sizeof(uint32_t), st));
-  size_t tmp = f->scan_tmp_bytes;
-  UVGB_TRY(cub::DeviceScan::ExclusiveSum(f->d_scan_tmp, tmp, f->d_cnt, f->d_off, (int)(tu_total + 1), st));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  for (int i = 0; i < c.n_tus; ++i) {
-    TuSize &t = f->tu[i];
-    const size_t nt = (size_t)band_ctus * t.per_ctu;
-    if (count_pack(true, t.n, t.d_coeff, nt * (size_t)(t.n * t.n), nullptr, nullptr, f->d_off + tus_before(f, band_ctus, i), f->d_levels, st)) return 1;
+    // the picture's level counter lives behind the offsets: d_off[total TUs of the band]
+    uint32_t *counter = f->d_off + tus_before(f, band_ctus, c.n_tus);
+    if (i == 0) UVGB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    return compact(t.n, t.d_coeff, nt * (size_t)nn, t.d_sig, f->d_off + tus_before(f, band_ctus, i), f->d_levels, counter, st);
   }
   return 0;
 }
@@ -711,14 +697,18 @@ static int stage_copies(Frame *f, int s, int ctu_begin, int ctu_end, int flags, 
     UVGB_TRY(cudaMemcpyAsync(t.h_cost, t.d_cost, nt * 4, cudaMemcpyDeviceToHost, sc));
     UVGB_TRY(cudaMemcpyAsync(t.h_sig, t.d_sig, (nt * nn + 31) / 32 * 4, cudaMemcpyDeviceToHost, sc));
     if (flags & UVG_B200_FRAME_DENSE_COEFF) UVGB_TRY(cudaMemcpyAsync(t.h_coeff, t.d_coeff, nt * nn * 2, cudaMemcpyDeviceToHost, sc));
+    const size_t before = tus_before(f, band_ctus, s - 1);
+    UVGB_TRY(cudaMemcpyAsync(f->h_off + before, f->d_off + before, nt * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+    if (s == c.n_tus) {                                      // the last size: the level counter is final
+      const size_t tu_total = tus_before(f, band_ctus, c.n_tus);
+      UVGB_TRY(cudaMemcpyAsync(f->h_off + tu_total, f->d_off + tu_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+      if (levels_pushed()) {
+        levels_push_kernel<<<kPushCtas, 256, 0, sc>>>(reinterpret_cast<const uint4 *>(f->d_levels), reinterpret_cast<uint4 *>(f->h_levels),
+                                                      f->d_off + tu_total);
+        UVGB_LAUNCH_CHECK();
+      }
+    }
     return 0;
-  }
-  const size_t tu_total = tus_before(f, band_ctus, c.n_tus);
-  UVGB_TRY(cudaMemcpyAsync(f->h_off, f->d_off, (tu_total + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
-  if (levels_pushed()) {
-    levels_push_kernel<<<kPushCtas, 256, 0, sc>>>(reinterpret_cast<const uint4 *>(f->d_levels), reinterpret_cast<uint4 *>(f->h_levels),
-                                                  f->d_off + tu_total);
-    UVGB_LAUNCH_CHECK();
   }
   return 0;
 }
