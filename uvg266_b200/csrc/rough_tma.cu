@@ -334,6 +334,209 @@ rough_tma_kernel(const __grid_constant__ CUtensorMap map_cand, const __grid_cons
   if (warp == 9) tmem_free(tmem, kTmemCols);
 }
 
+// ---- 8x8 blocks, BLOCK-ALIGNED tiles ---------------------------------------------------------------------------------
+// The flat layout above puts candidates 2r, 2r+1 of the launch into tile row r, so a row's two halves can belong to
+// different blocks and every half reads its own original (SAD) and its own H O H^T table row (SATD): 48 LDS.128 per row
+// and tile. Here a block's k candidates occupy RPB = ceil(k / 2) consecutive tile rows (BPT = 120 / RPB blocks per
+// tile), brought in by ONE 3-D TMA box per block: {128 bytes, RPB rows, 1 block} of the candidate array viewed as
+// [blocks][RPB][128] with a block stride of 64 k bytes. (A box with a 64-byte inner dimension does not pack two
+// candidates into a 128-byte row: under SWIZZLE_128B every box row starts a new 128-byte line.) For an odd k the box's
+// last half-row is the first candidate of the NEXT block - a dead slot, never scored; only the very last block of the
+// array has nothing behind it and is fetched as RPB - 1 rows plus its last candidate alone. Both halves of a row then
+// share the original and the table row: 28 LDS.128 per row and tile, and one table read serves both halves' TMEM
+// chunks. The price: that dead slot (4 % of the tile for k = 23). Measured on the bench's 8x8 level (k = 23, one 4K
+// picture): 0.0624 ms flat -> 0.0550 ms.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(s32addr(bar)) : "memory");
+}
+
+struct BaGeom { uint32_t n_blocks, k, rpb, bpt, recip; };   // recip = ceil(65536 / rpb): r / rpb = (r * recip) >> 16 for r < 128
+
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+rough_tma_ba_kernel(const __grid_constant__ CUtensorMap map_cand, const __grid_constant__ CUtensorMap map_cand_m1,
+                    const __grid_constant__ CUtensorMap map_c64, const __grid_constant__ CUtensorMap map_orig,
+                    uint32_t *__restrict__ out, BaGeom gm)
+{
+  constexpr int OR = 8, kCandRows = kRows - OR;
+  extern __shared__ __align__(1024) uint8_t dyn[];
+  uint8_t *const sB = dyn;
+  uint8_t *const sA = dyn + kSmemB;
+  int *const sTO = reinterpret_cast<int *>(dyn + kSmemB + kStages * kTileBytes);     // [group][16][kTOPitch]
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // B[n][kk], n = 64 s + c: the 64 pixels of half s of a row, sign (-1)^popcount(p & c), zero for the other half
+  for (int i = tid; i < 128 * 8; i += kThreads) {
+    const int n = i >> 3, ch = i & 7, s = n >> 6, c = n & 63;
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = 16 * ch + 4 * q + j, half = kk >> 6, p = kk & 63;
+        const uint32_t b = half != s ? 0u : ((__popc(p & c) & 1) ? 0xffu : 0x01u);
+        v |= b << (8 * j);
+      }
+      w[q] = v;
+    }
+    *reinterpret_cast<uint4 *>(sB + sw128(n, ch)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (tid == 0) {
+    if (s32addr(dyn) & 1023) __trap();
+    for (int i = 0; i < kStages; ++i) { bar_init(&full_bar[i], 1); bar_init(&empty_bar[i], 128); }
+    for (int i = 0; i < 2; ++i) { bar_init(&acc_full[i], 1); bar_init(&acc_empty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 9) tmem_alloc(&s_tmem, kTmemCols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  const uint32_t n_tiles = (gm.n_blocks + gm.bpt - 1) / gm.bpt;
+  const uint32_t tile0 = blockIdx.x, tstep = gridDim.x;
+  const uint32_t my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tstep - 1) / tstep : 0;
+
+  if (warp < 8) {
+    // ===== epilogue: thread = tile row; two groups of 128 threads take alternate tiles =====
+    const int r = tid & 127, grp = tid >> 7, wq = warp & 3;
+    const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16) + grp * kAccCols;
+    const uint32_t blk = ((uint32_t)r * gm.recip) >> 16, m0 = 2 * ((uint32_t)r - blk * gm.rpb);
+    const bool row_used = r < kCandRows && blk < gm.bpt;
+    for (uint32_t i = grp; i < my_tiles; i += 2) {
+      const uint32_t tile = tile0 + i * tstep, st = i % kStages;
+      const uint8_t *tileA = sA + st * kTileBytes;
+      int *const myTO = sTO + grp * (kMaxOrigRows * kTOPitch);
+      const uint32_t b_first = tile * gm.bpt, gblk = b_first + blk;
+      const uint32_t oidx = (b_first & 1) + blk;          // the tile's originals start at matrix row b_first >> 1
+      const int torow = (int)(oidx >> 1), tohalf = (int)(oidx & 1);
+      const bool blk_live = row_used && gblk < gm.n_blocks;
+      const bool live[2] = { blk_live && m0 < gm.k, blk_live && m0 + 1 < gm.k };
+      // ---- SAD first: it only needs the stage (the TMA's bytes), not the MMA -----------------------------------
+      bar_wait(&full_bar[st], (i / kStages) & 1);
+      unsigned sad[2];
+      {
+        const int orow = kCandRows + (row_used ? torow : 0);
+        unsigned sd[2][2] = { { 0, 0 }, { 0, 0 } };
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 o = *reinterpret_cast<const uint4 *>(tileA + sw128(orow, 4 * tohalf + c));
+          const uint4 p0 = *reinterpret_cast<const uint4 *>(tileA + sw128(r, c));
+          const uint4 p1 = *reinterpret_cast<const uint4 *>(tileA + sw128(r, 4 + c));
+          sd[0][0] = __vsadu4(p0.x, o.x) + sd[0][0]; sd[0][1] = __vsadu4(p0.y, o.y) + sd[0][1];
+          sd[0][0] = __vsadu4(p0.z, o.z) + sd[0][0]; sd[0][1] = __vsadu4(p0.w, o.w) + sd[0][1];
+          sd[1][0] = __vsadu4(p1.x, o.x) + sd[1][0]; sd[1][1] = __vsadu4(p1.y, o.y) + sd[1][1];
+          sd[1][0] = __vsadu4(p1.z, o.z) + sd[1][0]; sd[1][1] = __vsadu4(p1.w, o.w) + sd[1][1];
+        }
+        sad[0] = sd[0][0] + sd[0][1]; sad[1] = sd[1][0] + sd[1][1];
+      }
+      bar_wait(&acc_full[i & 1], (i >> 1) & 1);
+      fence_after_sync();
+      bar_arrive(&empty_bar[st]);                              // stage read by this thread and consumed by the MMA: the TMA may refill it
+      // ---- rows 120..127: H O H^T of the tile's blocks -> shared memory ------------------------------------------
+      if (wq == 3) {
+        int z[2][16];
+        tmem_ld16(tlane, z[0]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          tmem_ld_wait();
+          if (q < 7) tmem_ld16(tlane + 16 * (q + 1), z[(q + 1) & 1]);
+          if (r >= kCandRows) {
+            int4 *dst = reinterpret_cast<int4 *>(myTO + (r - kCandRows) * kTOPitch + (q >> 2) * kTOHalf + 16 * (q & 3));
+            const int(&v)[16] = z[q & 1];
+            dst[0] = make_int4(v[0], v[1], v[2], v[3]); dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+            dst[2] = make_int4(v[8], v[9], v[10], v[11]); dst[3] = make_int4(v[12], v[13], v[14], v[15]);
+          }
+        }
+      }
+      // chunk order: coefficients 16 j .. 16 j + 15 of half 0, then of half 1 (TMEM columns 16 j and 64 + 16 j): one table
+      // read serves both halves
+      int z[2][16];
+      tmem_ld16(tlane, z[0]);
+      asm volatile("bar.sync %0, 128;\n" :: "r"(1 + grp) : "memory");
+      const int *T = myTO + (row_used ? torow : 0) * kTOPitch + tohalf * kTOHalf;
+      unsigned ac[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } }, dc[2] = { 0, 0 };
+      int4 t0, t1, t2, t3;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = q >> 1, h = q & 1;
+        if (h == 0) {
+          t0 = *reinterpret_cast<const int4 *>(T + 16 * j); t1 = *reinterpret_cast<const int4 *>(T + 16 * j + 4);
+          t2 = *reinterpret_cast<const int4 *>(T + 16 * j + 8); t3 = *reinterpret_cast<const int4 *>(T + 16 * j + 12);
+        }
+        tmem_ld_wait();
+        if (q < 7) {
+          const int qn = q + 1;
+          tmem_ld16(tlane + 64 * (qn & 1) + 16 * (qn >> 1), z[qn & 1]);
+        } else {
+          fence_before_sync();
+          bar_arrive(&acc_empty[i & 1]);                      // accumulator drained: the next MMA into it may start
+        }
+        const int(&v)[16] = z[q & 1];
+        unsigned(&a)[4] = ac[h];
+        if (j == 0) dc[h] = (unsigned)abs(v[0] - t0.x);
+        a[0] = __sad(v[0], t0.x, a[0]); a[1] = __sad(v[1], t0.y, a[1]); a[2] = __sad(v[2], t0.z, a[2]); a[3] = __sad(v[3], t0.w, a[3]);
+        a[0] = __sad(v[4], t1.x, a[0]); a[1] = __sad(v[5], t1.y, a[1]); a[2] = __sad(v[6], t1.z, a[2]); a[3] = __sad(v[7], t1.w, a[3]);
+        a[0] = __sad(v[8], t2.x, a[0]); a[1] = __sad(v[9], t2.y, a[1]); a[2] = __sad(v[10], t2.z, a[2]); a[3] = __sad(v[11], t2.w, a[3]);
+        a[0] = __sad(v[12], t3.x, a[0]); a[1] = __sad(v[13], t3.y, a[1]); a[2] = __sad(v[14], t3.z, a[2]); a[3] = __sad(v[15], t3.w, a[3]);
+      }
+      const size_t oc = (size_t)gblk * gm.k + m0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const unsigned acc = (ac[h][0] + ac[h][1]) + (ac[h][2] + ac[h][3]);
+        const unsigned satd = (acc - dc[h] + (dc[h] >> 2) + 2) >> 2;             // picture-generic.c:341-345
+        if (live[h]) out[oc + h] = min(satd, 2 * sad[h]);
+      }
+    }
+  } else if (warp == 8) {
+    // ===== TMA producer (one lane): one 3-D box per block of the tile + the originals' rows =====
+    if (lane == 0) {
+      for (uint32_t i = 0; i < my_tiles; ++i) {
+        const uint32_t st = i % kStages, tile = tile0 + i * tstep;
+        if (i >= (uint32_t)kStages) bar_wait(&empty_bar[st], ((i / kStages) - 1) & 1);
+        const uint32_t b_first = tile * gm.bpt, nb = min(gm.bpt, gm.n_blocks - b_first);
+        const uint32_t dst = s32addr(sA + st * kTileBytes);
+        // bytes: full boxes of RPB rows; the array's last block with an odd k: RPB - 1 rows + one 64-byte candidate
+        const bool tail = (gm.k & 1) && b_first + nb == gm.n_blocks;
+        bar_expect_tx(&full_bar[st], nb * gm.rpb * kRowBytes - (tail ? 64u : 0u) + OR * kRowBytes);
+        for (uint32_t j = 0; j < nb; ++j) {
+          const uint32_t d = dst + j * gm.rpb * kRowBytes;
+          if (tail && j == nb - 1) {
+            tma_load_3d(d, &map_cand_m1, 0, 0, (int)(b_first + j), &full_bar[st]);
+            tma_load_2d(d + (gm.rpb - 1) * kRowBytes, &map_c64, 0, (int)((b_first + j) * gm.k + gm.k - 1), &full_bar[st]);
+          } else {
+            tma_load_3d(d, &map_cand, 0, 0, (int)(b_first + j), &full_bar[st]);
+          }
+        }
+        tma_load_2d(dst + kCandRows * kRowBytes, &map_orig, 0, (int)(b_first >> 1), &full_bar[st]);
+      }
+    }
+  } else if (lane == 0) {
+    // ===== MMA issuer (warp 9, one lane) =====
+    const uint64_t bd = smem_desc_sw128(s32addr(sB));
+    for (uint32_t i = 0; i < my_tiles; ++i) {
+      const uint32_t st = i % kStages;
+      bar_wait(&full_bar[st], (i / kStages) & 1);
+      if (i >= 2) bar_wait(&acc_empty[i & 1], ((i >> 1) - 1) & 1);
+      fence_after_sync();
+      const uint64_t ad = smem_desc_sw128(s32addr(sA + st * kTileBytes));
+      const uint32_t d = tmem + (i & 1) * kAccCols;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) umma_i8(d, ad + 2 * ks, bd + 2 * ks, kIdesc, ks > 0);   // 32 bytes of K per MMA
+      umma_commit(&acc_full[i & 1]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 9) tmem_free(tmem, kTmemCols);
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -364,6 +567,30 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t bo
   return r == CUDA_SUCCESS ? 0 : 1;
 }
 
+// candidates viewed as [blocks][rows][128 bytes] with a block stride of 64 k bytes; box = `box_rows` rows of one block
+static int make_map_cand3(CUtensorMap *m, const void *base, uint64_t n_blocks, uint32_t k, uint32_t rows, uint32_t box_rows)
+{
+  EncodeTiledFn f = encode_tiled();
+  if (!f) return 1;
+  const cuuint64_t dims[3] = { 128, rows, n_blocks }, strides[2] = { 128, 64ull * k };
+  const cuuint32_t box[3] = { 128, box_rows, 1 }, estr[3] = { 1, 1, 1 };
+  const CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+// single candidates: rows of 64 bytes, box = one row (lands at the start of a 128-byte line)
+static int make_map_c64(CUtensorMap *m, const void *base, uint64_t n_cands)
+{
+  EncodeTiledFn f = encode_tiled();
+  if (!f) return 1;
+  const cuuint64_t dims[2] = { 64, n_cands }, strides[1] = { 64 };
+  const cuuint32_t box[2] = { 64, 1 }, estr[2] = { 1, 1 };
+  const CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+
 std::atomic<uint64_t> g_rough_tma_launches{0};
 
 // Returns -1 when the layout does not qualify (caller falls through to the other kernels).
@@ -380,6 +607,32 @@ int launch_rough_tma(const Blocks &A, const Blocks &B, uint32_t *out, size_t n_i
   if (n == 8 && (n_blocks & 1)) return -1;                 // rows hold pairs of 8x8 blocks
   CUtensorMap mc, mo;
   const uint64_t cand_rows = n_items * (uint64_t)(n * n) / 128, orig_rows = n_blocks * (uint64_t)(n * n) / 128;
+  // 8x8 with 15..24 candidates per block: block-aligned tiles (UVG266_B200_ROUGH_TILES=flat keeps the flat layout)
+  static const bool flat_only = getenv("UVG266_B200_ROUGH_TILES") && !strcmp(getenv("UVG266_B200_ROUGH_TILES"), "flat");
+  if (n == 8 && k >= 15 && k <= 24 && !flat_only) {
+    BaGeom gm;
+    gm.n_blocks = (uint32_t)n_blocks; gm.k = (uint32_t)k; gm.rpb = (uint32_t)(k + 1) / 2; gm.bpt = 120 / gm.rpb;
+    gm.recip = (65536 + gm.rpb - 1) / gm.rpb;
+    CUtensorMap mc1, m64;
+    if (make_map_cand3(&mc, B.base, n_blocks, (uint32_t)k, gm.rpb, gm.rpb) || make_map_cand3(&mc1, B.base, n_blocks, (uint32_t)k, gm.rpb, gm.rpb - 1) ||
+        make_map_c64(&m64, B.base, n_items) || make_map(&mo, A.base, orig_rows, 8)) return -1;
+    size_t tiles = (n_blocks + gm.bpt - 1) / gm.bpt;
+    const size_t cap2 = (size_t)sm_count() * kCtasPerSm;
+    if (tiles > cap2) tiles = cap2;
+    static std::once_flag once_ba;
+    static cudaError_t err_ba = cudaSuccess;
+    std::call_once(once_ba, [] {
+      err_ba = cudaFuncSetAttribute(reinterpret_cast<const void *>(rough_tma_ba_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+      if (err_ba == cudaSuccess)
+        err_ba = cudaFuncSetAttribute(reinterpret_cast<const void *>(rough_tma_ba_kernel), cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared);
+    });
+    UVGB_TRY(err_ba);
+    rough_tma_ba_kernel<<<(unsigned)tiles, kThreads, kSmemTotal, st>>>(mc, mc1, m64, mo, out, gm);
+    UVGB_LAUNCH_CHECK();
+    g_rough_tma_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
   if (make_map(&mc, B.base, cand_rows, (uint32_t)crows) || make_map(&mo, A.base, orig_rows, (uint32_t)orows)) return -1;
   FastDivK kd;
   kd.k = (uint32_t)k;
