@@ -45,6 +45,8 @@ def run(n, k, nb, check_all):
             assert got[b, c] == e, (n, k, nb, b, c, int(got[b, c]), e)
     return used, got, (d_o, d_c, A, B)
 for (n, k, nb) in ((8, 23, 2), (8, 23, 520), (8, 24, 10), (8, 10, 64), (8, 67, 38), (8, 31, 1002),
+                   (8, 15, 46), (8, 17, 26), (8, 20, 122), (8, 22, 14), (8, 21, 1000),      # block-aligned tiles: every rows-per-block count, odd / even k, partial last tiles
+
                    (16, 24, 1), (16, 24, 131), (16, 10, 57), (16, 67, 9), (16, 23, 300)):
     used, _, _ = run(n, k, nb, nb <= 64)
     assert used == 1, ("the tcgen05 + TMA kernel did not take", n, k, nb)
@@ -62,12 +64,16 @@ print("CHILD_OK")
 '''
 
 
-@pytest.mark.parametrize("mode", ["tc5", None])
+@pytest.mark.parametrize("mode", ["tc5", None, "flat"])
 def test_rough_tma_kernel_vs_oracle(tmp_path, mode):
-    """mode None: no UVG266_B200_ROUGH at all - the kernel must be what the library picks by default."""
+    """mode None: no UVG266_B200_ROUGH at all - the kernel must be what the library picks by default; "flat": the 8x8
+    levels with 15..24 candidates stay on the flat tile layout instead of the block-aligned one."""
     env = dict(os.environ)
     env.pop("UVG266_B200_ROUGH", None)
-    if mode:
+    env.pop("UVG266_B200_ROUGH_TILES", None)
+    if mode == "flat":
+        env["UVG266_B200_ROUGH_TILES"] = "flat"
+    elif mode:
         env["UVG266_B200_ROUGH"] = mode
     code = CHILD % {"here": HERE, "tmp": str(tmp_path)}
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
