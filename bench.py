@@ -411,7 +411,7 @@ def gpu_arm(args):
                         O=U.Blocks.dense(rec.data_ptr(), n, n), bytes=nt * (5 * n * n + 9)))
     step_bytes = sum(x["bytes"] for x in rough) + sum(x["bytes"] for x in tus)
 
-    names = ["rough_cost 8x8 k=23 (rough_tma_kernel<8>: tcgen05 + tensor-map TMA)", "rough_cost 16x16 k=24 (rough_tma_kernel<16>: tcgen05 + tensor-map TMA)",
+    names = ["rough_cost 8x8 k=23 (rough_tma_ba_kernel: tcgen05 + tensor-map TMA, block-aligned tiles)", "rough_cost 16x16 k=24 (rough_tma_kernel<16>: tcgen05 + tensor-map TMA)",
              "quantize_residual 4x4 (fused_small_kernel<4>)", "quantize_residual 8x8 (fused_imma8_kernel)",
              "quantize_residual 16x16 (fused_imma_kernel<16>)", "quantize_residual 32x32 (fused_imma_kernel<32>)"]
     kbytes = [x["bytes"] for x in rough] + [x["bytes"] for x in tus]
