@@ -185,6 +185,57 @@ def test_frame_other_level_sets():
     compare(g, run_ref(flat, LEVELS, TUS, 2, 27), LEVELS, TUS)
 
 
+def test_frames_in_flight_from_two_threads_repeat_their_results():
+    """Two frame objects driven from two host threads (the bench's e2e driver, an encoder's frame-level parallelism): the
+    library orders their kernels in one compute stream and replays per-stage CUDA graphs from the third pass on. Every
+    pass of either thread must give what a pass of that picture gives on its own - checked on the expanded
+    coefficients, the per-TU results and the candidate lists (the order of the TUs inside `levels` is unspecified)."""
+    import threading
+    L = U.lib()
+    w, h = 320, 192
+    planes = [synth(w, h, 21), synth(w, h, 22)]
+    alone = [run_gpu(p, LEVELS, TUS, 2, 27, flags=0) for p in planes]
+    cfg = U.FrameCfg.make(w, h, LEVELS, TUS, 2, U.QuantCfg.make(27, 8, 1, 0, 0), WEIGHTS)
+    frames = [L.uvg_b200_frame_create(C.byref(cfg)) for _ in planes]
+    assert all(frames)
+    errors = []
+
+    def drive(i):
+        try:
+            res = U.FrameResult()
+            for it in range(6):
+                U.check(L.uvg_b200_frame_submit(frames[i], planes[i].ctypes.data, w, 0, 0, 0))
+                U.check(L.uvg_b200_frame_wait(frames[i], C.byref(res)))
+                n_ctu = res.ctu_end - res.ctu_begin
+                assert int(res.n_levels) == alone[i]["n_levels"], (i, it)
+                lv = U.np_view(res.levels, np.int16, int(res.n_levels)).copy()
+                for k, (n, modes) in enumerate(LEVELS):
+                    nb = n_ctu * (64 // n) ** 2
+                    assert (U.np_view(res.rough_best[k], np.uint8, nb * 2) == alone[i]["best%d" % k]).all(), (i, it, k)
+                    assert (U.np_view(res.rough_best_cost[k], np.uint32, nb * 2) == alone[i]["bestcost%d" % k]).all(), (i, it, k)
+                for k, (n, cnt) in enumerate(TUS):
+                    nt = n_ctu * cnt
+                    for key, field, dt in (("mode", res.tu_mode, np.uint8), ("has", res.tu_has_coeffs, np.uint8),
+                                           ("ssd", res.tu_ssd, np.uint32), ("tcost", res.tu_cost, np.uint32)):
+                        assert (U.np_view(field[k], dt, nt) == alone[i]["%s%d" % (key, k)]).all(), (i, it, key, k)
+                    sig = U.np_view(res.tu_sig[k], np.uint32, (nt * n * n + 31) // 32).copy()
+                    off = U.np_view(res.tu_level_off[k], np.uint32, nt).copy()
+                    dense = np.zeros(nt * n * n, np.int16)
+                    L.uvg_b200_frame_expand_coeffs(sig.ctypes.data, off.ctypes.data, lv.ctypes.data, n * n, nt, dense.ctypes.data)
+                    assert (dense == alone[i]["coeff%d" % k]).all(), (i, it, k)
+        except Exception as exc:                                  # surfaced in the main thread
+            errors.append(exc)
+
+    th = [threading.Thread(target=drive, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for f in frames:
+        L.uvg_b200_frame_destroy(f)
+    assert not errors, errors[0]
+
+
 def test_frame_samples_against_oracle():
     """The same pass against the oracle restatement (no reference library needed) on sampled blocks."""
     O = load_oracle(8)
