@@ -754,21 +754,30 @@ def strong_frame(torch, U, L, rank, world, args, barrier, dist, dev):
     """Strong scaling of the same end-to-end work: ONE 4K picture per step, split into `world` bands of CTU rows (the
     partition of uvg_b200_band_rows), every rank pushing its own band through the frame pipeline from host memory
     (H2D of the band's rows + halo, kernels, D2H of the band's results). No collective: all-intra. ms per picture =
-    max over ranks."""
+    max over ranks. Inside a rank the band is cut once more into `--strong-subbands` pieces on as many frame objects,
+    submitted back to back: the second piece's rows arrive while the first one's kernels run and the first one's results
+    leave under the second one's kernels - the double-buffering of one picture that a single pass cannot have."""
     H = CTU_ROWS * CTU
     cfg = U.FrameCfg.make(FRAME_W, H, FRAME_LEVELS, TUS, FRAME_NBEST, U.QuantCfg.make(QP, 8, 1, 0, 0), COST_WEIGHTS)
-    f = L.uvg_b200_frame_create(C.byref(cfg))
-    if not f:
-        raise RuntimeError("uvg_b200_frame_create: " + L.uvg_b200_last_error().decode())
     hp = torch.empty((H, FRAME_W), dtype=torch.uint8, pin_memory=True)
     hp.copy_(torch.from_numpy(synth_plane_rows([(0, r) for r in range(CTU_ROWS)])))
     lo, hi = C.c_int(), C.c_int()
     L.uvg_b200_band_rows(rank, world, CTU_ROWS, C.byref(lo), C.byref(hi))
+    pieces = max(1, min(args.strong_subbands, (hi.value - lo.value) // 4))      # at least 4 CTU rows per piece
+    cuts = [lo.value + (hi.value - lo.value) * i // pieces for i in range(pieces + 1)]
+    frames = []
+    for _ in range(pieces):
+        f = L.uvg_b200_frame_create(C.byref(cfg))
+        if not f:
+            raise RuntimeError("uvg_b200_frame_create: " + L.uvg_b200_last_error().decode())
+        frames.append(f)
     res = U.FrameResult()
 
     def one():
-        U.check(L.uvg_b200_frame_submit(f, hp.data_ptr(), FRAME_W, lo.value, hi.value, 0))
-        U.check(L.uvg_b200_frame_wait(f, C.byref(res)))
+        for i, f in enumerate(frames):
+            U.check(L.uvg_b200_frame_submit(f, hp.data_ptr(), FRAME_W, cuts[i], cuts[i + 1], 0))
+        for f in frames:
+            U.check(L.uvg_b200_frame_wait(f, C.byref(res)))
     for _ in range(3):
         one()
     k = max(3, min(args.steps, args.e2e_steps))
@@ -783,9 +792,10 @@ def strong_frame(torch, U, L, rank, world, args, barrier, dist, dev):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     secs = float(t.item())
-    L.uvg_b200_frame_destroy(f)
+    for f in frames:
+        L.uvg_b200_frame_destroy(f)
     return {"ms_per_picture": 1e3 * secs / k, "value": CTU_COLS * CTU_ROWS * k / secs, "unit": "CTU/s", "bands": world,
-            "ctu_rows_of_rank0": [lo.value, hi.value] if rank == 0 else None, "steps": k,
+            "subbands_per_rank": pieces, "ctu_rows_of_rank0": [lo.value, hi.value] if rank == 0 else None, "steps": k,
             "what": "one 3840x2160 picture per step split into CTU-row bands across the GPUs, frame_pass end to end from host memory"}
 
 
@@ -968,6 +978,7 @@ def main():
     ap.add_argument("--ref-frame-rows", type=int, default=CTU_ROWS, help="CTU rows per pass of the reference frame pass")
     ap.add_argument("--e2e-inflight", type=int, default=2, help="frame objects in flight in the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--strong-subbands", type=int, default=4, help="pieces a rank cuts its band into (double-buffering inside one picture)")
     ap.add_argument("--e2e-frame-steps", type=int, default=60, help="pictures in the timed region of the frame-pipeline e2e (at most 2 x --steps)")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the *_host calls")
     ap.add_argument("--e2e-order", default="interleaved", choices=["interleaved", "sequential"],
