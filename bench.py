@@ -763,7 +763,8 @@ def strong_frame(torch, U, L, rank, world, args, barrier, dist, dev):
     hp.copy_(torch.from_numpy(synth_plane_rows([(0, r) for r in range(CTU_ROWS)])))
     lo, hi = C.c_int(), C.c_int()
     L.uvg_b200_band_rows(rank, world, CTU_ROWS, C.byref(lo), C.byref(hi))
-    pieces = max(1, min(args.strong_subbands, (hi.value - lo.value) // 4))      # at least 4 CTU rows per piece
+    # at least 8 CTU rows per piece: measured, 4-row pieces at N=2 cost more in small kernels than the overlap gives back
+    pieces = max(1, min(args.strong_subbands, (hi.value - lo.value) // 8))
     cuts = [lo.value + (hi.value - lo.value) * i // pieces for i in range(pieces + 1)]
     frames = []
     for _ in range(pieces):
