@@ -418,7 +418,9 @@ struct Frame {
   uvg_b200_frame_cfg cfg;
   int W = 0, H = 0, pitch = 0, ctu_cols = 0, ctu_rows = 0, n_ctu = 0;
   cudaStream_t s_in = nullptr, s_copy = nullptr;         // source rows in, results out; the kernels go into the lane
+  cudaStream_t s_side[kMaxLv - 1] = {};                  // side branches of a stage (independent kernels run side by side)
   cudaEvent_t ev_stage[kMaxStages] = {}, ev_in = nullptr, ev_done = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxLv - 1] = {};
   uint8_t *d_plane = nullptr;
   Level lv[kMaxLv];
   TuSize tu[kMaxLv];
@@ -456,7 +458,9 @@ static void frame_release(Frame *f)
   for (Frame::PassGraph &g : f->graphs)
     for (int s = 0; s < kMaxStages; ++s) { if (g.kernels[s]) cudaGraphExecDestroy(g.kernels[s]); if (g.copies[s]) cudaGraphExecDestroy(g.copies[s]); }
   for (cudaEvent_t e : f->ev_stage) if (e) cudaEventDestroy(e);
-  for (cudaEvent_t e : { f->ev_in, f->ev_done, f->ev_t0, f->ev_t1 }) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : { f->ev_in, f->ev_done, f->ev_t0, f->ev_t1, f->ev_fork }) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : f->ev_join) if (e) cudaEventDestroy(e);
+  for (cudaStream_t q : f->s_side) if (q) cudaStreamDestroy(q);
   if (f->s_in) cudaStreamDestroy(f->s_in);
   if (f->s_copy) cudaStreamDestroy(f->s_copy);
   cudaGetLastError();
@@ -472,6 +476,9 @@ static int frame_build(Frame *f, const uvg_b200_frame_cfg *c)
   f->ctu_cols = (c->width + kCtu - 1) / kCtu; f->ctu_rows = (c->height + kCtu - 1) / kCtu;
   f->n_ctu = f->ctu_cols * f->ctu_rows;
   UVGB_TRY(cudaStreamCreateWithFlags(&f->s_in, cudaStreamNonBlocking));
+  for (cudaStream_t &q : f->s_side) UVGB_TRY(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+  UVGB_TRY(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+  for (cudaEvent_t &e : f->ev_join) UVGB_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   UVGB_TRY(cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking));
   for (cudaEvent_t &e : f->ev_stage) UVGB_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   UVGB_TRY(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
@@ -628,14 +635,25 @@ static int stage_kernels(Frame *f, int s, int ctu_begin, int ctu_end, cudaStream
 {
   const uvg_b200_frame_cfg &c = f->cfg;
   const int W = f->W, H = f->H, band_ctus = ctu_end - ctu_begin;
-  if (s == 0) {                                            // ---- rough search, every level
+  if (s == 0) {
+    // ---- rough search: the levels are independent of each other, so level i > 0 runs on a side branch (fork / join by
+    // events; inside a capture these become parallel branches of the stage's graph): one level's last, partly filled wave
+    // of CTAs is topped up by the other level's instead of leaving SMs idle
+    static const bool serial = getenv("UVG266_B200_FRAME_SIDE") && !strcmp(getenv("UVG266_B200_FRAME_SIDE"), "0");
+    if (c.n_levels > 1 && !serial) UVGB_TRY(cudaEventRecord(f->ev_fork, st));
     for (int i = 0; i < c.n_levels; ++i) {
       Level &l = f->lv[i];
       const size_t nb = (size_t)band_ctus * l.ppc;
+      cudaStream_t q = (i == 0 || serial) ? st : f->s_side[i - 1];
+      if (q != st) UVGB_TRY(cudaStreamWaitEvent(q, f->ev_fork, 0));
       const PlaneSrc ps{ f->d_plane, f->pitch, W, H, f->ctu_cols, ctu_begin };
-      if (launch_intra_rough_plane(l.n, ps, l.modes, l.k, l.d_cost, nb, st)) return 1;
-      frame_topk_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(l.d_cost, nb, l.k, c.n_best, l.d_modes, l.d_best, l.d_best_cost);
+      if (launch_intra_rough_plane(l.n, ps, l.modes, l.k, l.d_cost, nb, q)) return 1;
+      frame_topk_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, q>>>(l.d_cost, nb, l.k, c.n_best, l.d_modes, l.d_best, l.d_best_cost);
       UVGB_LAUNCH_CHECK();
+      if (q != st) {
+        UVGB_TRY(cudaEventRecord(f->ev_join[i - 1], q));
+        UVGB_TRY(cudaStreamWaitEvent(st, f->ev_join[i - 1], 0));
+      }
     }
     return 0;
   }
