@@ -977,7 +977,7 @@ def main():
     ap.add_argument("--ref-ctus", type=int, default=2040, help="CTUs per step of the reference arm")
     ap.add_argument("--cpu-ctus", type=int, default=2040, help="CTUs of the cpu_baseline sample")
     ap.add_argument("--ref-frame-rows", type=int, default=CTU_ROWS, help="CTU rows per pass of the reference frame pass")
-    ap.add_argument("--e2e-inflight", type=int, default=2, help="frame objects in flight in the e2e leg")
+    ap.add_argument("--e2e-inflight", type=int, default=3, help="frame objects in flight in the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--strong-subbands", type=int, default=4, help="pieces a rank cuts its band into (double-buffering inside one picture)")
     ap.add_argument("--e2e-frame-steps", type=int, default=60, help="pictures in the timed region of the frame-pipeline e2e (at most 2 x --steps)")
