@@ -65,3 +65,37 @@ def test_product_does_not_link_the_oracle():
     assert "oracle" not in out and "uvg266ref" not in out
     syms = subprocess.check_output(["nm", "-D", U.LIB_PATH]).decode()
     assert "orc_" not in syms and "refh_" not in syms
+
+
+def test_ctypes_mirror_has_the_headers_struct_layout(tmp_path):
+    """tests and bench.py reach the C ABI through the ctypes mirror in uvg266_b200/__init__.py: every public struct must
+    have the size and field offsets a C compiler gives the header's."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    import uvg266_b200 as U
+    if not shutil.which("gcc"):
+        pytest.skip("no C compiler")
+    pairs = [("uvg_b200_blocks", U.Blocks), ("uvg_b200_quant_cfg", U.QuantCfg), ("uvg_b200_frame_level", U.FrameLevel),
+             ("uvg_b200_frame_tu", U.FrameTu), ("uvg_b200_frame_cfg", U.FrameCfg), ("uvg_b200_frame_result", U.FrameResult),
+             ("uvg_b200_frame_device", U.FrameDevice)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "uvg266_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        a, b, c = ln.split()
+        got[(a, b)] = int(c)
+    for cname, cls in pairs:
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
