@@ -151,8 +151,11 @@ fused_small_kernel(FusedArgs a, size_t n_tus, QParams q, SmallTr<N> tr)
     const unsigned ul = ((unsigned)abs(c[i]) * (unsigned)q.coeff_default + (unsigned)q.add) >> q.q_bits;
     qc[i] = c[i] < 0 ? -(int)ul : (int)ul;
     nz |= ul;
-    cost += __byte_perm(wlo, whi, min(ul, 3u) * 0x22u + 0x10u) & 0xffffu;   // weight of min(|level|, 3), packed Q8.8 table
+    // weight of min(|level|, 3) from the packed Q8.8 table; bytes 2, 3 of the PRMT result are copies of the table's byte
+    // 0 - a constant, taken off once after the loop
+    cost += __byte_perm(wlo, whi, min(ul, 3u) * 0x22u + 0x10u);
   }
+  cost -= ((wlo & 0xffu) * 0x01010000u) * (unsigned)(N * N);
   // coefficients out: N*N int16 contiguous per TU
   {
     uint32_t *dst = reinterpret_cast<uint32_t *>(a.coeff_out + tu * (size_t)(N * N));
@@ -161,7 +164,7 @@ fused_small_kernel(FusedArgs a, size_t n_tus, QParams q, SmallTr<N> tr)
       uint32_t w[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        w[k] = ((uint32_t)qc[8 * i + 2 * k] & 0xffffu) | ((uint32_t)qc[8 * i + 2 * k + 1] << 16);
+        w[k] = __byte_perm((uint32_t)qc[8 * i + 2 * k], (uint32_t)qc[8 * i + 2 * k + 1], 0x5410);
       reinterpret_cast<uint4 *>(dst)[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
@@ -205,21 +208,33 @@ fused_small_kernel(FusedArgs a, size_t n_tus, QParams q, SmallTr<N> tr)
     constexpr int PW = BlockWords<Pix, N>::PW;
 #pragma unroll
     for (int wi = 0; wi < BlockWords<Pix, N>::NWORDS; ++wi) {
-      uint32_t x = 0;
+      if constexpr (sizeof(Pix) == 1) {                      // 8-bit: clip to 0..255 and pack in two saturating packs
+        int t[4];
 #pragma unroll
-      for (int j = 0; j < PW; ++j) {
-        const int i = wi * PW + j;
-        x |= (uint32_t)clip3(0, q.pixel_max, (int)(short)(r[i] + predb.at(i))) << (j * (32 / PW));
+        for (int j = 0; j < 4; ++j) t[j] = (int)(short)(r[wi * 4 + j] + predb.at(wi * 4 + j));
+        recb.w[wi] = pack4_sat_u8(t[0], t[1], t[2], t[3]);
+      } else {
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+          const int i = wi * PW + j;
+          x |= (uint32_t)clip3(0, q.pixel_max, (int)(short)(r[i] + predb.at(i))) << (j * (32 / PW));
+        }
+        recb.w[wi] = x;
       }
-      recb.w[wi] = x;
     }
   }
   if (recon || !a.rec_is_pred) store_block<Pix, N>(prec, a.rec.stride, recb);
   a.has_coeffs[tu] = nz ? 1 : 0;
   if (a.ssd) {
     unsigned ssd = 0;
+    if constexpr (sizeof(Pix) == 1) {
 #pragma unroll
-    for (int i = 0; i < N * N; ++i) { const int df = refb.at(i) - recb.at(i); ssd += (unsigned)(df * df); }
+      for (int wi = 0; wi < BlockWords<Pix, N>::NWORDS; ++wi) { const uint32_t d4 = __vabsdiffu4(refb.w[wi], recb.w[wi]); ssd = __dp4a(d4, d4, ssd); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) { const int df = refb.at(i) - recb.at(i); ssd += (unsigned)(df * df); }
+    }
     a.ssd[tu] = (uint32_t)((int32_t)ssd >> q.ssd_shift);
   }
   if (a.cost) a.cost[tu] = (cost + 128u) >> 8;
