@@ -214,6 +214,7 @@ intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restr
         __syncwarp();
       }
       const int lim = min(3 << mp.scale, N);
+      const PdpcTab tab = mp.pdpc ? pdpc_tab(mp, sx, lim) : PdpcTab{};
 #pragma unroll 1
       for (int sy = 0; sy < NS; ++sy) {
         uint32_t wo[8][2], wc[8][2];
@@ -222,7 +223,7 @@ intra_rough_kernel(Blocks A, const uint8_t *__restrict__ refs, uint32_t *__restr
           const int r = sy * 8 + rr;
           const uint2 o = *reinterpret_cast<const uint2 *>(orig + r * N);
           wo[rr][0] = o.x; wo[rr][1] = o.y;
-          angular_row8(mp, mainr, side, ext0, r, sx, lim, wc[rr][0], wc[rr][1]);
+          angular_row8<true>(mp, mainr, side, ext0, r, sx, lim, wc[rr][0], wc[rr][1], tab);
         }
         unsigned s1 = 0;
         satd += satd8_words_u8<true>(wo, wc, s1);

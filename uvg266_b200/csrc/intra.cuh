@@ -164,9 +164,30 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
 // a window that starts left of index 0 ends at most 11 bytes right of it, so a row's four words come from ONE base.
 constexpr int kExtMirror = 12;
 
-// One row (8 pixels: work-row r, work-columns 8*sx..8*sx+7) of an angular prediction.
+// PDPC of an angular mode does not depend on the row: per column cc the side-reference offset
+// ((256 + (cc + 1) * inv_angle) >> 9) + 1 and the weight 32 >> ((2 cc) >> scale). A caller that generates many rows of
+// one (mode, strip) computes them once (pdpc_tab) - one byte each, zero weight beyond the PDPC range - and the row
+// generator picks them with one PRMT instead of recomputing five instructions per pixel.
+struct PdpcTab { uint32_t off[2], w[2]; };
+__device__ __forceinline__ PdpcTab pdpc_tab(const ModeParam &mp, int sx, int lim)
+{
+  PdpcTab t = { { 0, 0 }, { 0, 0 } };
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int cc = 8 * sx + c;
+    if (cc < lim) {
+      t.off[c >> 2] |= (uint32_t)(((256 + (cc + 1) * mp.inv_angle) >> 9) + 1) << (8 * (c & 3));
+      t.w[c >> 2] |= (uint32_t)(32 >> ((2 * cc) >> mp.scale)) << (8 * (c & 3));
+    }
+  }
+  return t;
+}
+
+// One row (8 pixels: work-row r, work-columns 8*sx..8*sx+7) of an angular prediction. TAB: PDPC offsets / weights from `tab`.
+template <bool TAB = false>
 __device__ __forceinline__ void angular_row8(const ModeParam &mp, const uint8_t *mainr, const uint8_t *side,
-                                             const uint8_t *ext0, int r, int sx, int lim, uint32_t &lo, uint32_t &hi)
+                                             const uint8_t *ext0, int r, int sx, int lim, uint32_t &lo, uint32_t &hi,
+                                             const PdpcTab &tab = PdpcTab{})
 {
   const int dpos = (r + 1) * mp.sample_disp, di = dpos >> 5, fr = dpos & 31;
   int cw;
@@ -198,13 +219,22 @@ __device__ __forceinline__ void angular_row8(const ModeParam &mp, const uint8_t 
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int cc = 8 * sx + c;
-      if (cc < lim) v[c] = min(max(v[c] + (((32 >> ((2 * cc) >> mp.scale)) * d + 32) >> 6), 0), 255);
+      if (TAB) {                                                           // weight 0 beyond the range: (0 * d + 32) >> 6 = 0
+        const int w = (int)__byte_perm(tab.w[c >> 2], 0, 0x4440 + (c & 3));
+        v[c] = min(max(v[c] + ((w * d + 32) >> 6), 0), 255);
+      } else if (cc < lim) {
+        v[c] = min(max(v[c] + (((32 >> ((2 * cc) >> mp.scale)) * d + 32) >> 6), 0), 255);
+      }
     }
   } else {                                                                 // :234-251
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int cc = 8 * sx + c;
-      if (cc < lim) {
+      if (TAB) {
+        const int w = (int)__byte_perm(tab.w[c >> 2], 0, 0x4440 + (c & 3));
+        const int l = side[r + (int)__byte_perm(tab.off[c >> 2], 0, 0x4440 + (c & 3))];   // offset 0 (any sample) where w = 0
+        v[c] = (v[c] + ((w * (l - v[c]) + 32) >> 6)) & 255;
+      } else if (cc < lim) {
         const int l = side[r + ((256 + (cc + 1) * mp.inv_angle) >> 9) + 1];
         v[c] = (v[c] + (((32 >> ((2 * cc) >> mp.scale)) * (l - v[c]) + 32) >> 6)) & 255;
       }
