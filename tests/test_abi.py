@@ -99,3 +99,35 @@ def test_ctypes_mirror_has_the_headers_struct_layout(tmp_path):
         assert got[(cname, "size")] == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_expand_coeffs_accepts_tus_in_any_order():
+    """uvg_b200_frame_expand_coeffs is host code (no GPU needed): the frame pipeline guarantees that a TU's levels are
+    contiguous and in index order from tu_level_off[t], NOT that the TUs follow each other in index order - the helper
+    must rebuild the dense array from a shuffled layout."""
+    import numpy as np
+    L = U.lib()
+    rng = np.random.default_rng(9)
+    n_tus, cpt = 37, 64
+    dense = np.where(rng.random(n_tus * cpt) < 0.2, rng.integers(-300, 301, n_tus * cpt), 0).astype(np.int16)
+    dense[5 * cpt: 6 * cpt] = 0                                    # a TU without coefficients
+    sig = np.zeros((n_tus * cpt + 31) // 32, np.uint32)
+    for g in np.nonzero(dense)[0]:
+        sig[g >> 5] |= np.uint32(1) << np.uint32(g & 31)
+    order = rng.permutation(n_tus)
+    off = np.zeros(n_tus, np.uint32)
+    levels = []
+    pos = 3                                                         # and not starting at zero either
+    levels.extend([7, 7, 7])
+    for t in order:
+        nz = dense[t * cpt: (t + 1) * cpt]
+        nz = nz[nz != 0]
+        off[t] = pos
+        levels.extend(int(v) for v in nz)
+        pos += len(nz)
+    levels = np.array(levels, np.int16)
+    out = np.full(n_tus * cpt, 99, np.int16)
+    L.uvg_b200_frame_expand_coeffs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]
+    L.uvg_b200_frame_expand_coeffs.restype = None
+    L.uvg_b200_frame_expand_coeffs(sig.ctypes.data, off.ctypes.data, levels.ctypes.data, cpt, n_tus, out.ctypes.data)
+    assert (out == dense).all()
